@@ -1,0 +1,136 @@
+/*
+ * b200nerf.h -- C ABI of libb200nerf.so: the B200 (sm_100a) render_rays hot path of nerf-sampling.
+ *
+ * The reference (MarcinKadziolka/nerf-sampling) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary a maintainer binds is therefore "one entry point per reference operator", called with raw device
+ * pointers (tensor.data_ptr()), element counts and a cudaStream_t.  Each declaration cites the reference
+ * function (path relative to nerf_sampling/) whose ATen op sequence it replaces.  See INTEGRATION.md for the
+ * ctypes stubs the reference side would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; b200nerf_last_error() gives the message
+ *   - no allocation, no host synchronisation inside device entry points; all work is enqueued on `stream`
+ *   - device pointers unless the parameter name starts with `h_`
+ *   - fp32 tensors, row-major, contiguous
+ */
+#ifndef B200NERF_H
+#define B200NERF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NERF_VERSION 100
+
+/* precision of the tensor-core MLPs */
+#define B200NERF_PREC_SPLIT 1 /* bf16 hi+lo operands, 3 MMAs / K16 block, ~16 mantissa bits (parity mode) */
+#define B200NERF_PREC_BF16 0  /* plain bf16 operands, 1 MMA / K16 block (PSNR-level parity only)           */
+
+/* sample placement modes (nerf_pytorch/utils.py:220-244) */
+#define B200NERF_PLACE_DEPTH_ONLY 0
+#define B200NERF_PLACE_UNIFORM 1
+#define B200NERF_PLACE_GAUSSIAN 2
+
+int b200nerf_version(void);
+const char* b200nerf_last_error(void);
+
+/* ---- weight packing (host side, run once per checkpoint load / optimizer step) ------------------------- */
+
+/* NeRF(D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True)
+ * (nerf_pytorch/run_nerf_helpers.py:67-107).  `h_tensors` = 24 host fp32 pointers in this order:
+ * pts_linears.0.weight, pts_linears.0.bias, ..., pts_linears.7.{weight,bias}, views_linears.0.{weight,bias},
+ * feature_linear.{weight,bias}, alpha_linear.{weight,bias}, rgb_linear.{weight,bias}.
+ * Produces the weight-slab stream (`h_wpack`, b200nerf_nerf_wpack_bytes(prec) bytes) and the fp32 bias/head
+ * block (`h_aux`, b200nerf_nerf_aux_floats() floats); copy both to the device. */
+size_t b200nerf_nerf_wpack_bytes(int prec);
+size_t b200nerf_nerf_aux_floats(void);
+int b200nerf_nerf_pack(const float* const* h_tensors, int prec, void* h_wpack, float* h_aux);
+
+/* DepthNet (depth_nets/depth_net.py:10-169) in inference form.  Its three branches apply no activation
+ * (depth_net.py:140,148,156 are no-ops), so branches + cat_layers[0] are one affine map of the encodings.
+ * The host folds them (fp64) into `h_w0` [256,256] / `h_b0` [256] over the kernel's input layout
+ *   cols   0.. 62 enc(o) | 64..126 enc(d) | 128..190 enc(hit_near) | 192..254 enc(hit_far)   (63,127,191,255 = 0)
+ * `h_hidden` = n_hidden pairs (weight [256,256], bias [256]) of the remaining cat_layers (LeakyReLU 0.01),
+ * `h_head_w` [256] / `h_head_b` [1] = to_depth.  Narrower layers are zero-padded to 256 by the caller. */
+size_t b200nerf_depthnet_wpack_bytes(int n_hidden, int prec);
+size_t b200nerf_depthnet_aux_floats(int n_hidden);
+int b200nerf_depthnet_pack(const float* h_w0, const float* h_b0, const float* const* h_hidden, int n_hidden,
+                           const float* h_head_w, const float* h_head_b, int prec, void* h_wpack, float* h_aux);
+
+/* ---- operators ------------------------------------------------------------------------------------------ */
+
+/* get_rays + view-direction normalisation for one pinhole view
+ * (run_nerf_helpers.py:187-202, nerf_utils.py:156-188).  h_c2w = 12 floats (3x4 row-major).
+ * Outputs [H*W,3] each; any may be NULL. */
+int b200nerf_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* h_c2w, float* rays_o,
+                      float* rays_d, float* viewdirs, void* stream);
+
+/* viewdirs = rays_d / ||rays_d||  (nerf_utils.py:173) */
+int b200nerf_normalize_dirs(const float* rays_d, int n_rays, float* viewdirs, void* stream);
+
+/* DepthNet.forward: one depth in [near, far] per ray (depth_nets/depth_net.py:117-169).  out_z [n_rays]. */
+int b200nerf_depthnet_fwd(const void* wpack, const float* aux, int n_hidden, int prec, const float* rays_o,
+                          const float* rays_d, int n_rays, float radius, float near_, float far_, float* out_z,
+                          void* stream);
+
+/* sample_points_around_mean (nerf_pytorch/utils.py:220-244) without materialising pts.
+ * mean [n_rays]; uniform: `offsets` = the S-1 grid values linspace(-std, std, S-1) (shared by all rays) and the
+ * result is clipped to [clip_lo, clip_hi]; gaussian: `offsets` = [n_rays, S-1] already scaled noise (std*randn),
+ * no clip; depth_only: S must be 1.  out_z [n_rays, S], ascending per ray. */
+int b200nerf_place_samples(const float* mean, const float* offsets, int n_rays, int S, int mode, float clip_lo,
+                           float clip_hi, float* out_z, void* stream);
+
+/* pts = rays_o + rays_d * z  ([n_rays,S,3]; the reference materialises it, we only do on request) */
+int b200nerf_points(const float* rays_o, const float* rays_d, const float* z, int n_rays, int S, float* out_pts,
+                    void* stream);
+
+/* Trainer.run_network + NeRF.forward (nerf_pytorch/trainers/Trainer.py:789-806,
+ * run_nerf_helpers.py:109-134): positional encoding of the sample positions (63) and view directions (27)
+ * fused into the 8x256 skip@4 MLP.  Sample positions are either o + d*z (`z` [n_rays,S], `pts` NULL) or explicit
+ * (`pts` [n_rays,S,3]).  out_raw [n_rays,S,4] = (r,g,b,sigma) pre-activation. */
+int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,
+                          const float* viewdirs, const float* z, const float* pts, int n_rays, int S, float* out_raw,
+                          void* stream);
+
+/* DepthNetTrainer.raw2outputs (trainers/sampling_trainer.py:153-230, raw2alpha nerf_utils.py:27-42).
+ * raw [n_rays,S,4], z [n_rays,S], rays_d [n_rays,3], noise [n_rays,S] or NULL (already scaled by raw_noise_std).
+ * Outputs: rgb [n_rays,3], disp/acc/depth [n_rays], weights/alphas [n_rays,S] (each may be NULL).
+ * S == 1 reproduces the reference's empty-interval quirk: rgb = sigmoid(raw rgb), acc = depth = 0, disp = 1e10. */
+int b200nerf_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays,
+                           int S, int white_bkgd, float* out_rgb, float* out_disp, float* out_acc, float* out_depth,
+                           float* out_weights, float* out_alphas, void* stream);
+
+/* render_rays_test, DepthNet mode (nerf_utils.py:736-876): depthnet -> place -> encode+MLP -> composite for
+ * n_rays rays already on the device.  ws_z [n_rays,S] and ws_raw [n_rays,S,4] are caller-provided workspaces
+ * that double as the `depth_net_z_vals` / `raw` extras; out_weights may be NULL. */
+int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_aux, int dn_hidden, const void* nerf_wpack,
+                             const float* nerf_aux, int prec, const float* rays_o, const float* rays_d,
+                             const float* viewdirs, int n_rays, int S, int mode, const float* offsets, float radius,
+                             float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, float* out_rgb,
+                             float* out_disp, float* out_acc, float* out_depth, float* out_weights, void* stream);
+
+/* Same, through host memory: copies h_rays_o / h_rays_d ([n_rays,3] each, ideally pinned) to the device
+ * workspace, renders, copies rgb [n_rays,3] and disp [n_rays] back and synchronises `stream`.
+ * d_ws must hold b200nerf_render_host_ws_bytes(n_rays, S) bytes. */
+size_t b200nerf_render_host_ws_bytes(int n_rays, int S);
+int b200nerf_render_depthnet_host(const void* dn_wpack, const float* dn_aux, int dn_hidden, const void* nerf_wpack,
+                                  const float* nerf_aux, int prec, const float* h_rays_o, const float* h_rays_d,
+                                  int n_rays, int S, int mode, const float* offsets, float radius, float near_,
+                                  float far_, void* d_ws, float* h_rgb, float* h_disp, void* stream);
+
+/* ---- diagnostics ------------------------------------------------------------------------------------------ */
+
+/* D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs (raw uint16), through the same shared-memory operand layout,
+ * UMMA descriptors and TMEM read-back as the MLP kernels.  K % 16 == 0, K <= 128, N % 16 == 0, N <= 256. */
+int b200nerf_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int K, int N, void* stream);
+
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+unsigned long long b200nerf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NERF_H */

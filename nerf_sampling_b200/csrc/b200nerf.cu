@@ -1,0 +1,602 @@
+// libb200nerf.so -- C ABI + the bandwidth-bound kernels of the render_rays hot path (see include/b200nerf.h).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/b200nerf.h"
+#include "mlp_chain.cuh"
+
+using namespace b200;
+
+// ------------------------------------------------------------------------------------------- error plumbing
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define LAUNCH_CHECK()  \
+  do {                  \
+    ++g_launches;       \
+    CUDA_TRY(cudaGetLastError()); \
+  } while (0)
+
+extern "C" int b200nerf_version(void) { return B200NERF_VERSION; }
+extern "C" const char* b200nerf_last_error(void) { return g_err; }
+extern "C" unsigned long long b200nerf_launch_count(void) { return g_launches.load(); }
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------- host packing
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((u >> 16) | 0x40);  // quiet NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+static inline float bf2f(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// W [N, ldw] fp32, columns [col0, col0+K) -> Kpad/16 slabs; one slab = hi [2][N/8][8 rows][8 k] bf16 (+ lo).
+static uint8_t* pack_linear(const float* W, int N, int K, int ldw, int col0, int Kpad, bool split, uint8_t* out) {
+  const size_t plane = static_cast<size_t>(N) * 32;
+  for (int k16 = 0; k16 < Kpad / 16; ++k16) {
+    uint16_t* hi = reinterpret_cast<uint16_t*>(out);
+    uint16_t* lo = reinterpret_cast<uint16_t*>(out + plane);
+    for (int kc = 0; kc < 2; ++kc)
+      for (int n = 0; n < N; ++n)
+        for (int e = 0; e < 8; ++e) {
+          const int k = k16 * 16 + kc * 8 + e;
+          const float w = k < K ? W[static_cast<size_t>(n) * ldw + col0 + k] : 0.f;
+          const size_t idx = static_cast<size_t>(kc) * N * 8 + static_cast<size_t>(n >> 3) * 64 + (n & 7) * 8 + e;
+          const uint16_t h = f2bf(w);
+          hi[idx] = h;
+          if (split) lo[idx] = f2bf(w - bf2f(h));
+        }
+    out += split ? 2 * plane : plane;
+  }
+  return out;
+}
+
+// NeRF aux block (float offsets)
+enum : uint32_t {
+  NERF_B0 = 0, NERF_BF = 2048, NERF_BV = 2304, NERF_WA = 2432, NERF_BA = 2688, NERF_WR = 2692, NERF_BR = 3076,
+  NERF_AUX_FLOATS = 3080
+};
+
+extern "C" size_t b200nerf_nerf_wpack_bytes(int prec) {
+  // K16 slabs: skip part 4 + L0 4 + 7 trunk layers x 16 + feature 16 (N=256) and 18 view slabs (N=128)
+  const size_t per256 = prec == B200NERF_PREC_SPLIT ? 16384 : 8192;
+  return (4 + 4 + 7 * 16 + 16) * per256 + 18 * (per256 / 2);
+}
+extern "C" size_t b200nerf_nerf_aux_floats(void) { return NERF_AUX_FLOATS; }
+
+extern "C" int b200nerf_nerf_pack(const float* const* t, int prec, void* h_wpack, float* h_aux) {
+  if (!t || !h_wpack || !h_aux) return fail("b200nerf_nerf_pack: null argument");
+  const bool split = prec == B200NERF_PREC_SPLIT;
+  uint8_t* o = static_cast<uint8_t*>(h_wpack);
+  const float* W[8];
+  const float* B[8];
+  for (int i = 0; i < 8; ++i) {
+    W[i] = t[2 * i];
+    B[i] = t[2 * i + 1];
+  }
+  const float *Wv = t[16], *Bv = t[17], *Wf = t[18], *Bf = t[19], *Wa = t[20], *Ba = t[21], *Wr = t[22], *Br = t[23];
+  o = pack_linear(W[5], 256, 63, 319, 0, 64, split, o);   // skip-connection part of pts_linears.5 (input_pts columns)
+  o = pack_linear(W[0], 256, 63, 63, 0, 64, split, o);    // pts_linears.0
+  for (int i = 1; i <= 4; ++i) o = pack_linear(W[i], 256, 256, 256, 0, 256, split, o);
+  o = pack_linear(W[5], 256, 256, 319, 63, 256, split, o);  // hidden part of pts_linears.5
+  o = pack_linear(W[6], 256, 256, 256, 0, 256, split, o);
+  o = pack_linear(W[7], 256, 256, 256, 0, 256, split, o);
+  o = pack_linear(Wf, 256, 256, 256, 0, 256, split, o);
+  o = pack_linear(Wv, 128, 283, 283, 0, 288, split, o);   // [feature | view encoding] -> 128
+  if (static_cast<size_t>(o - static_cast<uint8_t*>(h_wpack)) != b200nerf_nerf_wpack_bytes(prec))
+    return fail("b200nerf_nerf_pack: internal size mismatch");
+  memset(h_aux, 0, NERF_AUX_FLOATS * sizeof(float));
+  for (int i = 0; i < 8; ++i) memcpy(h_aux + NERF_B0 + 256 * i, B[i], 256 * sizeof(float));
+  memcpy(h_aux + NERF_BF, Bf, 256 * sizeof(float));
+  memcpy(h_aux + NERF_BV, Bv, 128 * sizeof(float));
+  memcpy(h_aux + NERF_WA, Wa, 256 * sizeof(float));
+  h_aux[NERF_BA] = Ba[0];
+  memcpy(h_aux + NERF_WR, Wr, 384 * sizeof(float));
+  memcpy(h_aux + NERF_BR, Br, 3 * sizeof(float));
+  return 0;
+}
+
+extern "C" size_t b200nerf_depthnet_wpack_bytes(int n_hidden, int prec) {
+  return static_cast<size_t>(n_hidden + 1) * 16 * (prec == B200NERF_PREC_SPLIT ? 16384 : 8192);
+}
+extern "C" size_t b200nerf_depthnet_aux_floats(int n_hidden) { return static_cast<size_t>(n_hidden + 1) * 256 + 256 + 4; }
+
+extern "C" int b200nerf_depthnet_pack(const float* h_w0, const float* h_b0, const float* const* h_hidden, int n_hidden,
+                                      const float* h_head_w, const float* h_head_b, int prec, void* h_wpack, float* h_aux) {
+  if (!h_w0 || !h_b0 || !h_head_w || !h_head_b || !h_wpack || !h_aux || (n_hidden > 0 && !h_hidden))
+    return fail("b200nerf_depthnet_pack: null argument");
+  if (n_hidden < 0 || n_hidden + 1 > MAX_STEPS) return fail("b200nerf_depthnet_pack: n_hidden=%d out of range", n_hidden);
+  const bool split = prec == B200NERF_PREC_SPLIT;
+  uint8_t* o = static_cast<uint8_t*>(h_wpack);
+  o = pack_linear(h_w0, 256, 256, 256, 0, 256, split, o);
+  memcpy(h_aux, h_b0, 256 * sizeof(float));
+  for (int i = 0; i < n_hidden; ++i) {
+    o = pack_linear(h_hidden[2 * i], 256, 256, 256, 0, 256, split, o);
+    memcpy(h_aux + 256 * (i + 1), h_hidden[2 * i + 1], 256 * sizeof(float));
+  }
+  memcpy(h_aux + 256 * (n_hidden + 1), h_head_w, 256 * sizeof(float));
+  float* hb = h_aux + 256 * (n_hidden + 2);
+  hb[0] = h_head_b[0];
+  hb[1] = hb[2] = hb[3] = 0.f;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- ray generation
+// get_rays (run_nerf_helpers.py:187-202) + viewdirs (nerf_utils.py:173); pixel centres without +0.5.
+struct Cam {
+  float r[12];
+};
+__global__ void get_rays_kernel(int H, int W, float fx, float fy, float cx, float cy, Cam cam, float* __restrict__ ro,
+                                float* __restrict__ rd, float* __restrict__ vd) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * W) return;
+  const float i = static_cast<float>(idx % W), j = static_cast<float>(idx / W);
+  const float d0 = __fdiv_rn(__fadd_rn(i, -cx), fx);
+  const float d1 = -__fdiv_rn(__fadd_rn(j, -cy), fy);
+  const float d2 = -1.f;
+  float d[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    d[a] = __fadd_rn(__fadd_rn(__fmul_rn(d0, cam.r[4 * a + 0]), __fmul_rn(d1, cam.r[4 * a + 1])), __fmul_rn(d2, cam.r[4 * a + 2]));
+  const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (ro) ro[idx * 3 + a] = cam.r[4 * a + 3];
+    if (rd) rd[idx * 3 + a] = d[a];
+    if (vd) vd[idx * 3 + a] = __fdiv_rn(d[a], nrm);
+  }
+}
+
+extern "C" int b200nerf_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* h_c2w, float* rays_o,
+                                 float* rays_d, float* viewdirs, void* stream) {
+  if (H <= 0 || W <= 0 || !h_c2w) return fail("b200nerf_get_rays: bad arguments");
+  Cam cam;
+  memcpy(cam.r, h_c2w, sizeof(cam.r));
+  const int n = H * W;
+  get_rays_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(H, W, fx, fy, cx, cy, cam, rays_o, rays_d, viewdirs);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void normalize_dirs_kernel(const float* __restrict__ rd, int n, float* __restrict__ vd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = rd[i * 3], y = rd[i * 3 + 1], z = rd[i * 3 + 2];
+  const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+  vd[i * 3] = __fdiv_rn(x, nrm);
+  vd[i * 3 + 1] = __fdiv_rn(y, nrm);
+  vd[i * 3 + 2] = __fdiv_rn(z, nrm);
+}
+extern "C" int b200nerf_normalize_dirs(const float* rays_d, int n_rays, float* viewdirs, void* stream) {
+  if (n_rays < 0 || (n_rays && (!rays_d || !viewdirs))) return fail("b200nerf_normalize_dirs: bad arguments");
+  if (n_rays == 0) return 0;
+  normalize_dirs_kernel<<<(n_rays + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(rays_d, n_rays, viewdirs);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- sample placement
+// sample_points_around_mean (nerf_pytorch/utils.py:220-244).  Uniform mode needs no sort: the grid is
+// monotone, so sort(cat([mean+grid, mean])) = the grid values below zero, then the mean, then the rest.
+__global__ void place_uniform_kernel(const float* __restrict__ mean, const float* __restrict__ grid, int n_rays, int S,
+                                     float lo, float hi, float* __restrict__ z) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(n_rays) * S) return;
+  const int s = static_cast<int>(idx % S);
+  const float m = mean[idx / S];
+  float v = m;  // slot n_neg (first slot whose grid value is not negative) holds the mean itself
+  if (s <= S - 2 && __ldg(grid + s) < 0.f) v = __fadd_rn(m, __ldg(grid + s));
+  else if (s >= 1 && !(__ldg(grid + s - 1) < 0.f)) v = __fadd_rn(m, __ldg(grid + s - 1));
+  v = v < lo ? lo : (v > hi ? hi : v);  // NaN (ray missed the sphere) stays NaN, like torch.clip
+  z[idx] = v;
+}
+
+// Gaussian mode: one warp sorts one ray's S values (bitonic network over a power-of-two padded row in smem).
+__global__ void place_sorted_kernel(const float* __restrict__ mean, const float* __restrict__ offs, int n_rays, int S,
+                                    int P /*pow2 >= S*/, float* __restrict__ z) {
+  extern __shared__ float srow[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * (blockDim.x >> 5) + wib;
+  float* row = srow + wib * P;
+  if (ray < n_rays) {
+    const float m = mean[ray];
+    for (int i = lane; i < P; i += 32)
+      row[i] = i < S - 1 ? __fadd_rn(m, offs[static_cast<size_t>(ray) * (S - 1) + i]) : (i == S - 1 ? m : __int_as_float(0x7f800000));
+  }
+  __syncwarp();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (ray < n_rays)
+        for (int i = lane; i < P; i += 32) {
+          const int l = i ^ j;
+          if (l > i) {
+            const float a = row[i], b = row[l];
+            const bool up = (i & k) == 0;
+            // NaN sorts last (as torch.sort does): treat NaN as +inf-and-beyond
+            const bool a_gt_b = (a != a) ? !(b != b) : (!(b != b) && a > b);
+            if (a_gt_b == up) {
+              row[i] = b;
+              row[l] = a;
+            }
+          }
+        }
+      __syncwarp();
+    }
+  if (ray < n_rays)
+    for (int i = lane; i < S; i += 32) z[static_cast<size_t>(ray) * S + i] = row[i];
+}
+
+extern "C" int b200nerf_place_samples(const float* mean, const float* offsets, int n_rays, int S, int mode, float clip_lo,
+                                      float clip_hi, float* out_z, void* stream) {
+  if (n_rays < 0 || S < 1 || !out_z || !mean) return fail("b200nerf_place_samples: bad arguments");
+  if (n_rays == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t total = static_cast<size_t>(n_rays) * S;
+  if (mode == B200NERF_PLACE_DEPTH_ONLY) {
+    if (S != 1) return fail("b200nerf_place_samples: depth_only needs S == 1");
+    CUDA_TRY(cudaMemcpyAsync(out_z, mean, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  if (S > 1 && !offsets) return fail("b200nerf_place_samples: offsets is null");
+  if (mode == B200NERF_PLACE_UNIFORM) {
+    place_uniform_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(mean, offsets, n_rays, S, clip_lo, clip_hi, out_z);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  if (mode == B200NERF_PLACE_GAUSSIAN) {
+    int P = 1;
+    while (P < S) P <<= 1;
+    if (P > 4096) return fail("b200nerf_place_samples: S=%d too large for gaussian mode", S);
+    const int wpb = 4;
+    place_sorted_kernel<<<(n_rays + wpb - 1) / wpb, wpb * 32, wpb * P * sizeof(float), st>>>(mean, offsets, n_rays, S, P, out_z);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  return fail("b200nerf_place_samples: unknown mode %d", mode);
+}
+
+__global__ void points_kernel(const float* __restrict__ ro, const float* __restrict__ rd, const float* __restrict__ z,
+                              size_t total, int S, float* __restrict__ pts) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total * 3) return;
+  const size_t pt = idx / 3;
+  const int a = static_cast<int>(idx % 3);
+  const size_t ray = pt / S;
+  pts[idx] = __fadd_rn(ro[ray * 3 + a], __fmul_rn(rd[ray * 3 + a], z[pt]));
+}
+extern "C" int b200nerf_points(const float* rays_o, const float* rays_d, const float* z, int n_rays, int S, float* out_pts,
+                               void* stream) {
+  if (n_rays < 0 || S < 1) return fail("b200nerf_points: bad arguments");
+  const size_t total = static_cast<size_t>(n_rays) * S;
+  if (total == 0) return 0;
+  points_kernel<<<static_cast<unsigned>((total * 3 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rays_o, rays_d, z, total, S, out_pts);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- compositing
+// raw2outputs (trainers/sampling_trainer.py:153-230).  LPR lanes cooperate on one ray: each lane owns one
+// sample per pass (float4 load of raw, coalesced), the exclusive transmittance product is a segmented warp
+// scan (double precision, like the CPU reference's cumprod), the three maps are reduced in registers.
+template <int LPR>
+__global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+                                                        const float* __restrict__ rays_d, const float* __restrict__ noise,
+                                                        int n_rays, int S, int white, float* __restrict__ o_rgb,
+                                                        float* __restrict__ o_disp, float* __restrict__ o_acc,
+                                                        float* __restrict__ o_depth, float* __restrict__ o_w,
+                                                        float* __restrict__ o_alpha) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lig = threadIdx.x & (LPR - 1);
+  int ray = gtid / LPR;
+  const bool live = ray < n_rays;
+  if (!live) ray = n_rays - 1;
+  const size_t base = static_cast<size_t>(ray) * S;
+  const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+  const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+
+  double carry = 1.0;
+  float s_r = 0.f, s_g = 0.f, s_b = 0.f, s_d = 0.f, s_a = 0.f;
+  for (int s0 = 0; s0 < S; s0 += LPR) {
+    const int s = s0 + lig;
+    const bool on = s < S;
+    float alpha = 0.f, zz = 0.f;
+    float4 rw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+      rw = __ldg(reinterpret_cast<const float4*>(raw) + base + s);
+      zz = __ldg(z + base + s);
+      const float dist = __fmul_rn(s + 1 < S ? __fadd_rn(__ldg(z + base + s + 1), -zz) : 1e10f, nrm);
+      float sg = rw.w;
+      if (noise) sg = __fadd_rn(sg, __ldg(noise + base + s));
+      alpha = __fadd_rn(1.0f, -expf(__fmul_rn(-fmaxf(sg, 0.f), dist)));
+    }
+    const float f = on ? __fadd_rn(__fadd_rn(1.0f, -alpha), 1e-10f) : 1.0f;
+    double incl = static_cast<double>(f);
+#pragma unroll
+    for (int off = 1; off < LPR; off <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, incl, off, LPR);
+      if (lig >= off) incl *= t;
+    }
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1, LPR);
+    if (lig == 0) excl = 1.0;
+    const float T = static_cast<float>(carry * excl);
+    carry *= __shfl_sync(0xffffffffu, incl, LPR - 1, LPR);
+    if (on) {
+      const float w = __fmul_rn(alpha, T);
+      s_r = fmaf(w, 1.0f / (1.0f + expf(-rw.x)), s_r);
+      s_g = fmaf(w, 1.0f / (1.0f + expf(-rw.y)), s_g);
+      s_b = fmaf(w, 1.0f / (1.0f + expf(-rw.z)), s_b);
+      s_d = fmaf(w, zz, s_d);
+      s_a += w;
+      if (live && o_w) o_w[base + s] = w;
+      if (live && o_alpha) o_alpha[base + s] = alpha;
+    }
+  }
+#pragma unroll
+  for (int off = LPR >> 1; off > 0; off >>= 1) {
+    s_r += __shfl_xor_sync(0xffffffffu, s_r, off, LPR);
+    s_g += __shfl_xor_sync(0xffffffffu, s_g, off, LPR);
+    s_b += __shfl_xor_sync(0xffffffffu, s_b, off, LPR);
+    s_d += __shfl_xor_sync(0xffffffffu, s_d, off, LPR);
+    s_a += __shfl_xor_sync(0xffffffffu, s_a, off, LPR);
+  }
+  if (live && lig == 0) {
+    if (white) {
+      const float bg = __fadd_rn(1.0f, -s_a);
+      s_r += bg;
+      s_g += bg;
+      s_b += bg;
+    }
+    if (o_rgb) {
+      o_rgb[ray * 3] = s_r;
+      o_rgb[ray * 3 + 1] = s_g;
+      o_rgb[ray * 3 + 2] = s_b;
+    }
+    if (o_disp) o_disp[ray] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(s_d, __fadd_rn(s_a, 1e-10f))));
+    if (o_acc) o_acc[ray] = s_a;
+    if (o_depth) o_depth[ray] = s_d;
+  }
+}
+
+// S == 1: the reference pads the interval list from an EMPTY slice, so every per-sample tensor is [N,0]
+// and the colour is sigmoid(raw rgb) (sampling_trainer.py:178-180, :220-221).
+__global__ void composite_single_kernel(const float* __restrict__ raw, int n_rays, float* __restrict__ o_rgb,
+                                        float* __restrict__ o_disp, float* __restrict__ o_acc, float* __restrict__ o_depth) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= n_rays) return;
+  const float4 rw = __ldg(reinterpret_cast<const float4*>(raw) + ray);
+  if (o_rgb) {
+    o_rgb[ray * 3] = 1.0f / (1.0f + expf(-rw.x));
+    o_rgb[ray * 3 + 1] = 1.0f / (1.0f + expf(-rw.y));
+    o_rgb[ray * 3 + 2] = 1.0f / (1.0f + expf(-rw.z));
+  }
+  if (o_disp) o_disp[ray] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(0.f, 1e-10f)));
+  if (o_acc) o_acc[ray] = 0.f;
+  if (o_depth) o_depth[ray] = 0.f;
+}
+
+template <int LPR>
+static void launch_composite(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays, int S,
+                             int white, float* o_rgb, float* o_disp, float* o_acc, float* o_depth, float* o_w,
+                             float* o_alpha, cudaStream_t st) {
+  const long long threads = static_cast<long long>(n_rays) * LPR;
+  composite_kernel<LPR><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(raw, z, rays_d, noise, n_rays, S, white, o_rgb, o_disp,
+                                                                                   o_acc, o_depth, o_w, o_alpha);
+}
+
+extern "C" int b200nerf_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays,
+                                      int S, int white_bkgd, float* out_rgb, float* out_disp, float* out_acc,
+                                      float* out_depth, float* out_weights, float* out_alphas, void* stream) {
+  if (n_rays < 0 || S < 1) return fail("b200nerf_composite_fwd: bad sizes n_rays=%d S=%d", n_rays, S);
+  if (n_rays == 0) return 0;
+  if (!raw || !z || !rays_d) return fail("b200nerf_composite_fwd: null input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (S == 1) {
+    composite_single_kernel<<<(n_rays + 255) / 256, 256, 0, st>>>(raw, n_rays, out_rgb, out_disp, out_acc, out_depth);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  if (S <= 2) launch_composite<2>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  else if (S <= 4) launch_composite<4>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  else if (S <= 8) launch_composite<8>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  else if (S <= 16) launch_composite<16>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  else launch_composite<32>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- MLP launches
+template <bool SPLIT, int INPUT>
+static int launch_chain(const ChainParams& p, cudaStream_t st) {
+  static bool configured = false;
+  constexpr int smem = chain_smem_bytes<SPLIT>();
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(mlp_chain_kernel<SPLIT, INPUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int sms = sm_count();
+  if (sms <= 0) return fail("no CUDA device");
+  const int tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+  const int grid = tiles < sms ? tiles : sms;
+  mlp_chain_kernel<SPLIT, INPUT><<<grid, CHAIN_THREADS, smem, st>>>(p);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static Step make_step(int a_begin, int n_k16, int n, int acc_col, int accumulate, int wait_a, int epi, int act, uint32_t bias_off) {
+  Step s;
+  s.a_k16_begin = static_cast<uint16_t>(a_begin);
+  s.n_k16 = static_cast<uint16_t>(n_k16);
+  s.n = static_cast<uint16_t>(n);
+  s.acc_col = static_cast<uint16_t>(acc_col);
+  s.accumulate = static_cast<uint8_t>(accumulate);
+  s.wait_a = static_cast<uint8_t>(wait_a);
+  s.epi = static_cast<uint8_t>(epi);
+  s.act = static_cast<uint8_t>(act);
+  s.bias_off = bias_off;
+  return s;
+}
+
+extern "C" int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,
+                                     const float* viewdirs, const float* z, const float* pts, int n_rays, int S, float* out_raw,
+                                     void* stream) {
+  if (n_rays < 0 || S < 1) return fail("b200nerf_nerf_mlp_fwd: bad sizes n_rays=%d S=%d", n_rays, S);
+  if (n_rays == 0) return 0;
+  if (!wpack || !aux || !viewdirs || !out_raw) return fail("b200nerf_nerf_mlp_fwd: null argument");
+  if (!pts && (!z || !rays_o || !rays_d)) return fail("b200nerf_nerf_mlp_fwd: need pts or (rays_o, rays_d, z)");
+  if (static_cast<long long>(n_rays) * S > 0x7fffff00LL) return fail("b200nerf_nerf_mlp_fwd: too many points for one call");
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.wpack = static_cast<const uint8_t*>(wpack);
+  p.aux = aux;
+  int n = 0;
+  // run_nerf_helpers.py:109-134.  TMEM: X = columns 0..255, Y = columns 256..511.
+  p.steps[n++] = make_step(0, 4, 256, 256, 0, 1, EPI_NONE, ACT_NONE, 0);              // enc(pts) . W5[:, :63]^T -> Y (kept for layer 5)
+  p.steps[n++] = make_step(0, 4, 256, 0, 0, 0, EPI_STORE, ACT_RELU, NERF_B0);         // layer 0
+  for (int i = 1; i <= 4; ++i) p.steps[n++] = make_step(0, 16, 256, 0, 0, 1, EPI_STORE, ACT_RELU, NERF_B0 + 256 * i);
+  p.steps[n++] = make_step(0, 16, 256, 256, 1, 1, EPI_STORE, ACT_RELU, NERF_B0 + 256 * 5);  // layer 5 = Y + h4 . W5[:, 63:]^T
+  p.steps[n++] = make_step(0, 16, 256, 0, 0, 1, EPI_STORE, ACT_RELU, NERF_B0 + 256 * 6);
+  p.steps[n++] = make_step(0, 16, 256, 0, 0, 1, EPI_STORE_ALPHA, ACT_RELU, NERF_B0 + 256 * 7);  // layer 7 + alpha_linear
+  p.steps[n++] = make_step(0, 16, 256, 0, 0, 1, EPI_STORE, ACT_NONE, NERF_BF);        // feature_linear (no activation)
+  p.steps[n++] = make_step(0, 18, 128, 0, 0, 1, EPI_NERF_OUT, ACT_RELU, NERF_BV);     // views_linears.0 + rgb_linear
+  p.n_steps = n;
+  p.n_rows = n_rays * S;
+  p.S = S;
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.viewdirs = viewdirs;
+  p.z = z;
+  p.pts = pts;
+  p.out = out_raw;
+  p.head_w_off = NERF_WA;
+  p.head_b_off = NERF_BA;
+  p.rgb_w_off = NERF_WR;
+  p.rgb_b_off = NERF_BR;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return prec == B200NERF_PREC_SPLIT ? launch_chain<true, IN_NERF>(p, st) : launch_chain<false, IN_NERF>(p, st);
+}
+
+extern "C" int b200nerf_depthnet_fwd(const void* wpack, const float* aux, int n_hidden, int prec, const float* rays_o,
+                                     const float* rays_d, int n_rays, float radius, float near_, float far_, float* out_z,
+                                     void* stream) {
+  if (n_rays < 0) return fail("b200nerf_depthnet_fwd: bad n_rays");
+  if (n_rays == 0) return 0;
+  if (!wpack || !aux || !rays_o || !rays_d || !out_z) return fail("b200nerf_depthnet_fwd: null argument");
+  if (n_hidden < 0 || n_hidden + 1 > MAX_STEPS) return fail("b200nerf_depthnet_fwd: n_hidden=%d out of range", n_hidden);
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.wpack = static_cast<const uint8_t*>(wpack);
+  p.aux = aux;
+  for (int i = 0; i <= n_hidden; ++i)
+    p.steps[i] = make_step(0, 16, 256, 0, 0, 1, i == n_hidden ? EPI_DEPTH_OUT : EPI_STORE, ACT_LEAKY, 256 * i);
+  p.n_steps = n_hidden + 1;
+  p.n_rows = n_rays;
+  p.S = 1;
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.out = out_z;
+  p.head_w_off = 256 * (n_hidden + 1);
+  p.head_b_off = 256 * (n_hidden + 2);
+  p.radius = radius;
+  p.near = near_;
+  p.far = far_;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return prec == B200NERF_PREC_SPLIT ? launch_chain<true, IN_DEPTHNET>(p, st) : launch_chain<false, IN_DEPTHNET>(p, st);
+}
+
+// ------------------------------------------------------------------------------------------- fused render
+extern "C" int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_aux, int dn_hidden, const void* nerf_wpack,
+                                        const float* nerf_aux, int prec, const float* rays_o, const float* rays_d,
+                                        const float* viewdirs, int n_rays, int S, int mode, const float* offsets, float radius,
+                                        float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, float* out_rgb,
+                                        float* out_disp, float* out_acc, float* out_depth, float* out_weights, void* stream) {
+  if (n_rays == 0) return 0;
+  if (!ws_mean || !ws_z || !ws_raw) return fail("b200nerf_render_depthnet: null workspace");
+  int rc = b200nerf_depthnet_fwd(dn_wpack, dn_aux, dn_hidden, prec, rays_o, rays_d, n_rays, radius, near_, far_, ws_mean, stream);
+  if (rc) return rc;
+  // the reference clips uniform placements to the literal [2, 6] (nerf_pytorch/utils.py:241)
+  rc = b200nerf_place_samples(ws_mean, offsets, n_rays, S, mode, 2.0f, 6.0f, ws_z, stream);
+  if (rc) return rc;
+  rc = b200nerf_nerf_mlp_fwd(nerf_wpack, nerf_aux, prec, rays_o, rays_d, viewdirs, ws_z, nullptr, n_rays, S, ws_raw, stream);
+  if (rc) return rc;
+  // DepthNet path: noise 0 and white background regardless of the caller's flags (misspelled kwargs,
+  // nerf_utils.py:858-865)
+  return b200nerf_composite_fwd(ws_raw, ws_z, rays_d, nullptr, n_rays, S, 1, out_rgb, out_disp, out_acc, out_depth, out_weights,
+                                nullptr, stream);
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+extern "C" size_t b200nerf_render_host_ws_bytes(int n_rays, int S) {
+  const size_t n = static_cast<size_t>(n_rays);
+  return 3 * align256(n * 3 * 4) + align256(n * 4) /*mean*/ + align256(n * S * 4) /*z*/ + align256(n * S * 16) /*raw*/ +
+         align256(n * 3 * 4) /*rgb*/ + align256(n * 4) /*disp*/;
+}
+
+extern "C" int b200nerf_render_depthnet_host(const void* dn_wpack, const float* dn_aux, int dn_hidden, const void* nerf_wpack,
+                                             const float* nerf_aux, int prec, const float* h_rays_o, const float* h_rays_d,
+                                             int n_rays, int S, int mode, const float* offsets, float radius, float near_,
+                                             float far_, void* d_ws, float* h_rgb, float* h_disp, void* stream) {
+  if (n_rays <= 0 || !d_ws || !h_rays_o || !h_rays_d || !h_rgb || !h_disp) return fail("b200nerf_render_depthnet_host: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(n_rays);
+  uint8_t* w = static_cast<uint8_t*>(d_ws);
+  float* ro = reinterpret_cast<float*>(w); w += align256(n * 12);
+  float* rd = reinterpret_cast<float*>(w); w += align256(n * 12);
+  float* vd = reinterpret_cast<float*>(w); w += align256(n * 12);
+  float* mean = reinterpret_cast<float*>(w); w += align256(n * 4);
+  float* zb = reinterpret_cast<float*>(w); w += align256(n * S * 4);
+  float* rawb = reinterpret_cast<float*>(w); w += align256(n * S * 16);
+  float* rgb = reinterpret_cast<float*>(w); w += align256(n * 12);
+  float* disp = reinterpret_cast<float*>(w);
+  CUDA_TRY(cudaMemcpyAsync(ro, h_rays_o, n * 12, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(rd, h_rays_d, n * 12, cudaMemcpyHostToDevice, st));
+  int rc = b200nerf_normalize_dirs(rd, n_rays, vd, stream);
+  if (rc) return rc;
+  rc = b200nerf_render_depthnet(dn_wpack, dn_aux, dn_hidden, nerf_wpack, nerf_aux, prec, ro, rd, vd, n_rays, S, mode, offsets,
+                                radius, near_, far_, mean, zb, rawb, rgb, disp, nullptr, nullptr, nullptr, stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h_rgb, rgb, n * 12, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_disp, disp, n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- diagnostics
+extern "C" int b200nerf_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int K, int N, void* stream) {
+  if (!A || !B || !D || K % 16 || K <= 0 || K > 128 || N % 16 || N <= 0 || N > 256) return fail("b200nerf_umma_selftest: bad arguments");
+  const int smem = (K / 8) * ACT_KC_STRIDE + (K / 8) * N * 16;
+  CUDA_TRY(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  umma_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(A, B, D, K, N);
+  LAUNCH_CHECK();
+  return 0;
+}

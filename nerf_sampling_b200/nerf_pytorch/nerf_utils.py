@@ -1,0 +1,222 @@
+"""Mirror of the render driver ``nerf_sampling/nerf_pytorch/nerf_utils.py`` (:27-255, :393-494, :736-876)."""
+
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from . import run_nerf_helpers, utils
+from .utils import sample_points_around_mean  # noqa: F401  (re-exported like the reference)
+
+
+def raw2alpha(raw, dists):
+    """alpha = 1 - exp(-relu(sigma) * delta) (nerf_utils.py:27-42); fused in the composite kernel on the render path."""
+    return 1.0 - torch.exp(-F.relu(raw) * dists)
+
+
+def batchify(fn, chunk):
+    """nerf_utils.py:45-55."""
+    if chunk is None:
+        return fn
+    return lambda inputs: torch.cat([fn(inputs[i : i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+
+
+def prepare_rays(c2w, c2w_staticcam, use_viewdirs, ndc, H, W, K, near, far, rays):
+    """Ray batch rows [o(3), d(3), near, far, viewdir(3)] (nerf_utils.py:156-188)."""
+    if ndc:
+        raise NotImplementedError("NDC rays (LLFF forward-facing scenes) are outside the Blender/DepthNet path")
+    if c2w is not None:
+        dev = c2w.device if isinstance(c2w, torch.Tensor) and c2w.is_cuda else "cuda"
+        rays_o, rays_d, viewdirs = ops.get_rays(H, W, K, c2w, dev)
+        sh = (H, W, 3)
+        if c2w_staticcam is not None:
+            rays_o, rays_d, _ = ops.get_rays(H, W, K, c2w_staticcam, dev)
+    else:
+        rays_o, rays_d = rays
+        sh = tuple(rays_d.shape)
+        rays_o = rays_o.reshape(-1, 3).float().contiguous()
+        rays_d = rays_d.reshape(-1, 3).float().contiguous()
+        viewdirs = ops.normalize_dirs(rays_d)
+    near_t = torch.full_like(rays_d[..., :1], float(near))
+    far_t = torch.full_like(rays_d[..., :1], float(far))
+    packed = torch.cat([rays_o, rays_d, near_t, far_t], -1)
+    if use_viewdirs:
+        packed = torch.cat([packed, viewdirs], -1)
+    return packed, rays_o, rays_d, sh
+
+
+def _batchify(fn, rays_flat, chunk, **kwargs):
+    out = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        for k, v in fn(rays_flat[i : i + chunk], **kwargs).items():
+            out.setdefault(k, []).append(v)
+    return {k: torch.cat(v, 0) for k, v in out.items()}
+
+
+def batchify_rays_test(rays_flat, chunk=1024 * 32, **kwargs):
+    """Chunk loop of nerf_utils.py:73-85 (no allocator flush, no sync per chunk)."""
+    return _batchify(render_rays_test, rays_flat, chunk, **kwargs)
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    return _batchify(render_rays, rays_flat, chunk, **kwargs)
+
+
+def _finish(all_ret, sh, rays_o, rays_d):
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    head = ["depth_net_rgb_map", "depth_net_disp_map"]
+    extras = {k: v for k, v in all_ret.items() if k not in head}
+    extras["rays_o"], extras["rays_d"] = rays_o, rays_d
+    return [all_ret[k] for k in head] + [extras]
+
+
+def render_test(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.0, far=1.0, use_viewdirs=False,
+                c2w_staticcam=None, **kwargs):
+    """[rgb, disp, extras] for a full view or a ray batch (nerf_utils.py:191-255)."""
+    packed, rays_o, rays_d, sh = prepare_rays(c2w, c2w_staticcam, use_viewdirs, ndc, H, W, K, near, far, rays)
+    return _finish(batchify_rays_test(packed, chunk, **kwargs), sh, rays_o, rays_d)
+
+
+def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.0, far=1.0, use_viewdirs=False,
+           c2w_staticcam=None, **kwargs):
+    """Training-time render (nerf_utils.py:88-153)."""
+    packed, rays_o, rays_d, sh = prepare_rays(c2w, c2w_staticcam, use_viewdirs, ndc, H, W, K, near, far, rays)
+    return _finish(batchify_rays(packed, chunk, **kwargs), sh, rays_o, rays_d)
+
+
+def sample_as_in_NeRF(ray_batch, network_fn, network_fine, network_query_fn, N_samples, trainer, perturb, raw_noise_std,
+                      lindisp, white_bkgd, kwargs, pytest):
+    """Vanilla coarse + fine pass (nerf_utils.py:497-611)."""
+    n_rays = ray_batch.shape[0]
+    rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
+    viewdirs = ray_batch[:, -3:] if ray_batch.shape[-1] > 8 else None
+    bounds = torch.reshape(ray_batch[..., 6:8], [-1, 1, 2])
+    near, far = bounds[..., 0], bounds[..., 1]
+    c = trainer.sample_coarse_points(near=near, far=far, perturb=perturb, N_rays=n_rays, N_samples=N_samples,
+                                     viewdirs=viewdirs, network_fn=network_fn, network_query_fn=network_query_fn,
+                                     rays_o=rays_o, rays_d=rays_d, raw_noise_std=raw_noise_std, white_bkgd=white_bkgd,
+                                     pytest=pytest, lindisp=lindisp, kwargs=kwargs)
+    f = trainer.sample_fine_points(z_vals=c[5], weights=c[6], perturb=perturb, pytest=pytest, rays_d=rays_d, rays_o=rays_o,
+                                   rgb_map=c[0], disp_map=c[1], acc_map=c[2], network_fn=network_fn,
+                                   network_fine=network_fine, network_query_fn=network_query_fn, viewdirs=viewdirs,
+                                   raw_noise_std=raw_noise_std, white_bkgd=white_bkgd)
+    (_, _, _, fine_rgb, fine_disp, _, fine_raw, fine_z, fine_pts, fine_density, fine_alphas, fine_weights) = f
+    return fine_density, fine_z, fine_pts, fine_rgb, fine_weights, fine_alphas, fine_disp, fine_raw
+
+
+def render_rays_test(ray_batch, network_fn, network_query_fn, N_samples, trainer, retraw=True, lindisp=False, perturb=0.0,
+                     N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0.0, verbose=False, pytest=False,
+                     **kwargs):
+    """Inference render of one ray chunk (nerf_utils.py:736-876).
+
+    Differences from the reference, both documented in INTEGRATION.md: per-sample extras stay on the device
+    (the reference ``.cpu()``s ~0.8 GB per 800x800 view), and ``depth_net_pts`` is only materialised when the
+    trainer asks for scene data."""
+    rays_o, rays_d = ray_batch[:, 0:3].contiguous(), ray_batch[:, 3:6].contiguous()
+    viewdirs = ray_batch[:, -3:].contiguous() if ray_batch.shape[-1] > 8 else None
+    ret = {}
+    nerf_modes = trainer.compare_nerf or trainer.use_nerf_max_pts or trainer.use_full_nerf
+    if nerf_modes:
+        (fine_density, fine_z, fine_pts, fine_rgb, fine_weights, fine_alphas, fine_disp, fine_raw) = sample_as_in_NeRF(
+            ray_batch=ray_batch, N_samples=N_samples, network_fn=network_fn, network_fine=network_fine,
+            network_query_fn=network_query_fn, trainer=trainer, perturb=perturb, raw_noise_std=raw_noise_std,
+            lindisp=lindisp, white_bkgd=white_bkgd, pytest=pytest, kwargs=kwargs)
+        top, max_z, max_w, max_rgb = ops.argmax_gather(fine_weights, fine_z, fine_raw)
+        max_pts = ops.points(rays_o, rays_d, max_z)
+        ret["max_z_vals"], ret["max_pts"], ret["max_weights"] = max_z, max_pts, max_w
+
+    if trainer.use_nerf_max_pts:
+        rgb_map, disp, weights, pts, z = max_rgb, torch.zeros_like(max_rgb), max_w, max_pts, max_z
+    elif trainer.use_full_nerf:
+        rgb_map, disp, weights, pts, z = fine_rgb, fine_disp, fine_weights, fine_pts, fine_z
+    else:
+        net = network_fine if network_fine is not None else network_fn
+        out = ops.render_depthnet(kwargs["depth_network"].packed(), net.packed(), rays_o, rays_d, viewdirs,
+                                  trainer.n_depth_samples, trainer.sampling_mode, trainer.distance,
+                                  radius=float(kwargs["depth_network"].sphere_radius),
+                                  near=float(kwargs["depth_network"].near), far=float(kwargs["depth_network"].far))
+        rgb_map, disp, weights, z = out["rgb"], out["disp"], out["weights"], out["z"]
+        pts = ops.points(rays_o, rays_d, z) if getattr(trainer, "save_scene_data", False) else None
+        if retraw:
+            ret["raw"] = out["raw"]
+    ret["depth_net_rgb_map"] = rgb_map
+    ret["depth_net_weights"] = weights
+    ret["depth_net_disp_map"] = disp
+    ret["depth_net_z_vals"] = z
+    if pts is not None:
+        ret["depth_net_pts"] = pts
+    return ret
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, trainer, retraw=True, lindisp=False, perturb=0.0,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0.0, verbose=False, pytest=False, **kwargs):
+    """Training render (nerf_utils.py:614-733): hierarchical target depth + DepthNet with one sample per ray.
+    Forward only for now (the DepthNet backward kernels are the next milestone)."""
+    rays_o, rays_d = ray_batch[:, 0:3].contiguous(), ray_batch[:, 3:6].contiguous()
+    viewdirs = ray_batch[:, -3:].contiguous() if ray_batch.shape[-1] > 8 else None
+    (_, fine_z, _, _, fine_weights, _, _, fine_raw) = sample_as_in_NeRF(
+        ray_batch=ray_batch, N_samples=N_samples, network_fn=network_fn, network_fine=network_fine,
+        network_query_fn=network_query_fn, trainer=trainer, perturb=perturb, raw_noise_std=raw_noise_std, lindisp=lindisp,
+        white_bkgd=white_bkgd, pytest=pytest, kwargs=kwargs)
+    _, max_z, _, _ = ops.argmax_gather(fine_weights, fine_z, fine_raw)
+    z_dn = kwargs["depth_network"](rays_o, rays_d)
+    net = network_fine if network_fine is not None else network_fn
+    raw = net.query(viewdirs, rays_o=rays_o, rays_d=rays_d, z=z_dn)
+    rgb, disp, *_ = ops.composite(raw, z_dn, rays_d, white_bkgd=True)
+    ret = {"depth_net_rgb_map": rgb, "depth_net_disp_map": disp, "depth_net_z_vals": z_dn, "max_z_vals": max_z,
+           "depth_net_pts": ops.points(rays_o, rays_d, z_dn), "max_pts": ops.points(rays_o, rays_d, max_z)}
+    if retraw:
+        ret["raw"] = raw
+    return ret
+
+
+def create_nerf(args, model):
+    """Coarse/fine NeRF + optimizer + render kwargs (nerf_utils.py:393-494)."""
+    embed_fn, input_ch = run_nerf_helpers.get_embedder(args.multires, args.i_embed, args.input_dims_embed)
+    input_ch_views, embeddirs_fn = 0, None
+    if args.use_viewdirs:
+        embeddirs_fn, input_ch_views = run_nerf_helpers.get_embedder(args.multires_views, args.i_embed, args.input_dims_embed)
+    output_ch = 5 if args.N_importance > 0 else 4
+    skips = [4]
+    mk = lambda d, w: model(D=d, W=w, input_ch=input_ch, output_ch=output_ch, skips=skips,  # noqa: E731
+                            input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs).to(args.device)
+    model_nerf = mk(args.netdepth, args.netwidth)
+    grad_vars = list(model_nerf.parameters())
+    model_fine = None
+    if args.N_importance > 0:
+        model_fine = mk(args.netdepth_fine, args.netwidth_fine)
+        grad_vars += list(model_fine.parameters())
+
+    def network_query_fn(inputs, viewdirs, network_fn):
+        return args.run_network(inputs, viewdirs, network_fn, embed_fn=embed_fn, embeddirs_fn=embeddirs_fn, netchunk=args.netchunk)
+
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    start = 0
+    if args.ft_path is not None and args.ft_path != "None":
+        ckpts = [args.ft_path]
+    else:
+        d = os.path.join(args.basedir, args.expname)
+        ckpts = [os.path.join(d, f) for f in sorted(os.listdir(d)) if "tar" in f] if os.path.isdir(d) else []
+    if len(ckpts) > 0 and not args.no_reload:
+        ckpt = torch.load(ckpts[-1], map_location=args.device, weights_only=False)
+        start = ckpt["global_step"]
+        utils.load_nerf(model_nerf, model_fine, optimizer, ckpt)
+
+    render_kwargs_train = {
+        "network_query_fn": network_query_fn, "perturb": args.perturb, "N_importance": args.N_importance,
+        "network_fine": model_fine, "N_samples": args.N_samples, "network_fn": model_nerf,
+        "use_viewdirs": args.use_viewdirs, "white_bkgd": args.white_bkgd, "raw_noise_std": args.raw_noise_std,
+        "trainer": args,
+    }
+    if args.dataset_type != "llff" or getattr(args, "no_ndc", False):
+        render_kwargs_train["ndc"] = False
+        render_kwargs_train["lindisp"] = args.lindisp
+    render_kwargs_test = dict(render_kwargs_train)
+    render_kwargs_test["perturb"] = False
+    render_kwargs_test["raw_noise_std"] = 0.0
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer

@@ -1,0 +1,91 @@
+"""Mirror of ``nerf_pytorch/trainers/Trainer.py`` restricted to what the render_rays path reads:
+the constructor's config bag (:18-130), intrinsics (:136-146), ``run_network`` (:789-806) and the
+coarse / fine samplers (:553-710).  Data loading, logging and the training loop are caller context."""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ... import ops
+from .. import nerf_utils
+
+
+class Trainer:
+    def __init__(self, dataset_type, basedir, expname, no_batching, datadir, device="cpu", render_test=False,
+                 config_path=None, N_rand=32 * 32 * 4, render_only=False, chunk=1024 * 32, render_factor=0, multires=10,
+                 i_embed=0, multires_views=4, netchunk=1024 * 64, lrate=5e-4, lrate_decay=250, use_viewdirs=True,
+                 N_importance=0, netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, ft_path=None, perturb=1.0,
+                 raw_noise_std=0.0, N_samples=64, lindisp=True, precrop_iters=0, precrop_frac=0.5, i_weights=10000,
+                 i_testset=100, i_video=5000, i_print=100, input_dims_embed: int = 1, save_train_set_render: bool = True,
+                 depth_net_lr: float = 0.0001, train_depth_net_only: bool = False, trial=None, single_image=False,
+                 single_ray=False, save_scene_data=False, compare_nerf=False, use_nerf_max_pts=False, use_full_nerf=False):
+        loc = dict(locals())
+        loc.pop("self")
+        for k, v in loc.items():
+            setattr(self, k, v)
+        self.start = None
+        self.use_batching = not self.no_batching
+        self.no_reload = False
+        self.K = self.global_step = self.W = self.H = self.c2w = None
+
+    def load_data(self):
+        raise NotImplementedError("dataset loading is outside the B200 hot path; feed poses/rays directly")
+
+    def cast_intrinsics_to_right_types(self, hwf):
+        H, W, focal = hwf
+        H, W = int(H), int(W)
+        if self.K is None:
+            self.K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+        self.H, self.W = H, W
+        return [H, W, focal]
+
+    # ------------------------------------------------------------------ operators on the hot path
+    def run_network(self, inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+        """raw [N,S,4] for sample positions ``inputs`` [N,S,3] (Trainer.py:789-806).
+
+        The encodings described by ``embed_fn`` / ``embeddirs_fn`` are fused into the MLP kernel and the whole batch
+        is one launch, so ``netchunk`` has nothing left to bound."""
+        if getattr(embed_fn, "multires", 10) != 10 or getattr(embeddirs_fn, "multires", 4) != 4 or viewdirs is None:
+            raise NotImplementedError("the fused kernel implements multires=10 / multires_views=4 with view directions")
+        lead = list(inputs.shape[:-1])
+        pts = inputs.reshape(viewdirs.shape[0], -1, 3)
+        raw = fn.query(viewdirs, pts=pts)
+        return raw.reshape(lead + [4])
+
+    def raw2outputs(self, raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
+        raise NotImplementedError
+
+    def _sample_points(self, z_vals_mid, weights, perturb, pytest, rays_d, rays_o, n_importance=None):
+        """Inverse-CDF samples + their positions (Trainer.py:553-577)."""
+        if n_importance is None:
+            n_importance = self.N_importance
+        z_samples = nerf_utils.run_nerf_helpers.sample_pdf(z_vals_mid, weights[..., 1:-1], n_importance,
+                                                           det=(perturb == 0.0), pytest=pytest)
+        return z_samples, ops.points(rays_o, rays_d, z_samples)
+
+    def sample_coarse_points(self, near, far, perturb, N_rays, N_samples, viewdirs, network_fn, network_query_fn, rays_o,
+                             rays_d, raw_noise_std, white_bkgd, pytest, lindisp, **kwargs):
+        """Stratified coarse pass (Trainer.py:579-649); 9-tuple with ``weights`` at slots 3 and 6."""
+        if N_samples <= 0:
+            return (None,) * 9
+        t_rand = torch.rand(N_rays, N_samples, device=rays_o.device) if perturb > 0.0 else None
+        z = ops.coarse_z(near, far, N_rays, N_samples, lindisp, t_rand)
+        raw = network_fn.query(viewdirs, rays_o=rays_o, rays_d=rays_d, z=z)
+        rgb, disp, acc, depth, density, alphas, weights = self.raw2outputs(raw, z, rays_d, raw_noise_std, white_bkgd, pytest=pytest)
+        return rgb, disp, acc, weights, depth, z, weights, raw, None
+
+    def sample_fine_points(self, z_vals, weights, perturb, pytest, rays_d, rays_o, rgb_map, disp_map, acc_map, network_fn,
+                           network_fine, network_query_fn, viewdirs, raw_noise_std, white_bkgd):
+        """Importance pass: sample_pdf, merge with the coarse depths, re-evaluate all (Trainer.py:651-710)."""
+        if self.N_importance <= 0:
+            return (None,) * 12
+        u = None if perturb == 0.0 else torch.rand(z_vals.shape[0], self.N_importance, device=z_vals.device)
+        z_samples, z_all, _ = ops.sample_pdf_merge(z_vals, weights, self.N_importance, u)
+        run_fn = network_fn if network_fine is None else network_fine
+        raw = run_fn.query(viewdirs, rays_o=rays_o, rays_d=rays_d, z=z_all)
+        rgb, disp, acc, depth, density, alphas, w = self.raw2outputs(raw, z_all, rays_d, raw_noise_std, white_bkgd, pytest=pytest)
+        pts = ops.points(rays_o, rays_d, z_all) if getattr(self, "save_scene_data", False) else None
+        return rgb_map, disp_map, acc_map, rgb, disp, acc, raw, z_all, pts, density, alphas, w

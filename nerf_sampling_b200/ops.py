@@ -1,0 +1,185 @@
+"""Operator-level host API: torch CUDA tensors in, C-ABI kernels on the current stream, torch tensors out.
+
+Every function here is a thin marshal around one ``b200nerf_*`` entry point; there is no torch arithmetic on the
+data path and no CPU fallback (CPU tensors are rejected).
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .packing import PackedDepthNet, PackedNeRF
+
+PLACE_MODES = {"depth_only": 0, "uniform": 1, "gaussian": 2}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.B200NerfError(f"{name} must be a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def get_rays(H: int, W: int, K, c2w, device=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """rays_o, rays_d, viewdirs ([H*W,3] each) for a pinhole view (run_nerf_helpers.py:187-202)."""
+    device = torch.device(device if device is not None else "cuda")
+    c = torch.as_tensor(c2w, dtype=torch.float32, device="cpu")[:3, :4].contiguous()
+    n = H * W
+    ro = torch.empty(n, 3, device=device)
+    rd = torch.empty(n, 3, device=device)
+    vd = torch.empty(n, 3, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().b200nerf_get_rays(H, W, float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]),
+                                                c.data_ptr(), _p(ro), _p(rd), _p(vd), _stream()))
+    return ro, rd, vd
+
+
+def normalize_dirs(rays_d: torch.Tensor) -> torch.Tensor:
+    rays_d = _dev(rays_d, "rays_d").reshape(-1, 3)
+    out = torch.empty_like(rays_d)
+    with torch.cuda.device(rays_d.device):
+        _lib.check(_lib.lib().b200nerf_normalize_dirs(_p(rays_d), rays_d.shape[0], _p(out), _stream()))
+    return out
+
+
+def depthnet_forward(pk: PackedDepthNet, rays_o, rays_d, radius=2.0, near=2.0, far=6.0) -> torch.Tensor:
+    """DepthNet.forward -> [N,1] (depth_nets/depth_net.py:117-169)."""
+    rays_o, rays_d = _dev(rays_o, "rays_o"), _dev(rays_d, "rays_d")
+    n = rays_o.shape[0]
+    out = torch.empty(n, 1, device=rays_o.device)
+    with torch.cuda.device(rays_o.device):
+        _lib.check(_lib.lib().b200nerf_depthnet_fwd(_p(pk.wpack), _p(pk.aux), pk.n_hidden, pk.prec, _p(rays_o), _p(rays_d), n,
+                                                    float(radius), float(near), float(far), _p(out), _stream()))
+    return out
+
+
+def uniform_grid(std: float, n_samples: int, device) -> torch.Tensor:
+    """The S-1 offsets of uniform placement; computed by torch.linspace exactly as the reference does
+    (nerf_pytorch/utils.py:232) so that the depths are bit-identical."""
+    return torch.linspace(-std, std, steps=n_samples - 1, device="cpu").to(device)
+
+
+def place_samples(mean, n_samples: int, mode: str, std: float, noise: Optional[torch.Tensor] = None,
+                  clip=(2.0, 6.0)) -> torch.Tensor:
+    """z [N,S] of sample_points_around_mean (nerf_pytorch/utils.py:220-244); pts are not materialised."""
+    mean = _dev(mean, "mean").reshape(-1)
+    n = mean.shape[0]
+    m = PLACE_MODES[mode]
+    if mode == "depth_only":
+        n_samples = 1
+        offs = None
+    elif mode == "uniform":
+        offs = uniform_grid(std, n_samples, mean.device) if n_samples > 1 else None
+    else:
+        if noise is None:
+            noise = torch.randn(n, n_samples - 1, device=mean.device)
+        offs = _dev(std * noise, "noise")
+    z = torch.empty(n, n_samples, device=mean.device)
+    with torch.cuda.device(mean.device):
+        _lib.check(_lib.lib().b200nerf_place_samples(_p(mean), _p(offs), n, n_samples, m, float(clip[0]), float(clip[1]),
+                                                     _p(z), _stream()))
+    return z
+
+
+def points(rays_o, rays_d, z) -> torch.Tensor:
+    """pts [N,S,3] = o + d*z, only when somebody asks for it."""
+    rays_o, rays_d, z = _dev(rays_o, "rays_o"), _dev(rays_d, "rays_d"), _dev(z, "z")
+    n, s = z.shape
+    out = torch.empty(n, s, 3, device=z.device)
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.lib().b200nerf_points(_p(rays_o), _p(rays_d), _p(z), n, s, _p(out), _stream()))
+    return out
+
+
+def nerf_mlp(pk: PackedNeRF, viewdirs, *, rays_o=None, rays_d=None, z=None, pts=None) -> torch.Tensor:
+    """raw [N,S,4] = NeRF(encode(pts), encode(viewdirs)) with pts = o + d*z or explicit
+    (trainers/Trainer.py:789-806 + run_nerf_helpers.py:109-134)."""
+    viewdirs = _dev(viewdirs, "viewdirs")
+    n = viewdirs.shape[0]
+    if pts is not None:
+        pts = _dev(pts, "pts")
+        s = pts.shape[1]
+        ro = rd = zz = None
+    else:
+        ro, rd, zz = _dev(rays_o, "rays_o"), _dev(rays_d, "rays_d"), _dev(z, "z")
+        s = zz.shape[1]
+    raw = torch.empty(n, s, 4, device=viewdirs.device)
+    with torch.cuda.device(viewdirs.device):
+        _lib.check(_lib.lib().b200nerf_nerf_mlp_fwd(_p(pk.wpack), _p(pk.aux), pk.prec, _p(ro), _p(rd), _p(viewdirs), _p(zz),
+                                                    _p(pts), n, s, _p(raw), _stream()))
+    return raw
+
+
+def composite(raw, z, rays_d, white_bkgd=True, noise=None, want_alphas=True):
+    """raw2outputs -> (rgb, disp, acc, depth, weights, alphas) (trainers/sampling_trainer.py:153-230)."""
+    raw, z, rays_d = _dev(raw, "raw"), _dev(z, "z"), _dev(rays_d, "rays_d")
+    n, s = z.shape
+    dev = raw.device
+    rgb = torch.empty(n, 3, device=dev)
+    disp = torch.empty(n, device=dev)
+    acc = torch.empty(n, device=dev)
+    depth = torch.empty(n, device=dev)
+    sw = s if s > 1 else 0  # S == 1: the reference returns empty per-sample tensors
+    weights = torch.empty(n, sw, device=dev)
+    alphas = torch.empty(n, sw, device=dev) if want_alphas else None
+    nz = None if noise is None else _dev(noise, "noise")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200nerf_composite_fwd(_p(raw), _p(z), _p(rays_d), _p(nz), n, s, int(bool(white_bkgd)), _p(rgb),
+                                                     _p(disp), _p(acc), _p(depth), _p(weights) if sw else None,
+                                                     _p(alphas) if (sw and want_alphas) else None, _stream()))
+    return rgb, disp, acc, depth, weights, alphas
+
+
+def render_depthnet(dn: PackedDepthNet, nerf: PackedNeRF, rays_o, rays_d, viewdirs, n_samples: int, mode: str, std: float,
+                    radius=2.0, near=2.0, far=6.0, noise=None, want_weights=True):
+    """DepthNet branch of render_rays_test for rays on the device (nerf_utils.py:834-866), one C call."""
+    rays_o, rays_d, viewdirs = _dev(rays_o, "rays_o"), _dev(rays_d, "rays_d"), _dev(viewdirs, "viewdirs")
+    n = rays_o.shape[0]
+    dev = rays_o.device
+    if mode == "depth_only":
+        n_samples, offs = 1, None
+    elif mode == "uniform":
+        offs = uniform_grid(std, n_samples, dev) if n_samples > 1 else None
+    else:
+        if noise is None:
+            noise = torch.randn(n, n_samples - 1, device=dev)
+        offs = _dev(std * noise, "noise")
+    s = n_samples
+    mean = torch.empty(n, 1, device=dev)
+    z = torch.empty(n, s, device=dev)
+    raw = torch.empty(n, s, 4, device=dev)
+    rgb = torch.empty(n, 3, device=dev)
+    disp = torch.empty(n, device=dev)
+    acc = torch.empty(n, device=dev)
+    depth = torch.empty(n, device=dev)
+    sw = s if s > 1 else 0
+    weights = torch.empty(n, sw, device=dev) if want_weights else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200nerf_render_depthnet(
+            _p(dn.wpack), _p(dn.aux), dn.n_hidden, _p(nerf.wpack), _p(nerf.aux), nerf.prec, _p(rays_o), _p(rays_d), _p(viewdirs),
+            n, s, PLACE_MODES[mode], _p(offs), float(radius), float(near), float(far), _p(mean), _p(z), _p(raw), _p(rgb),
+            _p(disp), _p(acc), _p(depth), _p(weights) if (want_weights and sw) else None, _stream()))
+    return dict(rgb=rgb, disp=disp, acc=acc, depth=depth, weights=weights, z=z, raw=raw, z_mean=mean)
+
+
+def umma_selftest(a_bf16: torch.Tensor, b_bf16: torch.Tensor) -> torch.Tensor:
+    """D = A @ B^T through the MLP kernels' operand layout (A [128,K], B [N,K], bf16)."""
+    assert a_bf16.dtype == torch.bfloat16 and b_bf16.dtype == torch.bfloat16 and a_bf16.is_cuda
+    a, b = a_bf16.contiguous(), b_bf16.contiguous()
+    k, n = a.shape[1], b.shape[0]
+    d = torch.empty(128, n, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().b200nerf_umma_selftest(a.data_ptr(), b.data_ptr(), d.data_ptr(), k, n, _stream()))
+    return d

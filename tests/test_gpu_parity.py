@@ -1,0 +1,255 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.  Needs a B200."""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RGB_TOL = 1e-3      # north_star: rgb / depth max-abs error
+SIGMA_GUARD = 2e-3  # rays whose last sigma is this close to 0 sit on the alpha_last step function
+
+
+def cu(x):
+    return torch.as_tensor(np.asarray(x)).to(DEV)
+
+
+def scene_rays(H, W, theta=30.0, phi=-30.0, radius=4.0):
+    c2w = O.pose_spherical(theta, phi, radius)[:3, :4]
+    packed, ro, rd, _ = O.prepare_rays(H, W, O.intrinsics(H, W), c2w=c2w)
+    return c2w, packed
+
+
+# --------------------------------------------------------------------------------------------- tensor-core plumbing
+@pytest.mark.parametrize("K,N", [(16, 16), (64, 256), (128, 128), (32, 48)])
+def test_umma_selftest(lib, K, N):
+    """Operand layout, descriptors, instruction descriptor and TMEM read-back of the MLP kernels."""
+    from nerf_sampling_b200 import ops
+
+    g = torch.Generator().manual_seed(K * 1000 + N)
+    a = torch.randn(128, K, generator=g).to(torch.bfloat16).to(DEV)
+    b = torch.randn(N, K, generator=g).to(torch.bfloat16).to(DEV)
+    d = ops.umma_selftest(a, b)
+    torch.cuda.synchronize()
+    want = a.double() @ b.double().T
+    assert float((d.double() - want).abs().max()) < 1e-3 * max(1.0, float(want.abs().max()))
+
+
+# --------------------------------------------------------------------------------------------- small operators
+def test_get_rays_matches_oracle(lib):
+    from nerf_sampling_b200 import ops
+
+    for H, W in ((16, 16), (37, 53)):
+        c2w = O.pose_spherical(30.0, -30.0, 4.0)[:3, :4]
+        K = O.intrinsics(H, W)
+        ro, rd, vd = ops.get_rays(H, W, K, c2w)
+        _, oro, ord_, _ = O.prepare_rays(H, W, K, c2w=c2w)
+        packed = O.prepare_rays(H, W, K, c2w=c2w)[0]
+        assert torch.equal(ro.cpu(), oro)
+        assert float((rd.cpu() - ord_).abs().max()) <= 2e-7
+        assert float((vd.cpu() - packed[:, 8:11]).abs().max()) <= 2e-7
+
+
+def test_placement_bit_exact(lib):
+    from nerf_sampling_b200 import ops
+
+    g = load_golden("g3")
+    mean = cu(g["mean"])
+    for S in (1, 2, 3, 13, 32, 33, 64):
+        mode = "depth_only" if S == 1 else "uniform"
+        z = ops.place_samples(mean, S, mode, 0.25)
+        assert torch.equal(z.cpu(), torch.from_numpy(g[f"z_uniform_{S}"])), S
+    z = ops.place_samples(mean, 13, "gaussian", 0.3, noise=cu(g["noise"]))
+    assert torch.equal(z.cpu(), torch.from_numpy(g["z_gauss"]))
+    pts = ops.points(cu(g["rays_o"]), cu(g["rays_d"]), z)
+    assert torch.equal(pts.cpu(), torch.from_numpy(g["pts_gauss"]))
+    # a ray that misses the sphere has a NaN depth: NaN must survive the clip like torch.clip
+    m2 = mean.clone()
+    m2[0] = float("nan")
+    z = ops.place_samples(m2, 8, "uniform", 0.1)
+    assert bool(torch.isnan(z[0]).all()) and not bool(torch.isnan(z[1:]).any())
+
+
+@pytest.mark.parametrize("n,S", [(1, 2), (5, 3), (33, 8), (100, 32), (257, 64), (64, 192), (19, 1), (40, 70)])
+def test_composite_matches_oracle(lib, n, S):
+    from nerf_sampling_b200 import ops
+
+    g = torch.Generator().manual_seed(n * 7 + S)
+    raw = torch.randn(n, S, 4, generator=g) * 2
+    raw[..., 3] = torch.randn(n, S, generator=g) * 20  # mix of transparent / opaque samples
+    z = torch.sort(2 + 4 * torch.rand(n, S, generator=g), -1).values
+    if S > 2:
+        z[:, 1] = z[:, 0]  # zero-length interval, as the duplicated mean produces
+    rd = torch.randn(n, 3, generator=g)
+    for white in (True, False):
+        want = O.raw2outputs(raw, z, rd, 0.0, white)
+        rgb, disp, acc, depth, w, alphas = ops.composite(raw.to(DEV), z.to(DEV), rd.to(DEV), white)
+        for name, a, b in (("rgb", rgb, want[0]), ("acc", acc, want[2]), ("depth", depth, want[3]), ("weights", w, want[6]),
+                           ("alphas", alphas, want[5])):
+            assert a.shape == b.shape, name
+            assert float((a.cpu() - b).abs().max()) <= 2e-6 if a.numel() else True, name
+        rel = ((disp.cpu() - want[1]).abs() / want[1].abs().clamp_min(1e-10)).max()
+        assert float(rel) <= 1e-5
+    noise = torch.randn(n, S, generator=g)
+    want = O.raw2outputs(raw, z, rd, 0.5, True, noise=noise)
+    rgb, *_ = ops.composite(raw.to(DEV), z.to(DEV), rd.to(DEV), True, noise=(noise * 0.5).to(DEV))
+    if S > 1:
+        assert float((rgb.cpu() - want[0]).abs().max()) <= 2e-6
+
+
+def test_composite_empty_batch(lib):
+    from nerf_sampling_b200 import ops
+
+    rgb, disp, acc, depth, w, a = ops.composite(torch.zeros(0, 8, 4, device=DEV), torch.zeros(0, 8, device=DEV),
+                                                torch.zeros(0, 3, device=DEV))
+    assert rgb.shape == (0, 3) and w.shape == (0, 8)
+
+
+# --------------------------------------------------------------------------------------------- DepthNet
+def test_depthnet_matches_oracle_and_golden(lib, oracle_models, b200_models):
+    _, _, dn = oracle_models
+    _, _, b_dn = b200_models
+    g = load_golden("g1")
+    ro, rd = cu(g["rays_o"]).reshape(-1, 3), cu(g["rays_d"]).reshape(-1, 3)
+    with torch.no_grad():
+        z = b_dn(ro, rd)
+    assert z.shape == (ro.shape[0], 1)
+    assert float((z.cpu() - torch.from_numpy(g["z_mean"])).abs().max()) <= 2e-5
+    # ragged size (not a multiple of the 128-row tile) + a ray that misses the sphere
+    _, packed = scene_rays(37, 41)
+    ro2, rd2 = packed[:, 0:3].contiguous(), packed[:, 3:6].contiguous()
+    rd2[5] = torch.tensor([0.0, 1.0, 0.0])
+    with torch.no_grad():
+        want = O.depthnet_forward(dn, ro2, rd2)
+        got = b_dn(ro2.to(DEV), rd2.to(DEV)).cpu()
+    assert torch.isnan(want[5]) and torch.isnan(got[5])
+    ok = ~torch.isnan(want)
+    assert float((got[ok] - want[ok]).abs().max()) <= 2e-5
+
+
+def test_depthnet_bf16_mode_is_close(lib, oracle_models, b200_models):
+    from nerf_sampling_b200 import ops
+    from nerf_sampling_b200.packing import PREC_BF16, PackedDepthNet
+
+    _, _, dn = oracle_models
+    g = load_golden("g1")
+    ro, rd = cu(g["rays_o"]).reshape(-1, 3), cu(g["rays_d"]).reshape(-1, 3)
+    z = ops.depthnet_forward(PackedDepthNet(dn, DEV, PREC_BF16), ro, rd)
+    assert float((z.cpu() - torch.from_numpy(g["z_mean"])).abs().max()) <= 2e-2
+
+
+# --------------------------------------------------------------------------------------------- NeRF MLP
+def test_nerf_mlp_matches_golden_raw(lib, b200_models):
+    _, b_fine, _ = b200_models
+    g = load_golden("g1")
+    ro, rd = cu(g["rays_o"]).reshape(-1, 3), cu(g["rays_d"]).reshape(-1, 3)
+    vd = rd / torch.norm(rd, dim=-1, keepdim=True)
+    z = cu(g["z"]).reshape(-1, int(g["S"]))
+    raw = b_fine.query(vd, rays_o=ro, rays_d=rd, z=z)
+    want = torch.from_numpy(g["raw"])
+    assert raw.shape == want.shape
+    assert float((raw.cpu() - want).abs().max()) <= 1e-4
+    # explicit sample positions (the run_network entry point)
+    raw2 = b_fine.query(vd, pts=cu(g["pts"]).reshape(-1, int(g["S"]), 3))
+    assert float((raw2.cpu() - want).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("n,S", [(1, 1), (3, 5), (130, 1), (77, 13), (512, 64)])
+def test_nerf_mlp_ragged_shapes(lib, oracle_models, b200_models, n, S):
+    coarse, _, _ = oracle_models
+    b_coarse, _, _ = b200_models
+    g = torch.Generator().manual_seed(n + S)
+    pts = (torch.rand(n, S, 3, generator=g) * 8 - 4)
+    vd = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
+    with torch.no_grad():
+        want = O.run_network(pts, vd, coarse)
+    got = b_coarse.query(vd.to(DEV), pts=pts.to(DEV)).cpu()
+    assert float((got - want).abs().max()) <= 1e-4
+
+
+def test_nerf_mlp_bf16_mode(lib, oracle_models):
+    from nerf_sampling_b200 import ops
+    from nerf_sampling_b200.packing import PREC_BF16, PackedNeRF
+
+    _, fine, _ = oracle_models
+    g = load_golden("g1")
+    rd = cu(g["rays_d"]).reshape(-1, 3)
+    vd = rd / torch.norm(rd, dim=-1, keepdim=True)
+    raw = ops.nerf_mlp(PackedNeRF(fine, DEV, PREC_BF16), vd, pts=cu(g["pts"]).reshape(-1, int(g["S"]), 3))
+    err = (raw.cpu() - torch.from_numpy(g["raw"])).abs().max()
+    assert 1e-6 < float(err) < 5e-2  # plain bf16 operands: visibly lossy, but the same network
+
+
+# --------------------------------------------------------------------------------------------- whole path
+def render_b200(b200_models, H, W, S, chunk=1024 * 32, **flags):
+    from nerf_sampling_b200.nerf_pytorch import nerf_utils
+    from nerf_sampling_b200.trainers import DepthNetTrainer
+
+    b_coarse, b_fine, b_dn = b200_models
+    tr = DepthNetTrainer(dataset_type="blender", basedir="/tmp", expname="x", no_batching=True, datadir="x", half_res=True,
+                         white_bkgd=True, device=DEV, n_layers=10, layer_width=256, N_importance=128, N_samples=64,
+                         input_dims_embed=3, distance=0.1, sampling_mode="uniform", n_depth_samples=S, **flags)
+    kw = dict(network_fn=b_coarse, network_fine=b_fine, depth_network=b_dn, network_query_fn=None, N_samples=64,
+              N_importance=128, trainer=tr, white_bkgd=True, raw_noise_std=0.0, perturb=False, lindisp=True, ndc=False,
+              near=2.0, far=6.0, use_viewdirs=True, model_mode="test")
+    c2w = O.pose_spherical(30.0, -30.0, 4.0)
+    with torch.no_grad():
+        return nerf_utils.render_test(H, W, O.intrinsics(H, W), chunk=chunk, c2w=c2w[:3, :4], **kw)
+
+
+def test_render_tiny_view_matches_golden(lib, b200_models):
+    g = load_golden("g1")
+    rgb, disp, ex = render_b200(b200_models, int(g["H"]), int(g["W"]), int(g["S"]))
+    assert rgb.shape == (16, 16, 3) and disp.shape == (16, 16)
+    assert torch.equal(ex["depth_net_z_vals"].cpu() != ex["depth_net_z_vals"].cpu(), torch.zeros(16, 16, 8, dtype=torch.bool))
+    assert float((ex["depth_net_z_vals"].cpu() - torch.from_numpy(g["z"])).abs().max()) <= 2e-5
+    assert float((ex["depth_net_weights"].cpu() - torch.from_numpy(g["weights"])).abs().max()) <= RGB_TOL
+    assert float((rgb.cpu() - torch.from_numpy(g["rgb"])).abs().max()) <= RGB_TOL
+    rel = ((disp.cpu() - torch.from_numpy(g["disp"])).abs() / torch.from_numpy(g["disp"]).abs()).max()
+    assert float(rel) <= 1e-3
+
+
+def test_render_config1_matches_golden(lib, b200_models):
+    """BASELINE config #1 (200x200, 32 samples) against the reference's own output."""
+    g = load_golden("g2")
+    rgb, disp, ex = render_b200(b200_models, 200, 200, 32)
+    want = torch.from_numpy(g["rgb"])
+    err = (rgb.cpu() - want).abs().max(-1).values
+    knife = torch.from_numpy(np.abs(g["sigma_last"]) < SIGMA_GUARD).reshape(200, 200)
+    assert float(knife.float().mean()) < 0.02
+    assert float(err[~knife].max()) <= RGB_TOL, f"max err {float(err[~knife].max())}"
+    target = torch.rand(200, 200, 3, generator=torch.Generator().manual_seed(1))
+    assert abs(O.psnr(rgb.cpu(), target) - O.psnr(want, target)) <= 0.05
+    # chunk size must not change the result (the reference is chunk-invariant too)
+    rgb2, _, _ = render_b200(b200_models, 200, 200, 32, chunk=4096)
+    assert torch.equal(rgb, rgb2)
+
+
+def test_render_full_size_vs_oracle_on_device(lib, oracle_models, b200_models):
+    """BASELINE config #2 (800x800, 64 samples): oracle arithmetic evaluated by torch on the GPU (fp32, TF32 off)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    coarse, fine, dn = (O.params_to(p, DEV) for p in oracle_models)
+    H = W = 800
+    rgb, disp, ex = render_b200(b200_models, H, W, 64, chunk=H * W)
+    c2w = O.pose_spherical(30.0, -30.0, 4.0).to(DEV)
+    with torch.no_grad():
+        o = O.render_view(H, W, O.intrinsics(H, W), c2w[:3, :4], coarse, fine, dn, chunk=32768, n_depth_samples=64,
+                          sampling_mode="uniform", distance=0.1)
+    assert float((ex["depth_net_z_vals"] - o["depth_net_z_vals"]).abs().max()) <= 5e-5
+    err = (rgb - o["depth_net_rgb_map"]).abs().max(-1).values
+    knife = o["raw"][..., -1, 3].abs() < SIGMA_GUARD
+    frac = float(knife.float().mean())
+    print(f"knife-edge rays (|sigma_last| < {SIGMA_GUARD}): {int(knife.sum())} of {H * W} ({100 * frac:.3f}%); "
+          f"max rgb err elsewhere {float(err[~knife].max()):.2e}; flipped {int((err > RGB_TOL).sum())}")
+    assert frac < 0.02
+    assert float(err[~knife].max()) <= RGB_TOL
+    target = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(1)).to(DEV)
+    assert abs(O.psnr(rgb, target) - O.psnr(o["depth_net_rgb_map"], target)) <= 0.05
+    # size-independent properties: weights are a sub-probability distribution, depths sorted and clipped
+    w, z = ex["depth_net_weights"], ex["depth_net_z_vals"]
+    assert bool((w >= 0).all()) and float(w.sum(-1).max()) <= 1 + 1e-5
+    assert bool((z[..., 1:] >= z[..., :-1]).all()) and float(z.min()) >= 2.0 and float(z.max()) <= 6.0

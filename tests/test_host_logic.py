@@ -1,0 +1,269 @@
+"""CPU-only tests: C ABI surface, weight packing layout, DepthNet folding, reference known-answer tests."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import nerf_oracle as O
+
+
+# --------------------------------------------------------------------------------------------- ABI surface
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "b200nerf.h")).read()
+    names = set(re.findall(r"\b(b200nerf_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"libb200nerf.so does not export {n}"
+    from nerf_sampling_b200 import _lib
+
+    assert names == set(_lib.SIGNATURES), "ctypes signature table out of sync with include/b200nerf.h"
+    assert lib.b200nerf_version() == 100
+
+
+def test_no_cpu_fallback():
+    from nerf_sampling_b200 import _lib, ops
+
+    with pytest.raises(_lib.B200NerfError):
+        ops.composite(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3))
+
+
+# --------------------------------------------------------------------------------------------- packing
+def bf16_split(w):
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def decode_slabs(buf: torch.Tensor, n: int, kpad: int, split: bool):
+    """Inverse of the slab layout: per K16 block, hi plane [2][n/8][8][8] bf16 then lo plane."""
+    plane = n * 16
+    per = plane * (2 if split else 1)
+    u = buf.view(torch.bfloat16)
+    out_hi = torch.zeros(n, kpad, dtype=torch.bfloat16)
+    out_lo = torch.zeros(n, kpad, dtype=torch.bfloat16)
+    for k16 in range(kpad // 16):
+        blk = u[k16 * per : (k16 + 1) * per]
+        hi = blk[:plane].view(2, n // 8, 8, 8).permute(1, 2, 0, 3).reshape(n, 16)
+        out_hi[:, k16 * 16 : (k16 + 1) * 16] = hi
+        if split:
+            out_lo[:, k16 * 16 : (k16 + 1) * 16] = blk[plane:].view(2, n // 8, 8, 8).permute(1, 2, 0, 3).reshape(n, 16)
+    return out_hi, out_lo
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+def test_nerf_pack_layout(lib, oracle_models, prec):
+    from nerf_sampling_b200.packing import NERF_KEYS
+
+    _, fine, _ = oracle_models
+    host = [fine[k].contiguous() for k in NERF_KEYS]
+    arr = (C.c_void_p * 24)(*[t.data_ptr() for t in host])
+    wpack = torch.zeros(lib.b200nerf_nerf_wpack_bytes(prec), dtype=torch.uint8)
+    aux = torch.zeros(lib.b200nerf_nerf_aux_floats(), dtype=torch.float32)
+    assert lib.b200nerf_nerf_pack(C.cast(arr, C.c_void_p), prec, wpack.data_ptr(), aux.data_ptr()) == 0
+    split = prec == 1
+    per256 = 16384 if split else 8192
+    # stream order: W5[:, :63], W0, W1..W4, W5[:, 63:], W6, W7, feature (N=256); views (N=128, K=288)
+    w5 = fine["pts_linears.5.weight"]
+    want = [(w5[:, :63], 64), (fine["pts_linears.0.weight"], 64)]
+    want += [(fine[f"pts_linears.{i}.weight"], 256) for i in (1, 2, 3, 4)]
+    want += [(w5[:, 63:], 256), (fine["pts_linears.6.weight"], 256), (fine["pts_linears.7.weight"], 256),
+             (fine["feature_linear.weight"], 256)]
+    off = 0
+    for w, kpad in want:
+        nb = (kpad // 16) * per256
+        hi, lo = decode_slabs(wpack[off : off + nb], 256, kpad, split)
+        ref = torch.zeros(256, kpad)
+        ref[:, : w.shape[1]] = w
+        rh, rl = bf16_split(ref)
+        assert torch.equal(hi, rh)
+        if split:
+            assert torch.equal(lo, rl)
+            assert float((hi.float() + lo.float() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+        off += nb
+    hi, lo = decode_slabs(wpack[off:], 128, 288, split)
+    ref = torch.zeros(128, 288)
+    ref[:, :283] = fine["views_linears.0.weight"]
+    assert torch.equal(hi, bf16_split(ref)[0])
+    assert off + 18 * per256 // 2 == wpack.numel()
+    # aux block
+    assert torch.equal(aux[0:256], fine["pts_linears.0.bias"])
+    assert torch.equal(aux[1792:2048], fine["pts_linears.7.bias"])
+    assert torch.equal(aux[2048:2304], fine["feature_linear.bias"])
+    assert torch.equal(aux[2304:2432], fine["views_linears.0.bias"])
+    assert torch.equal(aux[2432:2688], fine["alpha_linear.weight"][0])
+    assert float(aux[2688]) == float(fine["alpha_linear.bias"])
+    assert torch.equal(aux[2692:3076].view(3, 128), fine["rgb_linear.weight"])
+    assert torch.equal(aux[3076:3079], fine["rgb_linear.bias"])
+
+
+def kernel_input_layout(rays_o, rays_d, radius=2.0):
+    """[enc(o)|0|enc(d)|0|enc(hit_near)|0|enc(hit_far)|0] -- the DepthNet kernel's 256-wide input."""
+    _, hits = O.sphere_intersections(rays_o, rays_d, torch.tensor([radius]))
+    z = torch.zeros(rays_o.shape[0], 1)
+    return torch.cat([O.embed(rays_o, 10), z, O.embed(rays_d, 10), z, O.embed(hits[:, 0], 10), z, O.embed(hits[:, 1], 10), z], -1)
+
+
+@pytest.mark.parametrize("widths", [([256] * 10, [256] * 10), ([128] * 6, [128, 128, 128, 128, 256]), ([64] * 2, [96])])
+def test_fold_depthnet_matches_literal_network(widths):
+    """Folding the activation-free branches into the first dense layer is exact up to fp32 round-off."""
+    from nerf_sampling_b200.packing import fold_depthnet
+
+    torch.manual_seed(3)
+    dn = O.init_depthnet(*widths)
+    H = W = 12
+    c2w = O.pose_spherical(10.0, -40.0, 4.0)[:3, :4]
+    ro, rd = O.get_rays(H, W, O.intrinsics(H, W), c2w)
+    ro, rd = ro.reshape(-1, 3).contiguous(), rd.reshape(-1, 3).contiguous()
+    rd[0] = torch.tensor([0.0, 1.0, 0.0])  # misses the sphere -> NaN depth in both
+    want = O.depthnet_forward(dn, ro, rd).double()
+    w0, b0, hidden, hw, hb = fold_depthnet(dn)
+    x = kernel_input_layout(ro, rd).double()
+    h = torch.nn.functional.leaky_relu(x @ w0.double().T + b0.double(), 0.01)
+    for w, b in hidden:
+        h = torch.nn.functional.leaky_relu(h @ w.double().T + b.double(), 0.01)
+    s = torch.sigmoid(h @ hw.double() + hb.double())
+    got = (2 * (1 - s) + 6 * s).reshape(-1, 1)
+    assert torch.isnan(want[0]) and torch.isnan(got[0])
+    assert float((want[1:] - got[1:]).abs().max()) < 2e-5
+    assert len(hidden) == len(widths[1]) - 1
+
+
+def test_depthnet_pack_roundtrip(lib):
+    from nerf_sampling_b200.packing import PackedDepthNet
+
+    torch.manual_seed(0)
+    dn = O.init_depthnet([256] * 3, [256] * 3)
+    pk = PackedDepthNet(dn, "cpu", prec=1)
+    assert pk.n_hidden == 2
+    assert pk.wpack.numel() == 3 * 16 * 16384
+    hi, lo = decode_slabs(pk.wpack[: 16 * 16384], 256, 256, True)
+    w0 = pk.folded[0]
+    assert torch.equal(hi, bf16_split(w0)[0]) and torch.equal(lo, bf16_split(w0)[1])
+    assert torch.equal(pk.aux[768:1024], pk.folded[3])  # head weights after 3 bias rows
+
+
+# --------------------------------------------------------------------------------------------- module shells
+def test_state_dict_keys_match_reference_layout(oracle_models):
+    from nerf_sampling_b200.depth_nets import DepthNet
+    from nerf_sampling_b200.nerf_pytorch.run_nerf_helpers import NeRF
+
+    coarse, fine, dn = oracle_models
+    torch.manual_seed(42)
+    a = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    b = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    d = DepthNet(hidden_sizes=[256] * 10, cat_hidden_sizes=[256] * 10, sphere_radius=2.0)
+    # same construction order => the seeded init reproduces the reference's weights bit for bit
+    for mod, sd in ((a, coarse), (b, fine), (d, dn)):
+        msd = mod.state_dict()
+        assert set(msd) == set(sd)
+        for k in sd:
+            assert torch.equal(msd[k], sd[k]), k
+    assert len(d.state_dict()) == 82 and sum(p.numel() for p in d.parameters()) == 3340545
+    assert sum(p.numel() for p in a.parameters()) == 595844
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    """save_state / load_nerf / load_depth_network keep the 200000.tar key layout (reference tests/tests.py:29-77)."""
+    from nerf_sampling_b200.depth_nets import DepthNet
+    from nerf_sampling_b200.nerf_pytorch import utils
+    from nerf_sampling_b200.nerf_pytorch.run_nerf_helpers import NeRF
+
+    mk = lambda: NeRF(D=8, W=256, input_ch=63, input_ch_views=27, skips=[4], use_viewdirs=True)  # noqa: E731
+    fn, fine, dn = mk(), mk(), DepthNet([32, 32], [32, 32])
+    opt = torch.optim.Adam(list(fn.parameters()) + list(fine.parameters()), lr=1e-3)
+    sopt = torch.optim.Adam(dn.parameters(), lr=1e-4)
+    path = str(tmp_path / "000123.tar")
+    utils.save_state(123, fn, fine, opt, dn, sopt, path)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"global_step", "network_fn_state_dict", "network_fine_state_dict", "optimizer_state_dict",
+                       "sampling_optimizer_state_dict", "depth_network"}
+    fn2, fine2, dn2 = mk(), mk(), DepthNet([32, 32], [32, 32])
+    utils.load_nerf(fn2, fine2, torch.optim.Adam(list(fn2.parameters()) + list(fine2.parameters())), ck)
+    utils.load_depth_network(dn2, torch.optim.Adam(dn2.parameters()), ck)
+    for a, b in ((fn, fn2), (fine, fine2), (dn, dn2)):
+        for (k, v), (_, v2) in zip(a.state_dict().items(), b.state_dict().items()):
+            assert torch.equal(v, v2), k
+
+
+def test_depthnet_layer_shapes():
+    """reference tests/tests.py:114-194."""
+    from nerf_sampling_b200.depth_nets import DepthNet
+
+    hidden, cat = [32, 64, 16], [24, 48]
+    d = DepthNet(hidden, cat)
+    assert d.origin_layers[0].in_features == 2 * 63 and d.intersection_layers[0].in_features == 2 * 126
+    for k in (1, 2):
+        assert d.origin_layers[k].in_features == hidden[k - 1] + 63
+        assert d.direction_layers[k].in_features == hidden[k - 1] + 63
+        assert d.intersection_layers[k].in_features == hidden[k - 1] + 126
+    assert d.cat_layers[0].in_features == 3 * hidden[-1] + 63 + 63 + 126
+    assert len(d.cat_layers) == 2 * len(cat)
+    assert isinstance(d.to_depth[0], torch.nn.Linear) and d.to_depth[0].out_features == 1
+    assert isinstance(d.to_depth[1], torch.nn.Sigmoid)
+
+
+def test_override_config_contract():
+    from nerf_sampling_b200.nerf_pytorch.utils import override_config
+
+    cfg = {"a": 1, "b": None}
+    override_config(cfg, {"b": 2})
+    assert cfg == {"a": 1, "b": 2}
+    with pytest.raises(KeyError):
+        override_config(cfg, {"c": 3})
+
+
+def test_plugin_hook_builds_trainer(tmp_path):
+    from nerf_sampling_b200.nerf_pytorch.utils import load_obj_from_config
+
+    tr = load_obj_from_config({"module": "nerf_sampling_b200.trainers.DepthNetTrainer",
+                               "kwargs": dict(dataset_type="blender", basedir=str(tmp_path), expname="e", no_batching=True,
+                                              datadir="x", half_res=True, white_bkgd=True, n_layers=10, layer_width=256,
+                                              N_importance=128, input_dims_embed=3)})
+    assert tr.lindisp is True and tr.near == 2.0 and tr.far == 6.0 and tr.chunk == 32768 and tr.netchunk == 65536
+
+
+# --------------------------------------------------------------------------------------------- reference KATs
+def nan_equal(a, b):
+    return torch.allclose(a[~torch.isnan(a)], b[~torch.isnan(b)], equal_nan=True) and torch.equal(torch.isnan(a), torch.isnan(b))
+
+
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+def test_quadratic_known_answers(impl):
+    """reference tests/tests.py:197-233."""
+    if impl == "oracle":
+        solve = O.solve_quadratic
+    else:
+        from nerf_sampling_b200.nerf_pytorch.utils import solve_quadratic_equation as solve
+    T = torch.Tensor
+    assert nan_equal(solve(T([1]), T([2]), T([1])), T([[-1], [-1]]))
+    got = solve(T([1, 4, 5, 1, 4, 5]), T([1, 4, 6, 1, 4, 6]), T([1, 1, 1, 1, 1, 1]))
+    nan = float("nan")
+    assert nan_equal(got, T([[nan, -0.5, -1, nan, -0.5, -1], [nan, -0.5, -0.2, nan, -0.5, -0.2]]))
+
+
+SPHERE_KATS = [  # (origin, direction, radius, expected hit points) -- reference tests/tests.py:236-331
+    ([-3.0, 0, 0], [1.0, 0, 0], 1.0, [[-1.0, 0, 0], [1.0, 0, 0]]),
+    ([-3.0, 0, 0], [0.0, 2.0, 0], 1.0, [[float("nan")] * 3] * 2),
+    ([-3.0, 0, 0], [-1.0, 0, 0], 1.0, [[1.0, 0, 0], [-1.0, 0, 0]]),
+    ([-3.0, 1.0, 0], [1.0, 0, 0], 1.0, [[0.0, 1.0, 0], [0.0, 1.0, 0]]),
+    ([1.0, 0, 0], [0.0, 1.0, 0], 1.0, [[1.0, 0, 0], [1.0, 0, 0]]),
+    ([0.0, 0, 0], [-1.0, 0, 0], 1.0, [[1.0, 0, 0], [-1.0, 0, 0]]),
+    ([1.0, 0, 0], [-1.0, 0, 0], 1.0, [[1.0, 0, 0], [-1.0, 0, 0]]),
+]
+
+
+@pytest.mark.parametrize("impl", ["oracle", "product"])
+@pytest.mark.parametrize("o,d,r,want", SPHERE_KATS)
+def test_sphere_intersection_known_answers(impl, o, d, r, want):
+    if impl == "oracle":
+        fn = O.sphere_intersections
+    else:
+        from nerf_sampling_b200.nerf_pytorch.utils import find_intersection_points_with_sphere as fn
+    t, pts = fn(torch.tensor([o]), torch.tensor([d]), torch.tensor([r]))
+    assert pts.shape == (1, 2, 3) and t.shape == (1, 2)
+    assert nan_equal(pts[0], torch.tensor(want))
