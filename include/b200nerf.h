@@ -121,6 +121,32 @@ int b200nerf_render_depthnet_host(const void* dn_wpack, const float* dn_aux, int
                                   int n_rays, int S, int mode, const float* offsets, float radius, float near_,
                                   float far_, void* d_ws, float* h_rgb, float* h_disp, void* stream);
 
+/* ---- vanilla hierarchical sampling (config #4 and the training target) ---------------------------------- */
+
+/* Stratified coarse depths of Trainer.sample_coarse_points (nerf_pytorch/trainers/Trainer.py:603-627).
+ * near_/far_ [n_rays], t [S] = linspace(0,1,S); lindisp != 0 samples linearly in disparity (the reference
+ * default); t_rand [n_rays,S] in [0,1) enables the stratified jitter (perturb > 0), NULL disables it. */
+int b200nerf_coarse_depths(const float* near_, const float* far_, const float* t, int n_rays, int S, int lindisp,
+                           const float* t_rand, float* out_z, void* stream);
+
+/* sample_pdf (nerf_pytorch/run_nerf_helpers.py:250-293): bins [n_rays,n_bins], weights [n_rays,n_bins-1],
+ * u = [n_samples] shared by all rays (u_per_ray == 0, the det=True linspace) or [n_rays,n_samples].
+ * out_samples [n_rays,n_samples]; out_inds (may be NULL) = the searchsorted(cdf, u, right=True) indices, int64. */
+int b200nerf_sample_pdf(const float* bins, const float* weights, const float* u, int u_per_ray, int n_rays, int n_bins,
+                        int n_samples, float* out_samples, long long* out_inds, void* stream);
+
+/* Trainer.sample_fine_points up to the network query (Trainer.py:668-686): mid-point bins of the coarse depths,
+ * inner coarse weights, inverse-CDF samples, then sort(cat([z_coarse, z_samples])) -> out_z_all
+ * [n_rays, n_coarse+n_importance].  out_samples / out_inds may be NULL. */
+int b200nerf_sample_pdf_merge(const float* z_coarse, const float* weights, const float* u, int u_per_ray, int n_rays,
+                              int n_coarse, int n_importance, float* out_samples, long long* out_inds, float* out_z_all,
+                              void* stream);
+
+/* top = weights.argmax(1) (first maximum) and the gathers that follow it (nerf_utils.py:689-690, :806-812):
+ * out_idx int64 [n_rays], out_z / out_w [n_rays], out_rgb [n_rays,3] = sigmoid(raw rgb at top) (raw may be NULL). */
+int b200nerf_argmax_gather(const float* weights, const float* z, const float* raw, int n_rays, int S, long long* out_idx,
+                           float* out_z, float* out_w, float* out_rgb, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------ */
 
 /* D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs (raw uint16), through the same shared-memory operand layout,

@@ -39,6 +39,10 @@ SIGNATURES = {
     "b200nerf_render_depthnet": (I, [P, P, I, P, P, I, P, P, P, I, I, I, P, F, F, F, P, P, P, P, P, P, P, P, P]),
     "b200nerf_render_host_ws_bytes": (SZ, [I, I]),
     "b200nerf_render_depthnet_host": (I, [P, P, I, P, P, I, P, P, I, I, I, P, F, F, F, P, P, P, P]),
+    "b200nerf_coarse_depths": (I, [P, P, P, I, I, I, P, P, P]),
+    "b200nerf_sample_pdf": (I, [P, P, P, I, I, I, I, P, P, P]),
+    "b200nerf_sample_pdf_merge": (I, [P, P, P, I, I, I, I, P, P, P, P]),
+    "b200nerf_argmax_gather": (I, [P, P, P, I, I, P, P, P, P, P]),
     "b200nerf_umma_selftest": (I, [P, P, P, I, I, P]),
 }
 

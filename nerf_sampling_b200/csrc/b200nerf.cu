@@ -6,35 +6,27 @@
 #include <vector>
 
 #include "../../include/b200nerf.h"
+#include "host_common.h"
 #include "mlp_chain.cuh"
 
 using namespace b200;
 
 // ------------------------------------------------------------------------------------------- error plumbing
 static thread_local char g_err[512] = "";
-static std::atomic<unsigned long long> g_launches{0};
+std::atomic<unsigned long long> g_b200_launches{0};
 
-static int fail(const char* fmt, ...) {
+int b200_fail(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return 1;
 }
-#define CUDA_TRY(expr)                                                                        \
-  do {                                                                                        \
-    cudaError_t e__ = (expr);                                                                 \
-    if (e__ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-  } while (0)
-#define LAUNCH_CHECK()  \
-  do {                  \
-    ++g_launches;       \
-    CUDA_TRY(cudaGetLastError()); \
-  } while (0)
+#define fail b200_fail
 
 extern "C" int b200nerf_version(void) { return B200NERF_VERSION; }
 extern "C" const char* b200nerf_last_error(void) { return g_err; }
-extern "C" unsigned long long b200nerf_launch_count(void) { return g_launches.load(); }
+extern "C" unsigned long long b200nerf_launch_count(void) { return g_b200_launches.load(); }
 
 static int sm_count() {
   static int n = 0;

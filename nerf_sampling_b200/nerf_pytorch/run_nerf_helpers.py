@@ -103,3 +103,10 @@ def get_rays(H, W, K, c2w):
     dev = c2w.device if isinstance(c2w, torch.Tensor) and c2w.is_cuda else "cuda"
     ro, rd, _ = ops.get_rays(H, W, K, c2w, dev)
     return ro.reshape(H, W, 3), rd.reshape(H, W, 3)
+
+
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
+    """Inverse-CDF sampling, signature of run_nerf_helpers.py:250-293 (``pytest`` is unusable in the reference --
+    it promotes to float64 and crashes -- and is ignored here)."""
+    u = None if det else torch.rand(list(bins.shape[:-1]) + [N_samples], device=bins.device)
+    return ops.sample_pdf(bins, weights, N_samples, u)

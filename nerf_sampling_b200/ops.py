@@ -174,6 +174,67 @@ def render_depthnet(dn: PackedDepthNet, nerf: PackedNeRF, rays_o, rays_d, viewdi
     return dict(rgb=rgb, disp=disp, acc=acc, depth=depth, weights=weights, z=z, raw=raw, z_mean=mean)
 
 
+def coarse_z(near, far, n_rays: int, n_samples: int, lindisp: bool, t_rand: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stratified coarse depths [N,S] (trainers/Trainer.py:603-627)."""
+    near, far = _dev(near, "near").reshape(-1), _dev(far, "far").reshape(-1)
+    dev = near.device
+    t = torch.linspace(0.0, 1.0, steps=n_samples, device="cpu").to(dev)  # the reference's own t grid
+    tr = None if t_rand is None else _dev(t_rand, "t_rand")
+    z = torch.empty(n_rays, n_samples, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200nerf_coarse_depths(_p(near), _p(far), _p(t), n_rays, n_samples, int(bool(lindisp)), _p(tr),
+                                                     _p(z), _stream()))
+    return z
+
+
+def _u_grid(u, n_samples, dev):
+    if u is None:  # det=True: u = linspace(0, 1, N_samples) shared by all rays (run_nerf_helpers.py:258-260)
+        return torch.linspace(0.0, 1.0, steps=n_samples, device="cpu").to(dev), 0
+    return _dev(u, "u"), 1
+
+
+def sample_pdf(bins, weights, n_samples: int, u: Optional[torch.Tensor] = None, return_inds: bool = False):
+    """Inverse-CDF samples [N,n_samples] (run_nerf_helpers.py:250-293); ``u`` [N,n_samples] overrides the det grid."""
+    bins, weights = _dev(bins, "bins"), _dev(weights, "weights")
+    n, b = bins.shape
+    uu, per_ray = _u_grid(u, n_samples, bins.device)
+    out = torch.empty(n, n_samples, device=bins.device)
+    inds = torch.empty(n, n_samples, device=bins.device, dtype=torch.int64) if return_inds else None
+    with torch.cuda.device(bins.device):
+        _lib.check(_lib.lib().b200nerf_sample_pdf(_p(bins), _p(weights), _p(uu), per_ray, n, b, n_samples, _p(out), _p(inds), _stream()))
+    return (out, inds) if return_inds else out
+
+
+def sample_pdf_merge(z_coarse, weights, n_importance: int, u: Optional[torch.Tensor] = None, return_inds: bool = False):
+    """(z_samples [N,Nf], z_all [N,Nc+Nf] sorted, inds or None) from the coarse pass (trainers/Trainer.py:668-686)."""
+    z_coarse, weights = _dev(z_coarse, "z_coarse"), _dev(weights, "weights")
+    n, sc = z_coarse.shape
+    dev = z_coarse.device
+    uu, per_ray = _u_grid(u, n_importance, dev)
+    zs = torch.empty(n, n_importance, device=dev)
+    za = torch.empty(n, sc + n_importance, device=dev)
+    inds = torch.empty(n, n_importance, device=dev, dtype=torch.int64) if return_inds else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200nerf_sample_pdf_merge(_p(z_coarse), _p(weights), _p(uu), per_ray, n, sc, n_importance, _p(zs),
+                                                        _p(inds), _p(za), _stream()))
+    return zs, za, inds
+
+
+def argmax_gather(weights, z, raw=None):
+    """(top [N,1] int64, z[top] [N,1], w[top] [N,1], sigmoid(rgb[top]) [N,3]) -- nerf_utils.py:689-690, :806-812."""
+    weights, z = _dev(weights, "weights"), _dev(z, "z")
+    n, s = weights.shape
+    dev = weights.device
+    raw = None if raw is None else _dev(raw, "raw")
+    idx = torch.empty(n, 1, device=dev, dtype=torch.int64)
+    mz = torch.empty(n, 1, device=dev)
+    mw = torch.empty(n, 1, device=dev)
+    rgb = torch.empty(n, 3, device=dev) if raw is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200nerf_argmax_gather(_p(weights), _p(z), _p(raw), n, s, _p(idx), _p(mz), _p(mw), _p(rgb), _stream()))
+    return idx, mz, mw, rgb
+
+
 def umma_selftest(a_bf16: torch.Tensor, b_bf16: torch.Tensor) -> torch.Tensor:
     """D = A @ B^T through the MLP kernels' operand layout (A [128,K], B [N,K], bf16)."""
     assert a_bf16.dtype == torch.bfloat16 and b_bf16.dtype == torch.bfloat16 and a_bf16.is_cuda

@@ -217,7 +217,7 @@ def solve_quadratic(a, b, c):
 def sphere_intersections(origin, direction, radius: torch.Tensor):
     """Line/sphere hits, centre 0 (nerf_pytorch/utils.py:182-217). Returns t [n,2], pts [n,2,3]."""
     b = 2 * (direction * origin).sum(dim=1)
-    c = torch.norm(origin, dim=1) ** 2 - radius.T**2
+    c = torch.norm(origin, dim=1) ** 2 - radius**2  # (reference writes radius.T: a no-op on a 1-D tensor)
     a = (direction * direction).sum(dim=1)
     t = solve_quadratic(a, b, c).T
     pts = origin.unsqueeze(1) + t.unsqueeze(2) * direction.unsqueeze(1)

@@ -10,7 +10,7 @@ from oracle import nerf_oracle as O
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 RGB_TOL = 1e-3      # north_star: rgb / depth max-abs error
-SIGMA_GUARD = 2e-3  # rays whose last sigma is this close to 0 sit on the alpha_last step function
+SIGMA_GUARD = 1e-5  # rays whose last sigma is this close to 0 sit on the alpha_last step function
 
 
 def cu(x):
@@ -219,7 +219,7 @@ def test_render_config1_matches_golden(lib, b200_models):
     want = torch.from_numpy(g["rgb"])
     err = (rgb.cpu() - want).abs().max(-1).values
     knife = torch.from_numpy(np.abs(g["sigma_last"]) < SIGMA_GUARD).reshape(200, 200)
-    assert float(knife.float().mean()) < 0.02
+    assert float(knife.float().mean()) < 0.002
     assert float(err[~knife].max()) <= RGB_TOL, f"max err {float(err[~knife].max())}"
     target = torch.rand(200, 200, 3, generator=torch.Generator().manual_seed(1))
     assert abs(O.psnr(rgb.cpu(), target) - O.psnr(want, target)) <= 0.05
@@ -245,7 +245,7 @@ def test_render_full_size_vs_oracle_on_device(lib, oracle_models, b200_models):
     frac = float(knife.float().mean())
     print(f"knife-edge rays (|sigma_last| < {SIGMA_GUARD}): {int(knife.sum())} of {H * W} ({100 * frac:.3f}%); "
           f"max rgb err elsewhere {float(err[~knife].max()):.2e}; flipped {int((err > RGB_TOL).sum())}")
-    assert frac < 0.02
+    assert frac < 0.002
     assert float(err[~knife].max()) <= RGB_TOL
     target = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(1)).to(DEV)
     assert abs(O.psnr(rgb, target) - O.psnr(o["depth_net_rgb_map"], target)) <= 0.05
@@ -253,3 +253,97 @@ def test_render_full_size_vs_oracle_on_device(lib, oracle_models, b200_models):
     w, z = ex["depth_net_weights"], ex["depth_net_z_vals"]
     assert bool((w >= 0).all()) and float(w.sum(-1).max()) <= 1 + 1e-5
     assert bool((z[..., 1:] >= z[..., :-1]).all()) and float(z.min()) >= 2.0 and float(z.max()) <= 6.0
+
+
+# --------------------------------------------------------------------------------------------- vanilla hierarchical path
+def test_coarse_depths_bit_exact(lib):
+    from nerf_sampling_b200 import ops
+
+    g = load_golden("g4")
+    n = g["z_coarse"].shape[0]
+    near, far = torch.full((n, 1), 2.0, device=DEV), torch.full((n, 1), 6.0, device=DEV)
+    z = ops.coarse_z(near, far, n, 64, True)
+    assert torch.equal(z.cpu(), torch.from_numpy(g["z_coarse"]))
+    for lindisp in (True, False):
+        tr = torch.rand(n, 64, generator=torch.Generator().manual_seed(5))
+        want = O.coarse_z(near.cpu(), far.cpu(), n, 64, lindisp, t_rand=tr)
+        got = ops.coarse_z(near, far, n, 64, lindisp, tr.to(DEV))
+        assert torch.equal(got.cpu(), want), lindisp
+
+
+def test_sample_pdf_indices_bit_exact_on_reference_inputs(lib):
+    """Integer-derived outputs: searchsorted indices on the reference's own (bins, weights)."""
+    from nerf_sampling_b200 import ops
+
+    g = load_golden("g4")
+    zc, wc = cu(g["z_coarse"]), cu(g["weights_coarse"])
+    zs, z_all, inds = ops.sample_pdf_merge(zc, wc, 128, return_inds=True)
+    want_inds = torch.from_numpy(g["inds"])
+    mism = int((inds.cpu() != want_inds).sum())
+    print(f"sample_pdf index mismatches: {mism} of {want_inds.numel()}")
+    assert mism == 0
+    assert float((zs.cpu() - torch.from_numpy(g["z_samples"])).abs().max()) <= 2e-6
+    assert float((z_all.cpu() - torch.from_numpy(g["z_fine"])).abs().max()) <= 2e-6
+    assert bool((z_all[:, 1:] >= z_all[:, :-1]).all())
+    # generic entry point (bins, weights) + random u (unsorted samples)
+    mid = 0.5 * (zc[:, 1:] + zc[:, :-1])
+    u = torch.rand(zc.shape[0], 40, generator=torch.Generator().manual_seed(9))
+    want, wi = O.sample_pdf(mid.cpu(), wc[:, 1:-1].cpu(), 40, u=u, return_inds=True)
+    got, gi = ops.sample_pdf(mid, wc[:, 1:-1].contiguous(), 40, u=u.to(DEV), return_inds=True)
+    assert int((gi.cpu() != wi).sum()) == 0
+    assert float((got.cpu() - want).abs().max()) <= 2e-6
+    _, za, _ = ops.sample_pdf_merge(zc, wc, 40, u=u.to(DEV))
+    want_all = torch.sort(torch.cat([zc.cpu(), want], -1), -1).values
+    assert float((za.cpu() - want_all).abs().max()) <= 2e-6
+
+
+def test_argmax_gather(lib):
+    from nerf_sampling_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    w = torch.rand(300, 192, generator=g)
+    w[5, 10] = w[5, 100] = 2.0      # tie -> first index
+    w[6] = 0.0                      # all equal -> index 0
+    z = torch.rand(300, 192, generator=g)
+    raw = torch.randn(300, 192, 4, generator=g)
+    idx, mz, mw, rgb = ops.argmax_gather(w.to(DEV), z.to(DEV), raw.to(DEV))
+    top = w.argmax(dim=1, keepdim=True)
+    assert torch.equal(idx.cpu(), top)
+    assert torch.equal(mz.cpu(), torch.gather(z, 1, top)) and torch.equal(mw.cpu(), torch.gather(w, 1, top))
+    want_rgb = torch.gather(torch.sigmoid(raw[..., :3]), 1, top.unsqueeze(-1).expand(-1, 1, 3)).squeeze(1)
+    assert float((rgb.cpu() - want_rgb).abs().max()) <= 1e-6
+
+
+def test_full_nerf_and_max_pts_modes_match_golden(lib, b200_models):
+    """render.py -nf / -nm: vanilla 64 + 128 hierarchical render (config #4 shape) against the reference."""
+    g = load_golden("g4")
+    H = W = int(g["H"])
+    rgb, disp, ex = render_b200(b200_models, H, W, 32, use_full_nerf=True)
+    assert float((ex["depth_net_z_vals"].reshape(-1, 192).cpu() - torch.from_numpy(g["z_fine"])).abs().max()) <= 1e-4
+    assert float((ex["depth_net_weights"].reshape(-1, 192).cpu() - torch.from_numpy(g["weights_fine"])).abs().max()) <= RGB_TOL
+    assert float((rgb.reshape(-1, 3).cpu() - torch.from_numpy(g["rgb"])).abs().max()) <= RGB_TOL
+    rgb_m, disp_m, ex_m = render_b200(b200_models, H, W, 32, use_nerf_max_pts=True)
+    assert float((ex_m["max_z_vals"].reshape(-1, 1).cpu() - torch.from_numpy(g["max_z"])).abs().max()) <= 1e-4
+    assert float((rgb_m.reshape(-1, 3).cpu() - torch.from_numpy(g["max_rgb"])).abs().max()) <= RGB_TOL
+    assert float(disp_m.abs().max()) == 0.0
+
+
+def test_training_render_forward_matches_golden(lib, b200_models):
+    """render_rays (train mode, perturb=0): arg-max target depth, DepthNet depth and the 1-sample colour."""
+    from nerf_sampling_b200.nerf_pytorch import nerf_utils
+    from nerf_sampling_b200.trainers import DepthNetTrainer
+
+    g = load_golden("g5")
+    b_coarse, b_fine, b_dn = b200_models
+    tr = DepthNetTrainer(dataset_type="blender", basedir="/tmp", expname="x", no_batching=True, datadir="x", half_res=True,
+                         white_bkgd=True, device=DEV, n_layers=10, layer_width=256, N_importance=128, N_samples=64,
+                         input_dims_embed=3, perturb=0.0)
+    kw = dict(network_fn=b_coarse, network_fine=b_fine, depth_network=b_dn, network_query_fn=None, N_samples=64,
+              N_importance=128, trainer=tr, white_bkgd=True, raw_noise_std=0.0, perturb=0.0, lindisp=True, ndc=False, near=2.0,
+              far=6.0, use_viewdirs=True, model_mode="train")
+    with torch.no_grad():
+        rgb, disp, ex = nerf_utils.render(800, 800, O.intrinsics(800, 800), rays=(cu(g["rays_o"]), cu(g["rays_d"])), retraw=True, **kw)
+    assert float((ex["depth_net_z_vals"].cpu() - torch.from_numpy(g["z_dn"])).abs().max()) <= 2e-5
+    assert float((ex["max_z_vals"].cpu() - torch.from_numpy(g["max_z"])).abs().max()) <= 1e-4
+    assert float((rgb.cpu() - torch.from_numpy(g["rgb"])).abs().max()) <= RGB_TOL
+    assert float(disp.min()) == 1e10  # S == 1 quirk
