@@ -175,7 +175,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--prec", default="split", choices=["split", "bf16"])
+    ap.add_argument("--prec", default="fast", choices=["fast", "fp16", "split", "bf16"],
+                    help="NeRF MLP precision: fast = fp16 single-pass + split-precision guard band (meets the 1e-3 contract), "
+                         "fp16 = single-pass only, split = bf16 hi+lo everywhere, bf16 = legacy single-pass on the exact kernel")
     ap.add_argument("--ref-rays", type=int, default=4096, help="rays per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -191,7 +193,9 @@ def main():
 
     import nerf_sampling_b200 as pkg
     from nerf_sampling_b200 import _lib, ops
-    from nerf_sampling_b200.packing import PREC_BF16, PREC_SPLIT
+    import ctypes as C
+
+    from nerf_sampling_b200.packing import PREC_BF16, PREC_FAST, PREC_FP16, PREC_SPLIT
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -200,10 +204,13 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    prec = PREC_SPLIT if args.prec == "split" else PREC_BF16
+    prec = {"fast": PREC_FAST, "fp16": PREC_FP16, "split": PREC_SPLIT, "bf16": PREC_BF16}[args.prec]
+    dn_prec = PREC_BF16 if prec == PREC_BF16 else PREC_SPLIT   # z feeds the 2^9 octave: DepthNet always runs split
     L = _lib.lib()
     coarse, fine, dn = build_models(dev, prec)
+    dn.precision = dn_prec
     pk_dn, pk_nerf = dn.packed(), fine.packed()
+    model = pk_nerf.c_model()
     K = intrinsics()
     n_rays = H * W
     total_steps = args.warmup + args.steps
@@ -219,6 +226,7 @@ def main():
     acc = torch.empty(n_rays, device=dev)
     depth = torch.empty(n_rays, device=dev)
     weights = torch.empty(n_rays, S, device=dev)
+    guard = torch.zeros(n_rays + 4, dtype=torch.int32, device=dev)
     tile = torch.empty(n_rays, 4, device=dev)
     gathered = torch.empty(world * n_rays, 4, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -231,15 +239,15 @@ def main():
         e = [ev() for _ in range(5)] if timed else None
         if timed:
             e[0].record()
-        _lib.check(L.b200nerf_depthnet_fwd(pk_dn.wpack.data_ptr(), pk_dn.aux.data_ptr(), pk_dn.n_hidden, prec, ro.data_ptr(), rd.data_ptr(),
+        _lib.check(L.b200nerf_depthnet_fwd(pk_dn.wpack.data_ptr(), pk_dn.aux.data_ptr(), pk_dn.n_hidden, dn_prec, ro.data_ptr(), rd.data_ptr(),
                                            n_rays, 2.0, 2.0, 6.0, mean.data_ptr(), st))
         if timed:
             e[1].record()
         _lib.check(L.b200nerf_place_samples(mean.data_ptr(), grid.data_ptr(), n_rays, S, 1, 2.0, 6.0, z.data_ptr(), st))
         if timed:
             e[2].record()
-        _lib.check(L.b200nerf_nerf_mlp_fwd(pk_nerf.wpack.data_ptr(), pk_nerf.aux.data_ptr(), prec, ro.data_ptr(), rd.data_ptr(), vd.data_ptr(),
-                                           z.data_ptr(), None, n_rays, S, raw.data_ptr(), st))
+        _lib.check(L.b200nerf_nerf_query(C.byref(model), ro.data_ptr(), rd.data_ptr(), vd.data_ptr(), z.data_ptr(), None, n_rays, S,
+                                         guard.data_ptr(), raw.data_ptr(), st))
         if timed:
             e[3].record()
         _lib.check(L.b200nerf_composite_fwd(raw.data_ptr(), z.data_ptr(), rd.data_ptr(), None, n_rays, S, 1, rgb.data_ptr(), disp.data_ptr(),
@@ -294,8 +302,8 @@ def main():
     ws = torch.empty(L.b200nerf_render_host_ws_bytes(n_rays, S), dtype=torch.uint8, device=dev)
 
     def e2e_step():
-        _lib.check(L.b200nerf_render_depthnet_host(pk_dn.wpack.data_ptr(), pk_dn.aux.data_ptr(), pk_dn.n_hidden, pk_nerf.wpack.data_ptr(),
-                                                   pk_nerf.aux.data_ptr(), prec, h_ro.data_ptr(), h_rd.data_ptr(), n_rays, S, 1, grid.data_ptr(),
+        _lib.check(L.b200nerf_render_depthnet_host(pk_dn.wpack.data_ptr(), pk_dn.aux.data_ptr(), pk_dn.n_hidden, dn_prec, C.byref(model),
+                                                   h_ro.data_ptr(), h_rd.data_ptr(), n_rays, S, 1, grid.data_ptr(),
                                                    2.0, 2.0, 6.0, ws.data_ptr(), h_rgb.data_ptr(), h_disp.data_ptr(), st))
 
     e2e_step()
@@ -316,7 +324,8 @@ def main():
         line = {
             "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x2-split (bf16 hi+lo operands, fp32 accumulate)" if prec == PREC_SPLIT else "bf16",
+            "dtype": {PREC_FAST: "fp16 operands, fp32 accumulate (+ bf16 hi/lo split re-evaluation of the guard band)",
+                      PREC_FP16: "fp16", PREC_SPLIT: "bf16x2-split (bf16 hi+lo operands, fp32 accumulate)", PREC_BF16: "bf16"}[prec],
             "data": "synthetic",
             "config": {"workload": f"800x800 lego-shaped view per GPU, DepthNet + {S} uniform samples/ray, 8x256 skip@4 NeRF "
                                    "(BASELINE config #2; #3 for N>1: one 640,000-ray slice of the view batch per rank)",
@@ -327,11 +336,15 @@ def main():
                     "api": "b200nerf_render_depthnet_host (pinned host rays -> host rgb+disp)", "steps": n_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "mlp_chain_kernel<SPLIT,NERF> (b200nerf_nerf_mlp_fwd)", "achieved": mlp_tflops,
+            "roofline": {"bound": "tensor",
+                         "kernel": ("nerf_fast_kernel<2,fp16> (+ mlp_chain_kernel<SPLIT> over the guard band) via b200nerf_nerf_query"
+                                    if prec in (PREC_FAST, PREC_FP16) else "mlp_chain_kernel<NERF> via b200nerf_nerf_query"),
+                         "achieved": mlp_tflops,
                          "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tf_sustained"], "traffic": None,
                          "peak_source": pk["src"] + ", sustained bf16", "ms_per_launch": k_ms[2],
                          "algorithmic_flop_per_point": NERF_FLOP_PER_POINT,
-                         "executed_mma_tflops": mlp_tflops * (3 if prec == PREC_SPLIT else 1) * (1_187_840 / 1_186_816)},
+                         "executed_mma_tflops": mlp_tflops * (3 if prec == PREC_SPLIT else 1) * (1_187_840 / 1_186_816),
+                         "guard_band_points_last_step": int(guard[0]) if prec == PREC_FAST else None},
             "roofline_composite": {"bound": "hbm", "kernel": "composite_kernel<32>", "achieved": comp_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                    "frac": comp_gbs / pk["hbm"], "ms_per_launch": k_ms[3], "bytes_per_ray": COMPOSITE_BYTES_PER_RAY},
             "kernel_ms": {"depthnet": k_ms[0], "place": k_ms[1], "nerf_mlp": k_ms[2], "composite": k_ms[3]},

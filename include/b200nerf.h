@@ -28,6 +28,18 @@ extern "C" {
 /* precision of the tensor-core MLPs */
 #define B200NERF_PREC_SPLIT 1 /* bf16 hi+lo operands, 3 MMAs / K16 block, ~16 mantissa bits (parity mode) */
 #define B200NERF_PREC_BF16 0  /* plain bf16 operands, 1 MMA / K16 block (PSNR-level parity only)           */
+#define B200NERF_PREC_FP16 2  /* plain fp16 operands, 1 MMA / K16 block, throughput kernel (PSNR-level parity)  */
+#define B200NERF_PREC_FAST 3  /* PREC_FP16 + split-precision re-evaluation of the guard band
+                                 (b200nerf_nerf_mlp_guarded_fwd): meets the 1e-3 max-abs contract          */
+
+/* A packed NeRF on the device, as the fused render entry points take it. */
+typedef struct b200nerf_nerf_model {
+  const void* wpack;      /* slab stream of b200nerf_nerf_pack (SPLIT or BF16); NULL for PREC_FP16          */
+  const void* wpack_fast; /* slab stream of b200nerf_nerf_pack_fast; NULL for SPLIT / BF16                   */
+  const float* aux;       /* fp32 bias / head block                                                          */
+  int prec;               /* B200NERF_PREC_*                                                                 */
+  float guard_kappa;      /* PREC_FAST: guard-band width (relative to sum |h7 * w_alpha|)                    */
+} b200nerf_nerf_model;
 
 /* sample placement modes (nerf_pytorch/utils.py:220-244) */
 #define B200NERF_PLACE_DEPTH_ONLY 0
@@ -95,6 +107,33 @@ int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int prec, const f
                           const float* viewdirs, const float* z, const float* pts, int n_rays, int S, float* out_raw,
                           void* stream);
 
+/* Single-pass 16-bit image of the same 24 NeRF tensors for the fast kernel (prec = FP16 or BF16):
+ * b200nerf_nerf_fast_wpack_bytes() bytes; the fp32 bias/head block is the `h_aux` of b200nerf_nerf_pack. */
+size_t b200nerf_nerf_fast_wpack_bytes(void);
+int b200nerf_nerf_pack_fast(const float* const* h_tensors, int prec, void* h_wpack);
+
+/* Same operator as b200nerf_nerf_mlp_fwd on the throughput kernel: two 128-row tiles per SM ping-pong between the
+ * tensor core and the epilogue warps, SMs paired as 2-CTA clusters (tcgen05 cta_group::2), one MMA per K16 block.
+ * Guard band (optional, guard_count != NULL): every LAST sample of a ray whose |sigma| < guard_kappa * sum|h7*w_alpha|
+ * is appended to guard_list (int point indices, at most guard_cap) and counted in guard_count[0] (zeroed by the
+ * caller) -- those are the samples whose sign raw2outputs turns into a step function (dist = 1e10,
+ * trainers/sampling_trainer.py:178-180). */
+int b200nerf_nerf_mlp_fast_fwd(const void* wpack_fast, const float* aux, int prec, const float* rays_o,
+                               const float* rays_d, const float* viewdirs, const float* z, const float* pts, int n_rays,
+                               int S, float* out_raw, int* guard_count, int* guard_list, int guard_cap, float guard_kappa,
+                               void* stream);
+
+/* Fast pass + split-precision re-evaluation of the guard band, in place: the result meets the reference within
+ * 1e-3 max-abs like PREC_SPLIT at ~1/3 of the tensor work.  ws_guard: n_rays + 4 ints of device workspace. */
+int b200nerf_nerf_mlp_guarded_fwd(const void* wpack_fast, const void* wpack_split, const float* aux, int prec,
+                                  const float* rays_o, const float* rays_d, const float* viewdirs, const float* z,
+                                  const float* pts, int n_rays, int S, float guard_kappa, int* ws_guard, float* out_raw,
+                                  void* stream);
+
+/* Precision dispatch over the three entry points above.  ws_guard (n_rays + 4 ints) is needed for PREC_FAST only. */
+int b200nerf_nerf_query(const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d, const float* viewdirs,
+                        const float* z, const float* pts, int n_rays, int S, int* ws_guard, float* out_raw, void* stream);
+
 /* DepthNetTrainer.raw2outputs (trainers/sampling_trainer.py:153-230, raw2alpha nerf_utils.py:27-42).
  * raw [n_rays,S,4], z [n_rays,S], rays_d [n_rays,3], noise [n_rays,S] or NULL (already scaled by raw_noise_std).
  * Outputs: rgb [n_rays,3], disp/acc/depth [n_rays], weights/alphas [n_rays,S] (each may be NULL).
@@ -105,19 +144,21 @@ int b200nerf_composite_fwd(const float* raw, const float* z, const float* rays_d
 
 /* render_rays_test, DepthNet mode (nerf_utils.py:736-876): depthnet -> place -> encode+MLP -> composite for
  * n_rays rays already on the device.  ws_z [n_rays,S] and ws_raw [n_rays,S,4] are caller-provided workspaces
- * that double as the `depth_net_z_vals` / `raw` extras; out_weights may be NULL. */
-int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_aux, int dn_hidden, const void* nerf_wpack,
-                             const float* nerf_aux, int prec, const float* rays_o, const float* rays_d,
+ * that double as the `depth_net_z_vals` / `raw` extras; ws_guard = n_rays + 4 ints (PREC_FAST only, else may be
+ * NULL); out_weights may be NULL.  dn_prec is the DepthNet's precision (SPLIT or BF16). */
+int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_aux, int dn_hidden, int dn_prec,
+                             const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d,
                              const float* viewdirs, int n_rays, int S, int mode, const float* offsets, float radius,
-                             float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, float* out_rgb,
-                             float* out_disp, float* out_acc, float* out_depth, float* out_weights, void* stream);
+                             float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, int* ws_guard,
+                             float* out_rgb, float* out_disp, float* out_acc, float* out_depth, float* out_weights,
+                             void* stream);
 
 /* Same, through host memory: copies h_rays_o / h_rays_d ([n_rays,3] each, ideally pinned) to the device
  * workspace, renders, copies rgb [n_rays,3] and disp [n_rays] back and synchronises `stream`.
  * d_ws must hold b200nerf_render_host_ws_bytes(n_rays, S) bytes. */
 size_t b200nerf_render_host_ws_bytes(int n_rays, int S);
-int b200nerf_render_depthnet_host(const void* dn_wpack, const float* dn_aux, int dn_hidden, const void* nerf_wpack,
-                                  const float* nerf_aux, int prec, const float* h_rays_o, const float* h_rays_d,
+int b200nerf_render_depthnet_host(const void* dn_wpack, const float* dn_aux, int dn_hidden, int dn_prec,
+                                  const b200nerf_nerf_model* nerf, const float* h_rays_o, const float* h_rays_d,
                                   int n_rays, int S, int mode, const float* offsets, float radius, float near_,
                                   float far_, void* d_ws, float* h_rgb, float* h_disp, void* stream);
 

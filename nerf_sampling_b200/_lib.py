@@ -35,16 +35,27 @@ SIGNATURES = {
     "b200nerf_place_samples": (I, [P, P, I, I, I, F, F, P, P]),
     "b200nerf_points": (I, [P, P, P, I, I, P, P]),
     "b200nerf_nerf_mlp_fwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P]),
+    "b200nerf_nerf_fast_wpack_bytes": (SZ, []),
+    "b200nerf_nerf_pack_fast": (I, [P, I, P]),
+    "b200nerf_nerf_mlp_fast_fwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, P, I, F, P]),
+    "b200nerf_nerf_mlp_guarded_fwd": (I, [P, P, P, I, P, P, P, P, P, I, I, F, P, P, P]),
     "b200nerf_composite_fwd": (I, [P, P, P, P, I, I, I, P, P, P, P, P, P, P]),
-    "b200nerf_render_depthnet": (I, [P, P, I, P, P, I, P, P, P, I, I, I, P, F, F, F, P, P, P, P, P, P, P, P, P]),
+    "b200nerf_nerf_query": (I, [P, P, P, P, P, P, I, I, P, P, P]),
+    "b200nerf_render_depthnet": (I, [P, P, I, I, P, P, P, P, I, I, I, P, F, F, F, P, P, P, P, P, P, P, P, P, P]),
     "b200nerf_render_host_ws_bytes": (SZ, [I, I]),
-    "b200nerf_render_depthnet_host": (I, [P, P, I, P, P, I, P, P, I, I, I, P, F, F, F, P, P, P, P]),
+    "b200nerf_render_depthnet_host": (I, [P, P, I, I, P, P, P, I, I, I, P, F, F, F, P, P, P, P]),
     "b200nerf_coarse_depths": (I, [P, P, P, I, I, I, P, P, P]),
     "b200nerf_sample_pdf": (I, [P, P, P, I, I, I, I, P, P, P]),
     "b200nerf_sample_pdf_merge": (I, [P, P, P, I, I, I, I, P, P, P, P]),
     "b200nerf_argmax_gather": (I, [P, P, P, I, I, P, P, P, P, P]),
     "b200nerf_umma_selftest": (I, [P, P, P, I, I, P]),
 }
+
+
+class NerfModel(C.Structure):
+    """``b200nerf_nerf_model`` of include/b200nerf.h."""
+
+    _fields_ = [("wpack", P), ("wpack_fast", P), ("aux", P), ("prec", I), ("guard_kappa", F)]
 
 
 class B200NerfError(RuntimeError):

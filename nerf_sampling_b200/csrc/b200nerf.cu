@@ -8,6 +8,8 @@
 #include "../../include/b200nerf.h"
 #include "host_common.h"
 #include "mlp_chain.cuh"
+#include "mlp_fast.cuh"
+#include <cuda.h>
 
 using namespace b200;
 
@@ -115,6 +117,74 @@ extern "C" int b200nerf_nerf_pack(const float* const* t, int prec, void* h_wpack
   h_aux[NERF_BA] = Ba[0];
   memcpy(h_aux + NERF_WR, Wr, 384 * sizeof(float));
   memcpy(h_aux + NERF_BR, Br, 3 * sizeof(float));
+  return 0;
+}
+
+
+// ---- single-pass 16-bit image for nerf_fast_kernel (mlp_fast.cuh) ------------------------------------------
+static inline uint16_t f2h(float f) {  // fp32 -> fp16, round to nearest even, subnormals and overflow handled
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  u &= 0x7fffffffu;
+  if (u > 0x7f800000u) return static_cast<uint16_t>(sign | 0x7e00u);   // NaN
+  if (u >= 0x477ff000u) return static_cast<uint16_t>(sign | 0x7c00u);  // rounds to >= 65520 -> inf
+  if (u < 0x33000001u) return static_cast<uint16_t>(sign);             // < 2^-25 -> 0
+  int e = static_cast<int>(u >> 23) - 127;
+  uint32_t m = (u & 0x7fffffu) | 0x800000u;
+  int shift = 13;
+  if (e < -14) {
+    shift += -14 - e;
+    e = -15;
+  }
+  uint32_t r = m >> shift;
+  const uint32_t rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+  if (rem > half || (rem == half && (r & 1u))) ++r;
+  // r carries the implicit bit for normals (bit 10); adding the biased exponent absorbs mantissa carries
+  return static_cast<uint16_t>(sign | (static_cast<uint32_t>(e + 15) << 10) + (e == -15 ? r : r - 0x400u));
+}
+
+// W [N, ldw] fp32, columns [col0, col0+K) zero-padded to Kpad -> Kpad/16 slabs.  One slab = two pieces (output rows
+// 0..N/2-1 and N/2..N-1, one per CTA of a pair); one piece = [2 k chunks][N/16 row groups][8 rows][8 k] 16-bit.
+static uint8_t* pack_linear_fast(const float* W, int N, int K, int ldw, int col0, int Kpad, bool fp16, uint8_t* out) {
+  const int half = N / 2;
+  for (int k16 = 0; k16 < Kpad / 16; ++k16) {
+    for (int r = 0; r < 2; ++r) {
+      uint16_t* dst = reinterpret_cast<uint16_t*>(out);
+      for (int kc = 0; kc < 2; ++kc)
+        for (int n = 0; n < half; ++n)
+          for (int e = 0; e < 8; ++e) {
+            const int k = k16 * 16 + kc * 8 + e;
+            const float w = k < K ? W[static_cast<size_t>(r * half + n) * ldw + col0 + k] : 0.f;
+            dst[static_cast<size_t>(kc) * half * 8 + static_cast<size_t>(n >> 3) * 64 + (n & 7) * 8 + e] = fp16 ? f2h(w) : f2bf(w);
+          }
+      out += static_cast<size_t>(half) * 32;
+    }
+  }
+  return out;
+}
+
+extern "C" size_t b200nerf_nerf_fast_wpack_bytes(void) { return fast::WPACK_BYTES; }
+
+extern "C" int b200nerf_nerf_pack_fast(const float* const* t, int prec, void* h_wpack) {
+  if (!t || !h_wpack) return fail("b200nerf_nerf_pack_fast: null argument");
+  if (prec != B200NERF_PREC_FP16 && prec != B200NERF_PREC_BF16) return fail("b200nerf_nerf_pack_fast: prec must be FP16 or BF16");
+  const bool fp16 = prec == B200NERF_PREC_FP16;
+  uint8_t* o = static_cast<uint8_t*>(h_wpack);
+  const float* W[8];
+  for (int i = 0; i < 8; ++i) W[i] = t[2 * i];
+  const float *Wv = t[16], *Wf = t[18];
+  o = pack_linear_fast(W[0], 256, 63, 63, 0, 64, fp16, o);              // step 0: pts_linears.0 over gamma(pts)
+  for (int i = 1; i <= 4; ++i) o = pack_linear_fast(W[i], 256, 256, 256, 0, 256, fp16, o);
+  o = pack_linear_fast(W[5], 256, 256, 319, 63, 256, fp16, o);          // step 5: hidden columns first ...
+  o = pack_linear_fast(W[5], 256, 63, 319, 0, 64, fp16, o);             //         ... then the re-concatenated gamma(pts)
+  o = pack_linear_fast(W[6], 256, 256, 256, 0, 256, fp16, o);
+  o = pack_linear_fast(W[7], 256, 256, 256, 0, 256, fp16, o);
+  o = pack_linear_fast(Wf, 256, 256, 256, 0, 256, fp16, o);             // step 8: feature_linear
+  o = pack_linear_fast(Wv, 128, 256, 283, 0, 256, fp16, o);             // step 9: views_linears.0, feature columns ...
+  o = pack_linear_fast(Wv, 128, 27, 283, 256, 32, fp16, o);             //         ... then gamma(viewdir)
+  if (static_cast<size_t>(o - static_cast<uint8_t*>(h_wpack)) != fast::WPACK_BYTES)
+    return fail("b200nerf_nerf_pack_fast: internal size mismatch");
   return 0;
 }
 
@@ -458,14 +528,10 @@ static Step make_step(int a_begin, int n_k16, int n, int acc_col, int accumulate
   return s;
 }
 
-extern "C" int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,
-                                     const float* viewdirs, const float* z, const float* pts, int n_rays, int S, float* out_raw,
-                                     void* stream) {
-  if (n_rays < 0 || S < 1) return fail("b200nerf_nerf_mlp_fwd: bad sizes n_rays=%d S=%d", n_rays, S);
-  if (n_rays == 0) return 0;
-  if (!wpack || !aux || !viewdirs || !out_raw) return fail("b200nerf_nerf_mlp_fwd: null argument");
-  if (!pts && (!z || !rays_o || !rays_d)) return fail("b200nerf_nerf_mlp_fwd: need pts or (rays_o, rays_d, z)");
-  if (static_cast<long long>(n_rays) * S > 0x7fffff00LL) return fail("b200nerf_nerf_mlp_fwd: too many points for one call");
+// row_index / n_rows_dev != nullptr: evaluate only the listed sample points (at most list_cap of them), in place
+static int nerf_chain_launch(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,
+                             const float* viewdirs, const float* z, const float* pts, int n_rays, int S, float* out_raw,
+                             const int* row_index, const int* n_rows_dev, int list_cap, cudaStream_t st) {
   ChainParams p;
   memset(&p, 0, sizeof(p));
   p.wpack = static_cast<const uint8_t*>(wpack);
@@ -481,7 +547,7 @@ extern "C" int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int pr
   p.steps[n++] = make_step(0, 16, 256, 0, 0, 1, EPI_STORE, ACT_NONE, NERF_BF);        // feature_linear (no activation)
   p.steps[n++] = make_step(0, 18, 128, 0, 0, 1, EPI_NERF_OUT, ACT_RELU, NERF_BV);     // views_linears.0 + rgb_linear
   p.n_steps = n;
-  p.n_rows = n_rays * S;
+  p.n_rows = row_index ? list_cap : n_rays * S;
   p.S = S;
   p.rays_o = rays_o;
   p.rays_d = rays_d;
@@ -489,12 +555,26 @@ extern "C" int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int pr
   p.z = z;
   p.pts = pts;
   p.out = out_raw;
+  p.row_index = row_index;
+  p.n_rows_dev = n_rows_dev;
   p.head_w_off = NERF_WA;
   p.head_b_off = NERF_BA;
   p.rgb_w_off = NERF_WR;
   p.rgb_b_off = NERF_BR;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   return prec == B200NERF_PREC_SPLIT ? launch_chain<true, IN_NERF>(p, st) : launch_chain<false, IN_NERF>(p, st);
+}
+
+extern "C" int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,
+                                     const float* viewdirs, const float* z, const float* pts, int n_rays, int S, float* out_raw,
+                                     void* stream) {
+  if (n_rays < 0 || S < 1) return fail("b200nerf_nerf_mlp_fwd: bad sizes n_rays=%d S=%d", n_rays, S);
+  if (n_rays == 0) return 0;
+  if (!wpack || !aux || !viewdirs || !out_raw) return fail("b200nerf_nerf_mlp_fwd: null argument");
+  if (!pts && (!z || !rays_o || !rays_d)) return fail("b200nerf_nerf_mlp_fwd: need pts or (rays_o, rays_d, z)");
+  if (prec != B200NERF_PREC_SPLIT && prec != B200NERF_PREC_BF16) return fail("b200nerf_nerf_mlp_fwd: prec must be SPLIT or BF16");
+  if (static_cast<long long>(n_rays) * S > 0x7fffff00LL) return fail("b200nerf_nerf_mlp_fwd: too many points for one call");
+  return nerf_chain_launch(wpack, aux, prec, rays_o, rays_d, viewdirs, z, pts, n_rays, S, out_raw, nullptr, nullptr, 0,
+                           static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b200nerf_depthnet_fwd(const void* wpack, const float* aux, int n_hidden, int prec, const float* rays_o,
@@ -525,20 +605,184 @@ extern "C" int b200nerf_depthnet_fwd(const void* wpack, const float* aux, int n_
   return prec == B200NERF_PREC_SPLIT ? launch_chain<true, IN_DEPTHNET>(p, st) : launch_chain<false, IN_DEPTHNET>(p, st);
 }
 
-// ------------------------------------------------------------------------------------------- fused render
-extern "C" int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_aux, int dn_hidden, const void* nerf_wpack,
-                                        const float* nerf_aux, int prec, const float* rays_o, const float* rays_d,
-                                        const float* viewdirs, int n_rays, int S, int mode, const float* offsets, float radius,
-                                        float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, float* out_rgb,
-                                        float* out_disp, float* out_acc, float* out_depth, float* out_weights, void* stream) {
+
+// ------------------------------------------------------------------------------------------- fast NeRF MLP
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// The weight pack viewed as [bytes/512, 256] 16-bit elements; a box of `rows` rows is a contiguous rows*512-byte piece.
+static int make_piece_tmap(const void* wpack, int rows, fast::TMap* out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  static_assert(sizeof(CUtensorMap) == sizeof(fast::TMap), "tensor map size");
+  const cuuint64_t gdim[2] = {256, fast::WPACK_BYTES / 512};
+  const cuuint64_t gstride[1] = {512};
+  const cuuint32_t box[2] = {256, static_cast<cuuint32_t>(rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(wpack), gdim,
+                         gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
+static int g_fast_ncta = 2;  // CTA-pair kernel by default; B200NERF_FAST_NCTA=1 selects the single-CTA variant
+static void read_fast_env() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* e = getenv("B200NERF_FAST_NCTA");
+  if (e && e[0] == '1') g_fast_ncta = 1;
+}
+
+template <int NCTA, bool FP16>
+static int launch_fast(const fast::FastParams& p, cudaStream_t st) {
+  static int grid_cap = 0;
+  constexpr int smem = fast::smem_bytes<NCTA>();
+  auto kern = fast::nerf_fast_kernel<NCTA, FP16>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(fast::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (grid_cap == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int sms = sm_count();
+    if (sms <= 0) return fail("no CUDA device");
+    int cap = (sms / NCTA) * NCTA;
+    if (NCTA > 1) {
+      // a persistent grid must be co-resident: ask how many clusters fit
+      cfg.gridDim = dim3(cap);
+      int n_clusters = 0;
+      CUDA_TRY(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
+      if (n_clusters <= 0) return fail("nerf_fast_kernel: no resident cluster fits");
+      if (n_clusters * NCTA < cap) cap = n_clusters * NCTA;
+    }
+    grid_cap = cap;
+  }
+  const int tiles = (p.n_rows + fast::TILE_M - 1) / fast::TILE_M;
+  const int units = (tiles + 2 * NCTA - 1) / (2 * NCTA);
+  int grid = units * NCTA;
+  if (grid > grid_cap) grid = grid_cap;
+  cfg.gridDim = dim3(grid);
+  fast::TMap tm_full, tm_half;
+  memset(&tm_full, 0, sizeof(tm_full));
+  memset(&tm_half, 0, sizeof(tm_half));
+  if (NCTA == 2) {
+    int rc = make_piece_tmap(p.wpack, 8, &tm_full);
+    if (rc) return rc;
+    rc = make_piece_tmap(p.wpack, 4, &tm_half);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, tm_full, tm_half));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200nerf_nerf_mlp_fast_fwd(const void* wpack_fast, const float* aux, int prec, const float* rays_o,
+                                          const float* rays_d, const float* viewdirs, const float* z, const float* pts,
+                                          int n_rays, int S, float* out_raw, int* guard_count, int* guard_list, int guard_cap,
+                                          float guard_kappa, void* stream) {
+  if (n_rays < 0 || S < 1) return fail("b200nerf_nerf_mlp_fast_fwd: bad sizes n_rays=%d S=%d", n_rays, S);
   if (n_rays == 0) return 0;
-  if (!ws_mean || !ws_z || !ws_raw) return fail("b200nerf_render_depthnet: null workspace");
-  int rc = b200nerf_depthnet_fwd(dn_wpack, dn_aux, dn_hidden, prec, rays_o, rays_d, n_rays, radius, near_, far_, ws_mean, stream);
+  if (!wpack_fast || !aux || !viewdirs || !out_raw) return fail("b200nerf_nerf_mlp_fast_fwd: null argument");
+  if (!pts && (!z || !rays_o || !rays_d)) return fail("b200nerf_nerf_mlp_fast_fwd: need pts or (rays_o, rays_d, z)");
+  if (prec != B200NERF_PREC_FP16 && prec != B200NERF_PREC_BF16) return fail("b200nerf_nerf_mlp_fast_fwd: prec must be FP16 or BF16");
+  if (static_cast<long long>(n_rays) * S > 0x7ffff000LL) return fail("b200nerf_nerf_mlp_fast_fwd: too many points for one call");
+  if (guard_count && (!guard_list || guard_cap <= 0)) return fail("b200nerf_nerf_mlp_fast_fwd: guard list missing");
+  read_fast_env();
+  fast::FastParams p;
+  memset(&p, 0, sizeof(p));
+  p.wpack = static_cast<const uint8_t*>(wpack_fast);
+  p.aux = aux;
+  p.n_rows = n_rays * S;
+  p.S = S;
+  p.rays_o = rays_o;
+  p.rays_d = rays_d;
+  p.viewdirs = viewdirs;
+  p.z = z;
+  p.pts = pts;
+  p.out = out_raw;
+  p.guard_count = guard_count;
+  p.guard_list = guard_list;
+  p.guard_cap = guard_cap;
+  p.guard_kappa = guard_kappa;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fp16 = prec == B200NERF_PREC_FP16;
+  if (g_fast_ncta == 2) return fp16 ? launch_fast<2, true>(p, st) : launch_fast<2, false>(p, st);
+  return fp16 ? launch_fast<1, true>(p, st) : launch_fast<1, false>(p, st);
+}
+
+extern "C" int b200nerf_nerf_mlp_guarded_fwd(const void* wpack_fast, const void* wpack_split, const float* aux, int prec,
+                                             const float* rays_o, const float* rays_d, const float* viewdirs, const float* z,
+                                             const float* pts, int n_rays, int S, float guard_kappa, int* ws_guard,
+                                             float* out_raw, void* stream) {
+  if (n_rays == 0) return 0;
+  if (!ws_guard || !wpack_split) return fail("b200nerf_nerf_mlp_guarded_fwd: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // ws_guard[0] = number of flagged points, ws_guard[4 .. 4+n_rays) = their indices (at most one per ray)
+  CUDA_TRY(cudaMemsetAsync(ws_guard, 0, 4 * sizeof(int), st));
+  int rc = b200nerf_nerf_mlp_fast_fwd(wpack_fast, aux, prec, rays_o, rays_d, viewdirs, z, pts, n_rays, S, out_raw, ws_guard,
+                                      ws_guard + 4, n_rays, guard_kappa, stream);
+  if (rc) return rc;
+  // re-evaluate the flagged points in split precision, in place
+  return nerf_chain_launch(wpack_split, aux, B200NERF_PREC_SPLIT, rays_o, rays_d, viewdirs, z, pts, n_rays, S, out_raw,
+                           ws_guard + 4, ws_guard, n_rays, st);
+}
+
+// ------------------------------------------------------------------------------------------- fused render
+extern "C" int b200nerf_nerf_query(const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d,
+                                   const float* viewdirs, const float* z, const float* pts, int n_rays, int S, int* ws_guard,
+                                   float* out_raw, void* stream) {
+  if (!nerf) return fail("b200nerf_nerf_query: null model");
+  switch (nerf->prec) {
+    case B200NERF_PREC_SPLIT:
+    case B200NERF_PREC_BF16:
+      return b200nerf_nerf_mlp_fwd(nerf->wpack, nerf->aux, nerf->prec, rays_o, rays_d, viewdirs, z, pts, n_rays, S, out_raw, stream);
+    case B200NERF_PREC_FP16:
+      return b200nerf_nerf_mlp_fast_fwd(nerf->wpack_fast, nerf->aux, B200NERF_PREC_FP16, rays_o, rays_d, viewdirs, z, pts, n_rays, S,
+                                        out_raw, nullptr, nullptr, 0, 0.f, stream);
+    case B200NERF_PREC_FAST:
+      return b200nerf_nerf_mlp_guarded_fwd(nerf->wpack_fast, nerf->wpack, nerf->aux, B200NERF_PREC_FP16, rays_o, rays_d, viewdirs, z,
+                                           pts, n_rays, S, nerf->guard_kappa, ws_guard, out_raw, stream);
+    default:
+      return fail("b200nerf_nerf_query: unknown precision %d", nerf->prec);
+  }
+}
+
+extern "C" int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_aux, int dn_hidden, int dn_prec,
+                                        const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d,
+                                        const float* viewdirs, int n_rays, int S, int mode, const float* offsets, float radius,
+                                        float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, int* ws_guard,
+                                        float* out_rgb, float* out_disp, float* out_acc, float* out_depth, float* out_weights,
+                                        void* stream) {
+  if (n_rays == 0) return 0;
+  if (!ws_mean || !ws_z || !ws_raw || !nerf) return fail("b200nerf_render_depthnet: null workspace or model");
+  int rc = b200nerf_depthnet_fwd(dn_wpack, dn_aux, dn_hidden, dn_prec, rays_o, rays_d, n_rays, radius, near_, far_, ws_mean, stream);
   if (rc) return rc;
   // the reference clips uniform placements to the literal [2, 6] (nerf_pytorch/utils.py:241)
   rc = b200nerf_place_samples(ws_mean, offsets, n_rays, S, mode, 2.0f, 6.0f, ws_z, stream);
   if (rc) return rc;
-  rc = b200nerf_nerf_mlp_fwd(nerf_wpack, nerf_aux, prec, rays_o, rays_d, viewdirs, ws_z, nullptr, n_rays, S, ws_raw, stream);
+  rc = b200nerf_nerf_query(nerf, rays_o, rays_d, viewdirs, ws_z, nullptr, n_rays, S, ws_guard, ws_raw, stream);
   if (rc) return rc;
   // DepthNet path: noise 0 and white background regardless of the caller's flags (misspelled kwargs,
   // nerf_utils.py:858-865)
@@ -551,11 +795,11 @@ static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 extern "C" size_t b200nerf_render_host_ws_bytes(int n_rays, int S) {
   const size_t n = static_cast<size_t>(n_rays);
   return 3 * align256(n * 3 * 4) + align256(n * 4) /*mean*/ + align256(n * S * 4) /*z*/ + align256(n * S * 16) /*raw*/ +
-         align256(n * 3 * 4) /*rgb*/ + align256(n * 4) /*disp*/;
+         align256(n * 3 * 4) /*rgb*/ + align256(n * 4) /*disp*/ + align256((n + 4) * 4) /*guard list*/;
 }
 
-extern "C" int b200nerf_render_depthnet_host(const void* dn_wpack, const float* dn_aux, int dn_hidden, const void* nerf_wpack,
-                                             const float* nerf_aux, int prec, const float* h_rays_o, const float* h_rays_d,
+extern "C" int b200nerf_render_depthnet_host(const void* dn_wpack, const float* dn_aux, int dn_hidden, int dn_prec,
+                                             const b200nerf_nerf_model* nerf, const float* h_rays_o, const float* h_rays_d,
                                              int n_rays, int S, int mode, const float* offsets, float radius, float near_,
                                              float far_, void* d_ws, float* h_rgb, float* h_disp, void* stream) {
   if (n_rays <= 0 || !d_ws || !h_rays_o || !h_rays_d || !h_rgb || !h_disp) return fail("b200nerf_render_depthnet_host: bad arguments");
@@ -569,13 +813,14 @@ extern "C" int b200nerf_render_depthnet_host(const void* dn_wpack, const float* 
   float* zb = reinterpret_cast<float*>(w); w += align256(n * S * 4);
   float* rawb = reinterpret_cast<float*>(w); w += align256(n * S * 16);
   float* rgb = reinterpret_cast<float*>(w); w += align256(n * 12);
-  float* disp = reinterpret_cast<float*>(w);
+  float* disp = reinterpret_cast<float*>(w); w += align256(n * 4);
+  int* guard = reinterpret_cast<int*>(w);
   CUDA_TRY(cudaMemcpyAsync(ro, h_rays_o, n * 12, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(rd, h_rays_d, n * 12, cudaMemcpyHostToDevice, st));
   int rc = b200nerf_normalize_dirs(rd, n_rays, vd, stream);
   if (rc) return rc;
-  rc = b200nerf_render_depthnet(dn_wpack, dn_aux, dn_hidden, nerf_wpack, nerf_aux, prec, ro, rd, vd, n_rays, S, mode, offsets,
-                                radius, near_, far_, mean, zb, rawb, rgb, disp, nullptr, nullptr, nullptr, stream);
+  rc = b200nerf_render_depthnet(dn_wpack, dn_aux, dn_hidden, dn_prec, nerf, ro, rd, vd, n_rays, S, mode, offsets, radius, near_,
+                                far_, mean, zb, rawb, guard, rgb, disp, nullptr, nullptr, nullptr, stream);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(h_rgb, rgb, n * 12, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(h_disp, disp, n * 4, cudaMemcpyDeviceToHost, st));

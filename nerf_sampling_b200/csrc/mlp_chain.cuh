@@ -67,6 +67,8 @@ struct ChainParams {
   const float* z;        // [rays,S]   (NeRF: depth of every sample)  or nullptr
   const float* pts;      // [rows,3]   (NeRF: explicit sample positions) or nullptr
   float* out;            // raw [rows,4] (NeRF) or z [rows] (DepthNet)
+  const int* row_index;  // NeRF only, optional: row i of this launch is sample point row_index[i] (input and output)
+  const int* n_rows_dev; // optional: the row count lives on the device (capped by n_rows); used with row_index
   uint32_t head_w_off, head_b_off;    // sigma head (NeRF) / depth head (DepthNet)
   uint32_t rgb_w_off, rgb_b_off;      // rgb head [3,128]
   float radius, near, far;
@@ -161,7 +163,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+  int n_rows = p.n_rows;
+  if (p.n_rows_dev != nullptr) n_rows = min(__ldg(p.n_rows_dev), p.n_rows);
+  const int num_tiles = (n_rows + TILE_M - 1) / TILE_M;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NUM_STAGES; ++i) {
@@ -249,8 +253,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const __gri
     uint32_t acc_cnt = 0;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int grow = tile * TILE_M + row;
-      const bool valid = grow < p.n_rows;
+      const bool valid = tile * TILE_M + row < n_rows;
+      // sample point this row evaluates (identity unless the launch works through an index list)
+      const int grow = (INPUT == IN_NERF && p.row_index != nullptr) ? (valid ? __ldg(p.row_index + tile * TILE_M + row) : 0)
+                                                                    : tile * TILE_M + row;
 
       // ---------------------------------------------------------------- prologue: network input
       if (INPUT == IN_NERF) {

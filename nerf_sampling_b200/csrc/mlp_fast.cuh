@@ -1,0 +1,528 @@
+// Fused NeRF MLP, single-pass 16-bit operands (fp16 or bf16, fp32 accumulate) on tcgen05 tensor cores (sm_100a).
+//
+// Reference semantics: Trainer.run_network (nerf_pytorch/trainers/Trainer.py:789-806) + NeRF.forward
+// (nerf_pytorch/run_nerf_helpers.py:109-134): gamma(pts) 63-wide, gamma(viewdirs) 27-wide, 8x256 ReLU trunk
+// with the input re-concatenated at layer 5, alpha head, feature layer, 128-wide view layer, rgb head.
+//
+// Throughput design (one persistent CTA per SM, optionally paired as a 2-CTA cluster):
+//   * two 128-row tiles ("slots") are resident per CTA and ping-pong: while the tensor core runs layer L of
+//     slot 0 the epilogue warps turn the finished accumulator of slot 1 into its next operand, so the tensor
+//     pipe never waits for an epilogue that is shorter than one layer of MMAs
+//   * NCTA == 2: the pair issues tcgen05.mma.cta_group::2 (M = 256 over both CTAs); each CTA streams only its
+//     half of every weight slab, which halves L2->SM weight traffic and B-operand shared-memory reads per SM
+//   * operands: per slot one K-major no-swizzle buffer of 44 K chunks: [h 0..255 | gamma(pts) 256..319 |
+//     gamma(viewdir) 320..351]; every epilogue rewrites h in place (its readers have retired: acc_full)
+//   * TMEM: slot 0 accumulates in columns 0..255, slot 1 in 256..511
+//   * warp roles: 0 = weight producer (TMA), 1 = MMA issuer, 2 = TMEM allocator, 4-11 = epilogue
+//     (tcgen05.ld, + bias, ReLU, 16-bit pack, st.shared; fp32 alpha / rgb heads), 12-15 = encoders
+//     (o + d*z, sin/cos octaves) which run one tile ahead of the tensor core
+//
+// Guard band (optional): raw2outputs turns sigma of the LAST sample of a ray into a step function
+// (dist = 1e10, trainers/sampling_trainer.py:178-180), so a rounding error that flips the sign of a tiny sigma
+// flips the pixel.  The final epilogue therefore appends every last-of-ray sample with
+// |sigma| < kappa * sum_i |h7_i * w_alpha_i| to a list; the caller re-evaluates those points with the
+// split-precision kernel (mlp_chain.cuh) and overwrites them.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+namespace fast {
+
+constexpr int TILE_M = 128;
+constexpr int KC_STRIDE = 2048;                       // bytes between 8-element K chunks: 16 row groups x 128 B
+constexpr int ENC_KB = 16;                            // K16 block of gamma(pts)      (K chunks 32..39)
+constexpr int VIEW_KB = 20;                           // K16 block of gamma(viewdir)  (K chunks 40..43)
+constexpr int TILE_KC = 44;
+constexpr int TILE_ACT_BYTES = TILE_KC * KC_STRIDE;   // 90,112 B per slot
+constexpr int RING_BYTES = 32768;
+constexpr int AUX_FLOATS = 3080;
+constexpr int THREADS = 512;
+constexpr int NSTEPS = 10;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, PRO_WARP0 = 12, PRO_WARPS = 4;
+constexpr size_t WPACK_BYTES = 1187840;               // 136 slabs x 8 KB + 18 slabs x 4 KB
+
+// aux block (float offsets) -- same layout as the split-precision kernel's NeRF aux
+enum : uint32_t { AUX_B0 = 0, AUX_BF = 2048, AUX_BV = 2304, AUX_WA = 2432, AUX_BA = 2688, AUX_WR = 2692, AUX_BR = 3076 };
+
+// The layer program.  Step s reads K16 blocks [kb1, kb1+nk1) then [kb2, kb2+nk2) of the slot's operand buffer.
+//   s: 0 = pts_linears.0 (gamma(pts) only), 1-4, 5 = skip layer [h | gamma(pts)], 6, 7 (+ alpha head),
+//      8 = feature_linear (no activation), 9 = views_linears.0 [feature | gamma(viewdir)] (N = 128, + rgb head)
+__host__ __device__ constexpr int step_nk1(int s) { return s == 0 ? 4 : 16; }
+__host__ __device__ constexpr int step_kb1(int s) { return s == 0 ? ENC_KB : 0; }
+__host__ __device__ constexpr int step_nk2(int s) { return s == 5 ? 4 : (s == 9 ? 2 : 0); }
+__host__ __device__ constexpr int step_kb2(int s) { return s == 5 ? ENC_KB : VIEW_KB; }
+__host__ __device__ constexpr int step_n(int s) { return s == 9 ? 128 : 256; }
+__host__ __device__ constexpr int step_nk(int s) { return step_nk1(s) + step_nk2(s); }
+__host__ __device__ constexpr uint32_t step_bias(int s) { return s < 8 ? AUX_B0 + 256u * s : (s == 8 ? AUX_BF : AUX_BV); }
+__host__ __device__ constexpr uint32_t step_woff(int s) {  // byte offset of the step's first slab in the pack
+  uint32_t o = 0;
+  for (int i = 0; i < s; ++i) o += static_cast<uint32_t>(step_nk(i)) * step_n(i) * 32u;
+  return o;
+}
+
+struct alignas(64) TMap {
+  uint8_t bytes[128];
+};
+
+struct FastParams {
+  const uint8_t* wpack;   // weight slabs in streaming order (fp16 or bf16)
+  const float* aux;       // biases + head weights (device)
+  int n_rows;             // sample points
+  int S;                  // samples per ray
+  const float* rays_o;    // [rays,3]
+  const float* rays_d;    // [rays,3]
+  const float* viewdirs;  // [rays,3]
+  const float* z;         // [rays,S] or nullptr
+  const float* pts;       // [rows,3] or nullptr
+  float* out;             // raw [rows,4]
+  int* guard_count;       // nullptr: no guard band
+  int* guard_list;        // [guard_cap] point indices to re-evaluate
+  int guard_cap;
+  float guard_kappa;
+};
+
+template <int NSTAGE>
+struct __align__(16) Tail {
+  uint64_t full[NSTAGE];
+  uint64_t empty[NSTAGE];
+  uint64_t acc_full[2];
+  uint64_t a_ready[2];
+  uint64_t enc_ready[2];
+  uint64_t view_ready[2];
+  uint64_t pts_free[2];
+  uint64_t view_free[2];
+  uint32_t tmem_base;
+  uint32_t pad[3];
+  float alpha_part[2][TILE_M];  // column half 1's part of the sigma head, per slot
+  float eabs_part[2][TILE_M];   // ... and of sum |h7 * w_alpha|
+};
+
+template <int NCTA>
+__host__ __device__ constexpr int num_stages() { return NCTA == 2 ? 8 : 4; }
+template <int NCTA>
+__host__ __device__ constexpr int smem_bytes() {
+  return 2 * TILE_ACT_BYTES + RING_BYTES + AUX_FLOATS * 4 + static_cast<int>(sizeof(Tail<num_stages<NCTA>()>));
+}
+
+// ---------------------------------------------------------------------------------------------
+// encoders
+// ---------------------------------------------------------------------------------------------
+template <bool FP16>
+__device__ __forceinline__ void store8(uint8_t* dst, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_half2<FP16, false>(v[0], v[1]), pack_half2<FP16, false>(v[2], v[3]),
+                                              pack_half2<FP16, false>(v[4], v[5]), pack_half2<FP16, false>(v[6], v[7]));
+}
+
+// [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(NF-1) x), cos(2^(NF-1) x)] zero-padded to NCHUNK*8 columns
+// (run_nerf_helpers.py:15-63).  Octaves 0 and 5 are evaluated with accurate sincosf, the others by exact-angle
+// doubling from them (<= 4 doublings: error ~1e-6, far below the 16-bit operand rounding).
+template <bool FP16, int NF, int NCHUNK>
+__device__ __forceinline__ void encode_store(const float (&x)[3], uint8_t* dst /* first K chunk + row offset */) {
+  float sn[NF][3], cs[NF][3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    sincosf(x[t], &sn[0][t], &cs[0][t]);
+    if (NF > 5) sincosf(x[t] * 32.0f, &sn[5][t], &cs[5][t]);
+#pragma unroll
+    for (int j = 1; j < NF; ++j) {
+      if (j == 5) continue;
+      const float s = sn[j - 1][t], c = cs[j - 1][t];
+      sn[j][t] = 2.0f * s * c;
+      cs[j][t] = (c - s) * (c + s);
+    }
+  }
+  constexpr int NCOL = 3 + 6 * NF;
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int cc = ch * 8 + i;
+      if (cc < 3) v[i] = x[cc];
+      else if (cc < NCOL) v[i] = ((cc - 3) % 6) < 3 ? sn[(cc - 3) / 6][(cc - 3) % 6] : cs[(cc - 3) / 6][(cc - 3) % 6 - 3];
+      else v[i] = 0.f;
+    }
+    store8<FP16>(dst + ch * KC_STRIDE, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogues (one thread = one accumulator row x one column half)
+// ---------------------------------------------------------------------------------------------
+// 32 accumulator columns: + bias, activation, pack, 4 x 16-byte operand stores (K chunks kc .. kc+3).
+// MODE 0: ReLU   1: ReLU + alpha-head partial sums   2: no activation (feature_linear)
+template <int MODE, bool FP16>
+__device__ __forceinline__ void epi_store32(const uint32_t (&v)[32], const float* bias, const float* hw, uint8_t* dst,
+                                            float& hsum, float& habs) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + j);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + j + 4);
+    float x[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] += __uint_as_float(v[j + i]);
+    uint32_t h[4];
+    if (MODE == 1) {
+      const float4 w0 = *reinterpret_cast<const float4*>(hw + j);
+      const float4 w1 = *reinterpret_cast<const float4*>(hw + j + 4);
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        x[i] = fmaxf(x[i], 0.f);
+        hsum = fmaf(x[i], w[i], hsum);
+        habs = fmaf(x[i], fabsf(w[i]), habs);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = pack_half2<FP16, false>(x[2 * i], x[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = pack_half2<FP16, MODE == 0>(x[2 * i], x[2 * i + 1]);
+    }
+    *reinterpret_cast<uint4*>(dst + (j >> 3) * KC_STRIDE) = make_uint4(h[0], h[1], h[2], h[3]);
+  }
+}
+
+template <int MODE, bool FP16>
+__device__ __forceinline__ void epilogue_store(uint32_t tacc, const float* bias, const float* hw, uint8_t* dst,
+                                               float& hsum, float& habs) {
+  uint32_t va[32], vb[32];
+  tmem_ld_32x32b_x32(tacc, va);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(tacc + 32, vb);
+  epi_store32<MODE, FP16>(va, bias, hw, dst, hsum, habs);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(tacc + 64, va);
+  epi_store32<MODE, FP16>(vb, bias + 32, hw + 32, dst + 4 * KC_STRIDE, hsum, habs);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(tacc + 96, vb);
+  epi_store32<MODE, FP16>(va, bias + 64, hw + 64, dst + 8 * KC_STRIDE, hsum, habs);
+  tmem_ld_wait();
+  epi_store32<MODE, FP16>(vb, bias + 96, hw + 96, dst + 12 * KC_STRIDE, hsum, habs);
+}
+
+// view layer: 32 columns of relu(acc + bias) folded into the three rgb dot products
+__device__ __forceinline__ void epi_rgb32(const uint32_t (&v)[32], const float* bias, const float* wr, float& r, float& g,
+                                          float& b) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 bb = *reinterpret_cast<const float4*>(bias + j);
+    const float4 w0 = *reinterpret_cast<const float4*>(wr + j);
+    const float4 w1 = *reinterpret_cast<const float4*>(wr + 128 + j);
+    const float4 w2 = *reinterpret_cast<const float4*>(wr + 256 + j);
+    const float x0 = fmaxf(__uint_as_float(v[j]) + bb.x, 0.f), x1 = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
+    const float x2 = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f), x3 = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
+    r = fmaf(x0, w0.x, r); r = fmaf(x1, w0.y, r); r = fmaf(x2, w0.z, r); r = fmaf(x3, w0.w, r);
+    g = fmaf(x0, w1.x, g); g = fmaf(x1, w1.y, g); g = fmaf(x2, w1.z, g); g = fmaf(x3, w1.w, g);
+    b = fmaf(x0, w2.x, b); b = fmaf(x1, w2.y, b); b = fmaf(x2, w2.z, b); b = fmaf(x3, w2.w, b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int NCTA, bool FP16>
+__global__ void __launch_bounds__(THREADS, 1)
+nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ TMap tm_full, const __grid_constant__ TMap tm_half) {
+  constexpr int NSTAGE = num_stages<NCTA>();
+  constexpr int STAGE_BYTES = RING_BYTES / NSTAGE;  // NCTA 2: this CTA's half slab (4 KB); NCTA 1: the whole slab (8 KB)
+  using TailT = Tail<NSTAGE>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* act = smem;
+  uint8_t* ring = smem + 2 * TILE_ACT_BYTES;
+  float* saux = reinterpret_cast<float*>(ring + RING_BYTES);
+  TailT* tail = reinterpret_cast<TailT*>(ring + RING_BYTES + AUX_FLOATS * 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x / NCTA;
+  const int n_clusters = gridDim.x / NCTA;
+  const int num_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
+  const int n_units = (num_tiles + 2 * NCTA - 1) / (2 * NCTA);   // one unit = 2 slots x NCTA tiles
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) {
+      mbar_init(&tail->full[i], 1);
+      mbar_init(&tail->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tail->acc_full[i], 1);
+      mbar_init(&tail->a_ready[i], EPI_WARPS * NCTA);
+      mbar_init(&tail->enc_ready[i], PRO_WARPS * NCTA);
+      mbar_init(&tail->view_ready[i], PRO_WARPS * NCTA);
+      mbar_init(&tail->pts_free[i], 1);
+      mbar_init(&tail->view_free[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    if (NCTA == 2) {
+      tmem_alloc_cg2(&tail->tmem_base, 512);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(&tail->tmem_base, 512);
+      tmem_relinquish();
+    }
+  }
+  for (int i = threadIdx.x; i < AUX_FLOATS; i += THREADS) saux[i] = p.aux[i];
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== weight producer
+    if (lane == 0) {
+      if (NCTA == 2) {
+        tma_prefetch_desc(&tm_full);
+        tma_prefetch_desc(&tm_half);
+      }
+      const uint32_t ring_addr = smem_u32(ring);
+      uint32_t it = 0;
+      for (int u = cluster_id; u < n_units; u += n_clusters) {
+        for (int s = 0; s < NSTEPS; ++s) {
+          const int nk = step_nk(s);
+          const uint32_t slab = static_cast<uint32_t>(step_n(s)) * 32u;   // bytes of one K16 slab (both halves)
+          const uint32_t woff = step_woff(s);
+          for (int slot = 0; slot < 2; ++slot) {
+            for (int k = 0; k < nk; ++k, ++it) {
+              const uint32_t stage = it % NSTAGE;
+              const uint32_t ph = (it / NSTAGE) & 1u;
+              mbar_wait(&tail->empty[stage], ph ^ 1u);
+              const uint32_t off = woff + static_cast<uint32_t>(k) * slab;
+              if (NCTA == 2) {
+                // the pair's leader owns the full barrier: both halves complete_tx on it
+                if (leader) mbar_arrive_expect_tx(&tail->full[stage], slab);
+                const uint32_t bar = mapa_u32(smem_u32(&tail->full[stage]), 0);
+                const uint32_t my_off = off + rank * (slab / 2);
+                tma_load_2d_cg2(ring_addr + stage * STAGE_BYTES, s == 9 ? &tm_half : &tm_full, 0,
+                                static_cast<int>(my_off / 512u), bar);
+              } else {
+                mbar_arrive_expect_tx(&tail->full[stage], slab);
+                tma_load_1d(ring + stage * STAGE_BYTES, p.wpack + off, slab, &tail->full[stage]);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (pair leader only)
+    if (lane == 0 && leader) {
+      const uint32_t act_addr = smem_u32(act);
+      const uint32_t ring_addr = smem_u32(ring);
+      uint32_t it = 0, ca[2] = {0, 0}, ce[2] = {0, 0}, cv[2] = {0, 0};
+      bool first = true;
+      for (int u = cluster_id; u < n_units; u += n_clusters) {
+        for (int s = 0; s < NSTEPS; ++s) {
+          const int nk1 = step_nk1(s), nk = step_nk(s);
+          const int kb1 = step_kb1(s), kb2 = step_kb2(s);
+          const uint32_t n = static_cast<uint32_t>(step_n(s));
+          const uint32_t piece = n * 16u;                       // bytes of one CTA's half of a K16 slab
+          const uint32_t idesc1 = umma_idesc_f16(FP16 ? 0u : 1u, 128, n / 2);
+          const uint32_t idesc2 = umma_idesc_f16(FP16 ? 0u : 1u, 256, n);
+          for (int slot = 0; slot < 2; ++slot) {
+            if (s == 0) {
+              mbar_wait_cluster(&tail->enc_ready[slot], ce[slot]++ & 1u);
+              if (!first) mbar_wait_cluster(&tail->a_ready[slot], ca[slot]++ & 1u);
+            } else {
+              mbar_wait_cluster(&tail->a_ready[slot], ca[slot]++ & 1u);
+            }
+            if (s == NSTEPS - 1) mbar_wait_cluster(&tail->view_ready[slot], cv[slot]++ & 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + slot * 256u;
+            const uint32_t a_base = act_addr + slot * TILE_ACT_BYTES;
+            for (int k = 0; k < nk; ++k, ++it) {
+              const uint32_t stage = it % NSTAGE;
+              const uint32_t ph = (it / NSTAGE) & 1u;
+              mbar_wait(&tail->full[stage], ph);
+              tc_fence_after();
+              const int kb = k < nk1 ? kb1 + k : kb2 + (k - nk1);
+              const uint64_t a_desc = umma_desc_kmajor(a_base + kb * 2 * KC_STRIDE, KC_STRIDE, 128);
+              const uint32_t b_addr = ring_addr + stage * STAGE_BYTES;
+              if (NCTA == 2) {
+                tc_mma_f16_cg2(d_tmem, a_desc, umma_desc_kmajor(b_addr, piece / 2, 128), idesc2, k > 0 ? 1u : 0u);
+                tc_commit_cg2(&tail->empty[stage], 3);
+              } else {
+                tc_mma_bf16(d_tmem, a_desc, umma_desc_kmajor(b_addr, piece / 2, 128), idesc1, k > 0 ? 1u : 0u);
+                tc_mma_bf16(d_tmem + n / 2, a_desc, umma_desc_kmajor(b_addr + piece, piece / 2, 128), idesc1, k > 0 ? 1u : 0u);
+                tc_commit(&tail->empty[stage]);
+              }
+            }
+            if (NCTA == 2) {
+              tc_commit_cg2(&tail->acc_full[slot], 3);
+              if (s == 5) tc_commit_cg2(&tail->pts_free[slot], 3);
+              if (s == NSTEPS - 1) tc_commit_cg2(&tail->view_free[slot], 3);
+            } else {
+              tc_commit(&tail->acc_full[slot]);
+              if (s == 5) tc_commit(&tail->pts_free[slot]);
+              if (s == NSTEPS - 1) tc_commit(&tail->view_free[slot]);
+            }
+          }
+        }
+        first = false;
+      }
+    }
+  } else if (warp >= PRO_WARP0) {
+    // ===================================================================== encoders (one tile ahead)
+    const int row = (warp - PRO_WARP0) * 32 + lane;
+    const int row_off = (row >> 3) * 128 + (row & 7) * 16;
+    uint32_t cp[2] = {0, 0}, cw[2] = {0, 0};
+    bool first = true;
+    uint32_t enc_bar[2], view_bar[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      enc_bar[i] = NCTA == 2 ? mapa_u32(smem_u32(&tail->enc_ready[i]), 0) : 0u;
+      view_bar[i] = NCTA == 2 ? mapa_u32(smem_u32(&tail->view_ready[i]), 0) : 0u;
+    }
+    for (int u = cluster_id; u < n_units; u += n_clusters) {
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        const int grow = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + row;
+        float x[3] = {0.f, 0.f, 0.f};
+        if (grow < p.n_rows) {
+          if (p.pts != nullptr) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) x[t] = __ldg(p.pts + static_cast<size_t>(grow) * 3 + t);
+          } else {
+            const int ray = grow / p.S;
+            const float zz = __ldg(p.z + grow);
+#pragma unroll
+            for (int t = 0; t < 3; ++t)  // o + d*z, product and sum rounded separately like torch
+              x[t] = __fadd_rn(__ldg(p.rays_o + ray * 3 + t), __fmul_rn(__ldg(p.rays_d + ray * 3 + t), zz));
+          }
+        }
+        if (!first) {
+          mbar_wait(&tail->pts_free[slot], cp[slot]++ & 1u);   // the previous tile's skip layer has retired
+          tc_fence_after();
+        }
+        encode_store<FP16, 10, 8>(x, act + slot * TILE_ACT_BYTES + ENC_KB * 2 * KC_STRIDE + row_off);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(enc_bar[slot]); else mbar_arrive(&tail->enc_ready[slot]);
+        }
+      }
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        const int grow = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + row;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (grow < p.n_rows) {
+          const int ray = grow / p.S;
+#pragma unroll
+          for (int t = 0; t < 3; ++t) v[t] = __ldg(p.viewdirs + ray * 3 + t);
+        }
+        if (!first) {
+          mbar_wait(&tail->view_free[slot], cw[slot]++ & 1u);  // the previous tile's view layer has retired
+          tc_fence_after();
+        }
+        encode_store<FP16, 4, 4>(v, act + slot * TILE_ACT_BYTES + VIEW_KB * 2 * KC_STRIDE + row_off);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(view_bar[slot]); else mbar_arrive(&tail->view_ready[slot]);
+        }
+      }
+      first = false;
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================================================================== epilogue warps
+    const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    const int hf = (warp - EPI_WARP0) >> 2;  // column half
+    const int row = q * 32 + lane;
+    const int row_off = (row >> 3) * 128 + (row & 7) * 16;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t cf[2] = {0, 0};
+    uint32_t rdy_bar[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) rdy_bar[i] = NCTA == 2 ? mapa_u32(smem_u32(&tail->a_ready[i]), 0) : 0u;
+    float alpha_keep[2] = {0.f, 0.f}, eabs_keep[2] = {0.f, 0.f};
+
+    for (int u = cluster_id; u < n_units; u += n_clusters) {
+#pragma unroll 1
+      for (int s = 0; s < NSTEPS; ++s) {
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+          mbar_wait(&tail->acc_full[slot], cf[slot]++ & 1u);
+          tc_fence_after();
+          const uint32_t tacc = t_lane + slot * 256u;
+          uint8_t* a_tile = act + slot * TILE_ACT_BYTES;
+          if (s < 8) {
+            uint8_t* dst = a_tile + hf * 16 * KC_STRIDE + row_off;
+            const float* bias = saux + step_bias(s) + hf * 128;
+            float hs = 0.f, ha = 0.f;
+            if (s == 7) {
+              epilogue_store<1, FP16>(tacc + hf * 128, bias, saux + AUX_WA + hf * 128, dst, hs, ha);
+              if (hf == 1) {
+                tail->alpha_part[slot][row] = hs;
+                tail->eabs_part[slot][row] = ha;
+              } else {
+                alpha_keep[slot] = hs;
+                eabs_keep[slot] = ha;
+              }
+            } else {
+              epilogue_store<0, FP16>(tacc + hf * 128, bias, nullptr, dst, hs, ha);
+            }
+          } else if (s == 8) {
+            uint8_t* dst = a_tile + hf * 16 * KC_STRIDE + row_off;
+            float hs = 0.f, ha = 0.f;
+            epilogue_store<2, FP16>(tacc + hf * 128, saux + AUX_BF + hf * 128, nullptr, dst, hs, ha);
+          } else if (hf == 0) {
+            // view layer (128 columns) + rgb head; sigma = alpha head of layer 7 (both column halves)
+            float r = 0.f, g = 0.f, b = 0.f;
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32b_x32(tacc, va);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(tacc + 32, vb);
+            epi_rgb32(va, saux + AUX_BV, saux + AUX_WR, r, g, b);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(tacc + 64, va);
+            epi_rgb32(vb, saux + AUX_BV + 32, saux + AUX_WR + 32, r, g, b);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(tacc + 96, vb);
+            epi_rgb32(va, saux + AUX_BV + 64, saux + AUX_WR + 64, r, g, b);
+            tmem_ld_wait();
+            epi_rgb32(vb, saux + AUX_BV + 96, saux + AUX_WR + 96, r, g, b);
+            const int grow = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + row;
+            const bool valid = grow < p.n_rows;
+            const float sigma = alpha_keep[slot] + tail->alpha_part[slot][row] + saux[AUX_BA];
+            if (valid) {
+              reinterpret_cast<float4*>(p.out)[grow] =
+                  make_float4(r + saux[AUX_BR], g + saux[AUX_BR + 1], b + saux[AUX_BR + 2], sigma);
+            }
+            if (p.guard_count != nullptr) {
+              const float eabs = eabs_keep[slot] + tail->eabs_part[slot][row] + fabsf(saux[AUX_BA]);
+              const bool flag = valid && (grow % p.S) == p.S - 1 && !(fabsf(sigma) >= p.guard_kappa * eabs);
+              const uint32_t m = __ballot_sync(0xffffffffu, flag);
+              if (m != 0) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(p.guard_count, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int idx = base + __popc(m & ((1u << lane) - 1u));
+                if (flag && idx < p.guard_cap) p.guard_list[idx] = grow;
+              }
+            }
+          }
+          if (s == 8) named_bar_sync(1, EPI_WARPS * 32);   // layer 7's alpha partials are visible to half 0
+          if (s < NSTEPS - 1) fence_proxy_async_smem();    // operand stores -> visible to the tensor core
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (NCTA == 2) mbar_arrive_cluster(rdy_bar[slot]); else mbar_arrive(&tail->a_ready[slot]);
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if (NCTA == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fast
+}  // namespace b200

@@ -6,12 +6,13 @@ data path and no CPU fallback (CPU tensors are rejected).
 
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
-from .packing import PackedDepthNet, PackedNeRF
+from .packing import PREC_FAST, PackedDepthNet, PackedNeRF
 
 PLACE_MODES = {"depth_only": 0, "uniform": 1, "gaussian": 2}
 
@@ -116,9 +117,12 @@ def nerf_mlp(pk: PackedNeRF, viewdirs, *, rays_o=None, rays_d=None, z=None, pts=
         ro, rd, zz = _dev(rays_o, "rays_o"), _dev(rays_d, "rays_d"), _dev(z, "z")
         s = zz.shape[1]
     raw = torch.empty(n, s, 4, device=viewdirs.device)
+    ws = torch.empty(n + 4, device=viewdirs.device, dtype=torch.int32) if pk.prec == PREC_FAST else None
+    model = pk.c_model()
     with torch.cuda.device(viewdirs.device):
-        _lib.check(_lib.lib().b200nerf_nerf_mlp_fwd(_p(pk.wpack), _p(pk.aux), pk.prec, _p(ro), _p(rd), _p(viewdirs), _p(zz),
-                                                    _p(pts), n, s, _p(raw), _stream()))
+        _lib.check(_lib.lib().b200nerf_nerf_query(C.byref(model), _p(ro), _p(rd), _p(viewdirs), _p(zz), _p(pts), n, s, _p(ws),
+                                                  _p(raw), _stream()))
+    nerf_mlp.last_guard_ws = ws  # PREC_FAST: ws[0] = number of samples re-evaluated in split precision
     return raw
 
 
@@ -166,12 +170,14 @@ def render_depthnet(dn: PackedDepthNet, nerf: PackedNeRF, rays_o, rays_d, viewdi
     depth = torch.empty(n, device=dev)
     sw = s if s > 1 else 0
     weights = torch.empty(n, sw, device=dev) if want_weights else None
+    ws = torch.empty(n + 4, device=dev, dtype=torch.int32) if nerf.prec == PREC_FAST else None
+    model = nerf.c_model()
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().b200nerf_render_depthnet(
-            _p(dn.wpack), _p(dn.aux), dn.n_hidden, _p(nerf.wpack), _p(nerf.aux), nerf.prec, _p(rays_o), _p(rays_d), _p(viewdirs),
-            n, s, PLACE_MODES[mode], _p(offs), float(radius), float(near), float(far), _p(mean), _p(z), _p(raw), _p(rgb),
+            _p(dn.wpack), _p(dn.aux), dn.n_hidden, dn.prec, C.byref(model), _p(rays_o), _p(rays_d), _p(viewdirs),
+            n, s, PLACE_MODES[mode], _p(offs), float(radius), float(near), float(far), _p(mean), _p(z), _p(raw), _p(ws), _p(rgb),
             _p(disp), _p(acc), _p(depth), _p(weights) if (want_weights and sw) else None, _stream()))
-    return dict(rgb=rgb, disp=disp, acc=acc, depth=depth, weights=weights, z=z, raw=raw, z_mean=mean)
+    return dict(rgb=rgb, disp=disp, acc=acc, depth=depth, weights=weights, z=z, raw=raw, z_mean=mean, guard_ws=ws)
 
 
 def coarse_z(near, far, n_rays: int, n_samples: int, lindisp: bool, t_rand: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -15,8 +15,11 @@ import torch
 
 from . import _lib
 
-PREC_SPLIT = 1  # bf16 hi+lo operands (parity mode)
-PREC_BF16 = 0   # plain bf16 operands
+PREC_SPLIT = 1  # bf16 hi+lo operands, 3 MMAs per K16 block (exact mode, ~16 mantissa bits)
+PREC_BF16 = 0   # plain bf16 operands on the exact kernel's schedule (legacy)
+PREC_FP16 = 2   # fp16 operands, 1 MMA per K16 block, throughput kernel, no guard band (PSNR-level parity)
+PREC_FAST = 3   # PREC_FP16 + split-precision re-evaluation of the guard band: meets the 1e-3 max-abs contract
+GUARD_KAPPA = 1.0 / 32.0  # |sigma_last| < kappa * sum|h7 * w_alpha| is re-evaluated in split precision
 
 NERF_KEYS = (
     [f"pts_linears.{i}.{w}" for i in range(8) for w in ("weight", "bias")]
@@ -49,12 +52,32 @@ class PackedNeRF:
             if tuple(state_dict[k].shape) != shp:
                 raise ValueError(f"{k} has shape {tuple(state_dict[k].shape)}, expected {shp}")
         host = [_host_f32(state_dict[k]) for k in NERF_KEYS]
-        wpack = torch.empty(L.b200nerf_nerf_wpack_bytes(prec), dtype=torch.uint8)
+        arr = C.cast(_ptr_array(host), C.c_void_p)
+        chain_prec = PREC_BF16 if prec == PREC_BF16 else PREC_SPLIT
         aux = torch.empty(L.b200nerf_nerf_aux_floats(), dtype=torch.float32)
-        _lib.check(L.b200nerf_nerf_pack(C.cast(_ptr_array(host), C.c_void_p), prec, wpack.data_ptr(), aux.data_ptr()))
         self.prec = prec
-        self.wpack = wpack.to(device)
+        self.wpack = None       # slab stream of the exact kernel (mlp_chain.cuh)
+        self.wpack_fast = None  # single-pass 16-bit slab stream of the throughput kernel (mlp_fast.cuh)
+        if prec != PREC_FP16:
+            wpack = torch.empty(L.b200nerf_nerf_wpack_bytes(chain_prec), dtype=torch.uint8)
+            _lib.check(L.b200nerf_nerf_pack(arr, chain_prec, wpack.data_ptr(), aux.data_ptr()))
+            self.wpack = wpack.to(device)
+        else:
+            scratch = torch.empty(L.b200nerf_nerf_wpack_bytes(PREC_BF16), dtype=torch.uint8)
+            _lib.check(L.b200nerf_nerf_pack(arr, PREC_BF16, scratch.data_ptr(), aux.data_ptr()))
+        if prec in (PREC_FP16, PREC_FAST):
+            wf = torch.empty(L.b200nerf_nerf_fast_wpack_bytes(), dtype=torch.uint8)
+            _lib.check(L.b200nerf_nerf_pack_fast(arr, PREC_FP16, wf.data_ptr()))
+            self.wpack_fast = wf.to(device)
         self.aux = aux.to(device)
+        self.guard_kappa = GUARD_KAPPA
+
+    def c_model(self) -> "_lib.NerfModel":
+        """The ``b200nerf_nerf_model`` descriptor of this image (pass with ctypes.byref)."""
+        return _lib.NerfModel(
+            None if self.wpack is None else self.wpack.data_ptr(),
+            None if self.wpack_fast is None else self.wpack_fast.data_ptr(),
+            self.aux.data_ptr(), int(self.prec), float(self.guard_kappa))
 
 
 def fold_depthnet(sd: Dict[str, torch.Tensor]):
