@@ -144,23 +144,30 @@ static inline uint16_t f2h(float f) {  // fp32 -> fp16, round to nearest even, s
   return static_cast<uint16_t>(sign | (static_cast<uint32_t>(e + 15) << 10) + (e == -15 ? r : r - 0x400u));
 }
 
-// W [N, ldw] fp32, columns [col0, col0+K) zero-padded to Kpad -> Kpad/16 slabs.  One slab = two pieces (output rows
-// 0..N/2-1 and N/2..N-1, one per CTA of a pair); one piece = [2 k chunks][N/16 row groups][8 rows][8 k] 16-bit.
-static uint8_t* pack_linear_fast(const float* W, int N, int K, int ldw, int col0, int Kpad, bool fp16, uint8_t* out) {
+// One step of the layer program: K = the concatenation of up to two column segments of W [N, ldw], each zero-padded
+// to a multiple of 16.  Layout [rank 0..1][K16 block][piece]: rank r holds output rows r*N/2 .. (r+1)*N/2-1 (the half
+// its CTA of the pair streams), one piece = [2 k chunks][N/16 row groups][8 rows][8 k] 16-bit.
+struct FastSeg {
+  const float* W;
+  int K, ldw, col0, Kpad;
+};
+static uint8_t* pack_step_fast(int N, const FastSeg* segs, int n_segs, bool fp16, uint8_t* out) {
   const int half = N / 2;
-  for (int k16 = 0; k16 < Kpad / 16; ++k16) {
-    for (int r = 0; r < 2; ++r) {
-      uint16_t* dst = reinterpret_cast<uint16_t*>(out);
-      for (int kc = 0; kc < 2; ++kc)
-        for (int n = 0; n < half; ++n)
-          for (int e = 0; e < 8; ++e) {
-            const int k = k16 * 16 + kc * 8 + e;
-            const float w = k < K ? W[static_cast<size_t>(r * half + n) * ldw + col0 + k] : 0.f;
-            dst[static_cast<size_t>(kc) * half * 8 + static_cast<size_t>(n >> 3) * 64 + (n & 7) * 8 + e] = fp16 ? f2h(w) : f2bf(w);
-          }
-      out += static_cast<size_t>(half) * 32;
+  for (int r = 0; r < 2; ++r)
+    for (int sg = 0; sg < n_segs; ++sg) {
+      const FastSeg& g = segs[sg];
+      for (int k16 = 0; k16 < g.Kpad / 16; ++k16) {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(out);
+        for (int kc = 0; kc < 2; ++kc)
+          for (int n = 0; n < half; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int k = k16 * 16 + kc * 8 + e;
+              const float w = k < g.K ? g.W[static_cast<size_t>(r * half + n) * g.ldw + g.col0 + k] : 0.f;
+              dst[static_cast<size_t>(kc) * half * 8 + static_cast<size_t>(n >> 3) * 64 + (n & 7) * 8 + e] = fp16 ? f2h(w) : f2bf(w);
+            }
+        out += static_cast<size_t>(half) * 32;
+      }
     }
-  }
   return out;
 }
 
@@ -174,15 +181,30 @@ extern "C" int b200nerf_nerf_pack_fast(const float* const* t, int prec, void* h_
   const float* W[8];
   for (int i = 0; i < 8; ++i) W[i] = t[2 * i];
   const float *Wv = t[16], *Wf = t[18];
-  o = pack_linear_fast(W[0], 256, 63, 63, 0, 64, fp16, o);              // step 0: pts_linears.0 over gamma(pts)
-  for (int i = 1; i <= 4; ++i) o = pack_linear_fast(W[i], 256, 256, 256, 0, 256, fp16, o);
-  o = pack_linear_fast(W[5], 256, 256, 319, 63, 256, fp16, o);          // step 5: hidden columns first ...
-  o = pack_linear_fast(W[5], 256, 63, 319, 0, 64, fp16, o);             //         ... then the re-concatenated gamma(pts)
-  o = pack_linear_fast(W[6], 256, 256, 256, 0, 256, fp16, o);
-  o = pack_linear_fast(W[7], 256, 256, 256, 0, 256, fp16, o);
-  o = pack_linear_fast(Wf, 256, 256, 256, 0, 256, fp16, o);             // step 8: feature_linear
-  o = pack_linear_fast(Wv, 128, 256, 283, 0, 256, fp16, o);             // step 9: views_linears.0, feature columns ...
-  o = pack_linear_fast(Wv, 128, 27, 283, 256, 32, fp16, o);             //         ... then gamma(viewdir)
+  {
+    const FastSeg sg[1] = {{W[0], 63, 63, 0, 64}};                               // step 0: pts_linears.0 over gamma(pts)
+    o = pack_step_fast(256, sg, 1, fp16, o);
+  }
+  for (int i = 1; i <= 4; ++i) {
+    const FastSeg sg[1] = {{W[i], 256, 256, 0, 256}};
+    o = pack_step_fast(256, sg, 1, fp16, o);
+  }
+  {
+    const FastSeg sg[2] = {{W[5], 256, 319, 63, 256}, {W[5], 63, 319, 0, 64}};   // step 5: hidden columns, then gamma(pts)
+    o = pack_step_fast(256, sg, 2, fp16, o);
+  }
+  for (int i = 6; i <= 7; ++i) {
+    const FastSeg sg[1] = {{W[i], 256, 256, 0, 256}};
+    o = pack_step_fast(256, sg, 1, fp16, o);
+  }
+  {
+    const FastSeg sg[1] = {{Wf, 256, 256, 0, 256}};                              // step 8: feature_linear
+    o = pack_step_fast(256, sg, 1, fp16, o);
+  }
+  {
+    const FastSeg sg[2] = {{Wv, 256, 283, 0, 256}, {Wv, 27, 283, 256, 32}};      // step 9: feature columns, then gamma(viewdir)
+    o = pack_step_fast(128, sg, 2, fp16, o);
+  }
   if (static_cast<size_t>(o - static_cast<uint8_t*>(h_wpack)) != fast::WPACK_BYTES)
     return fail("b200nerf_nerf_pack_fast: internal size mismatch");
   return 0;
@@ -638,20 +660,12 @@ static int make_piece_tmap(const void* wpack, int rows, fast::TMap* out) {
   return 0;
 }
 
-static int g_fast_ncta = 2;  // CTA-pair kernel by default; B200NERF_FAST_NCTA=1 selects the single-CTA variant
-static void read_fast_env() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  const char* e = getenv("B200NERF_FAST_NCTA");
-  if (e && e[0] == '1') g_fast_ncta = 1;
-}
-
-template <int NCTA, bool FP16>
+template <bool FP16>
 static int launch_fast(const fast::FastParams& p, cudaStream_t st) {
   static int grid_cap = 0;
-  constexpr int smem = fast::smem_bytes<NCTA>();
-  auto kern = fast::nerf_fast_kernel<NCTA, FP16>;
+  constexpr int smem = fast::smem_bytes();
+  constexpr int NCTA = fast::NCTA;
+  auto kern = fast::nerf_fast_kernel<FP16>;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -669,14 +683,12 @@ static int launch_fast(const fast::FastParams& p, cudaStream_t st) {
     const int sms = sm_count();
     if (sms <= 0) return fail("no CUDA device");
     int cap = (sms / NCTA) * NCTA;
-    if (NCTA > 1) {
-      // a persistent grid must be co-resident: ask how many clusters fit
-      cfg.gridDim = dim3(cap);
-      int n_clusters = 0;
-      CUDA_TRY(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
-      if (n_clusters <= 0) return fail("nerf_fast_kernel: no resident cluster fits");
-      if (n_clusters * NCTA < cap) cap = n_clusters * NCTA;
-    }
+    // a persistent grid must be co-resident: ask how many CTA pairs fit
+    cfg.gridDim = dim3(cap);
+    int n_clusters = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
+    if (n_clusters <= 0) return fail("nerf_fast_kernel: no resident cluster fits");
+    if (n_clusters * NCTA < cap) cap = n_clusters * NCTA;
     grid_cap = cap;
   }
   const int tiles = (p.n_rows + fast::TILE_M - 1) / fast::TILE_M;
@@ -685,14 +697,10 @@ static int launch_fast(const fast::FastParams& p, cudaStream_t st) {
   if (grid > grid_cap) grid = grid_cap;
   cfg.gridDim = dim3(grid);
   fast::TMap tm_full, tm_half;
-  memset(&tm_full, 0, sizeof(tm_full));
-  memset(&tm_half, 0, sizeof(tm_half));
-  if (NCTA == 2) {
-    int rc = make_piece_tmap(p.wpack, 8, &tm_full);
-    if (rc) return rc;
-    rc = make_piece_tmap(p.wpack, 4, &tm_half);
-    if (rc) return rc;
-  }
+  int rc = make_piece_tmap(p.wpack, 16, &tm_full);   // one ring stage of an N = 256 step: 2 pieces x 4 KB
+  if (rc) return rc;
+  rc = make_piece_tmap(p.wpack, 8, &tm_half);        // ... of the N = 128 view layer: 2 pieces x 2 KB
+  if (rc) return rc;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, tm_full, tm_half));
   LAUNCH_CHECK();
   return 0;
@@ -709,7 +717,6 @@ extern "C" int b200nerf_nerf_mlp_fast_fwd(const void* wpack_fast, const float* a
   if (prec != B200NERF_PREC_FP16 && prec != B200NERF_PREC_BF16) return fail("b200nerf_nerf_mlp_fast_fwd: prec must be FP16 or BF16");
   if (static_cast<long long>(n_rays) * S > 0x7ffff000LL) return fail("b200nerf_nerf_mlp_fast_fwd: too many points for one call");
   if (guard_count && (!guard_list || guard_cap <= 0)) return fail("b200nerf_nerf_mlp_fast_fwd: guard list missing");
-  read_fast_env();
   fast::FastParams p;
   memset(&p, 0, sizeof(p));
   p.wpack = static_cast<const uint8_t*>(wpack_fast);
@@ -727,9 +734,7 @@ extern "C" int b200nerf_nerf_mlp_fast_fwd(const void* wpack_fast, const float* a
   p.guard_cap = guard_cap;
   p.guard_kappa = guard_kappa;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool fp16 = prec == B200NERF_PREC_FP16;
-  if (g_fast_ncta == 2) return fp16 ? launch_fast<2, true>(p, st) : launch_fast<2, false>(p, st);
-  return fp16 ? launch_fast<1, true>(p, st) : launch_fast<1, false>(p, st);
+  return prec == B200NERF_PREC_FP16 ? launch_fast<true>(p, st) : launch_fast<false>(p, st);
 }
 
 extern "C" int b200nerf_nerf_mlp_guarded_fwd(const void* wpack_fast, const void* wpack_split, const float* aux, int prec,

@@ -4,12 +4,13 @@
 // (nerf_pytorch/run_nerf_helpers.py:109-134): gamma(pts) 63-wide, gamma(viewdirs) 27-wide, 8x256 ReLU trunk
 // with the input re-concatenated at layer 5, alpha head, feature layer, 128-wide view layer, rgb head.
 //
-// Throughput design (one persistent CTA per SM, optionally paired as a 2-CTA cluster):
+// Throughput design (one persistent CTA per SM, SMs paired as 2-CTA clusters):
 //   * two 128-row tiles ("slots") are resident per CTA and ping-pong: while the tensor core runs layer L of
 //     slot 0 the epilogue warps turn the finished accumulator of slot 1 into its next operand, so the tensor
 //     pipe never waits for an epilogue that is shorter than one layer of MMAs
-//   * NCTA == 2: the pair issues tcgen05.mma.cta_group::2 (M = 256 over both CTAs); each CTA streams only its
-//     half of every weight slab, which halves L2->SM weight traffic and B-operand shared-memory reads per SM
+//   * the pair issues tcgen05.mma.cta_group::2 (M = 256 over both CTAs); each CTA streams only its half of
+//     every weight slab (TMA, cta_group::2 completion on the leader's barrier), which halves L2->SM weight
+//     traffic and B-operand shared-memory reads per SM
 //   * operands: per slot one K-major no-swizzle buffer of 44 K chunks: [h 0..255 | gamma(pts) 256..319 |
 //     gamma(viewdir) 320..351]; every epilogue rewrites h in place (its readers have retired: acc_full)
 //   * TMEM: slot 0 accumulates in columns 0..255, slot 1 in 256..511
@@ -81,7 +82,10 @@ struct FastParams {
   float guard_kappa;
 };
 
-template <int NSTAGE>
+constexpr int NSTAGE = 4;                             // ring stages; one stage = this CTA's half of two K16 slabs
+constexpr int STAGE_BYTES = RING_BYTES / NSTAGE;      // 8 KB
+constexpr int NCTA = 2;                               // CTAs per cluster (tcgen05 cta_group::2 pair)
+
 struct __align__(16) Tail {
   uint64_t full[NSTAGE];
   uint64_t empty[NSTAGE];
@@ -97,11 +101,8 @@ struct __align__(16) Tail {
   float eabs_part[2][TILE_M];   // ... and of sum |h7 * w_alpha|
 };
 
-template <int NCTA>
-__host__ __device__ constexpr int num_stages() { return NCTA == 2 ? 8 : 4; }
-template <int NCTA>
 __host__ __device__ constexpr int smem_bytes() {
-  return 2 * TILE_ACT_BYTES + RING_BYTES + AUX_FLOATS * 4 + static_cast<int>(sizeof(Tail<num_stages<NCTA>()>));
+  return 2 * TILE_ACT_BYTES + RING_BYTES + AUX_FLOATS * 4 + static_cast<int>(sizeof(Tail));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,21 +221,18 @@ __device__ __forceinline__ void epi_rgb32(const uint32_t (&v)[32], const float* 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int NCTA, bool FP16>
+template <bool FP16>
 __global__ void __launch_bounds__(THREADS, 1)
 nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ TMap tm_full, const __grid_constant__ TMap tm_half) {
-  constexpr int NSTAGE = num_stages<NCTA>();
-  constexpr int STAGE_BYTES = RING_BYTES / NSTAGE;  // NCTA 2: this CTA's half slab (4 KB); NCTA 1: the whole slab (8 KB)
-  using TailT = Tail<NSTAGE>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;
   uint8_t* ring = smem + 2 * TILE_ACT_BYTES;
   float* saux = reinterpret_cast<float*>(ring + RING_BYTES);
-  TailT* tail = reinterpret_cast<TailT*>(ring + RING_BYTES + AUX_FLOATS * 4);
+  Tail* tail = reinterpret_cast<Tail*>(ring + RING_BYTES + AUX_FLOATS * 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x / NCTA;
   const int n_clusters = gridDim.x / NCTA;
@@ -257,108 +255,109 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
     fence_mbar_init();
   }
   if (warp == 2) {
-    if (NCTA == 2) {
-      tmem_alloc_cg2(&tail->tmem_base, 512);
-      tmem_relinquish_cg2();
-    } else {
-      tmem_alloc(&tail->tmem_base, 512);
-      tmem_relinquish();
-    }
+    tmem_alloc_cg2(&tail->tmem_base, 512);
+    tmem_relinquish_cg2();
   }
   for (int i = threadIdx.x; i < AUX_FLOATS; i += THREADS) saux[i] = p.aux[i];
   tc_fence_before();
-  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
+  const uint32_t tail_addr = smem_u32(tail);
+  const uint32_t full_addr = tail_addr + offsetof(Tail, full), empty_addr = tail_addr + offsetof(Tail, empty);
 
   if (warp == 0) {
-    // ===================================================================== weight producer
+    // ===================================================================== weight producer (whole warp, one lane issues)
     if (lane == 0) {
-      if (NCTA == 2) {
-        tma_prefetch_desc(&tm_full);
-        tma_prefetch_desc(&tm_half);
-      }
-      const uint32_t ring_addr = smem_u32(ring);
-      uint32_t it = 0;
-      for (int u = cluster_id; u < n_units; u += n_clusters) {
-        for (int s = 0; s < NSTEPS; ++s) {
-          const int nk = step_nk(s);
-          const uint32_t slab = static_cast<uint32_t>(step_n(s)) * 32u;   // bytes of one K16 slab (both halves)
-          const uint32_t woff = step_woff(s);
-          for (int slot = 0; slot < 2; ++slot) {
-            for (int k = 0; k < nk; ++k, ++it) {
-              const uint32_t stage = it % NSTAGE;
-              const uint32_t ph = (it / NSTAGE) & 1u;
-              mbar_wait(&tail->empty[stage], ph ^ 1u);
-              const uint32_t off = woff + static_cast<uint32_t>(k) * slab;
-              if (NCTA == 2) {
-                // the pair's leader owns the full barrier: both halves complete_tx on it
-                if (leader) mbar_arrive_expect_tx(&tail->full[stage], slab);
-                const uint32_t bar = mapa_u32(smem_u32(&tail->full[stage]), 0);
-                const uint32_t my_off = off + rank * (slab / 2);
-                tma_load_2d_cg2(ring_addr + stage * STAGE_BYTES, s == 9 ? &tm_half : &tm_full, 0,
-                                static_cast<int>(my_off / 512u), bar);
-              } else {
-                mbar_arrive_expect_tx(&tail->full[stage], slab);
-                tma_load_1d(ring + stage * STAGE_BYTES, p.wpack + off, slab, &tail->full[stage]);
-              }
+      tma_prefetch_desc(&tm_full);
+      tma_prefetch_desc(&tm_half);
+    }
+    const uint32_t ring_addr = smem_u32(ring);
+    const uint32_t lead_full = mapa_u32(full_addr, 0);   // both halves complete_tx on the leader's barrier
+    uint32_t stage = 0, phase = 0;
+    for (int u = cluster_id; u < n_units; u += n_clusters) {
+      for (int s = 0; s < NSTEPS; ++s) {
+        const int n2 = step_nk(s) / 2;                                          // stages of this step
+        const uint32_t piece = static_cast<uint32_t>(step_n(s)) * 16u;          // this CTA's half of one K16 slab
+        // this CTA's pieces of the step are contiguous in the pack: [step][rank][k16][piece]
+        const int row0 = static_cast<int>((step_woff(s) + rank * static_cast<uint32_t>(step_nk(s)) * piece) / 512u);
+        const int rows_per_stage = static_cast<int>(2u * piece / 512u);
+        const void* tm = s == NSTEPS - 1 ? static_cast<const void*>(&tm_half) : static_cast<const void*>(&tm_full);
+        for (int slot = 0; slot < 2; ++slot) {
+          for (int k2 = 0; k2 < n2; ++k2) {
+            mbar_wait_lean(empty_addr + stage * 8u, phase ^ 1u);
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx_addr(full_addr + stage * 8u, 4u * piece);
+              tma_load_2d_cg2(ring_addr + stage * STAGE_BYTES, tm, 0, row0 + k2 * rows_per_stage, lead_full + stage * 8u);
+            }
+            __syncwarp();
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1u;
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (pair leader only)
-    if (lane == 0 && leader) {
+    // ===================================================================== MMA issuer (pair leader; whole warp, one lane issues)
+    if (leader) {
       const uint32_t act_addr = smem_u32(act);
       const uint32_t ring_addr = smem_u32(ring);
-      uint32_t it = 0, ca[2] = {0, 0}, ce[2] = {0, 0}, cv[2] = {0, 0};
+      const uint32_t acc_full_addr = tail_addr + offsetof(Tail, acc_full);
+      const uint32_t a_ready_addr = tail_addr + offsetof(Tail, a_ready);
+      const uint32_t enc_ready_addr = tail_addr + offsetof(Tail, enc_ready);
+      const uint32_t view_ready_addr = tail_addr + offsetof(Tail, view_ready);
+      const uint32_t pts_free_addr = tail_addr + offsetof(Tail, pts_free);
+      const uint32_t view_free_addr = tail_addr + offsetof(Tail, view_free);
+      constexpr uint64_t A_STEP = (2 * KC_STRIDE) >> 4;   // descriptor increment of one K16 block of the operand
+      uint32_t stage = 0, phase = 0, ca[2] = {0, 0}, ce[2] = {0, 0}, cv[2] = {0, 0};
       bool first = true;
       for (int u = cluster_id; u < n_units; u += n_clusters) {
+#pragma unroll 1
         for (int s = 0; s < NSTEPS; ++s) {
-          const int nk1 = step_nk1(s), nk = step_nk(s);
-          const int kb1 = step_kb1(s), kb2 = step_kb2(s);
+          const int n1 = step_nk1(s) / 2, n2 = step_nk(s) / 2;
           const uint32_t n = static_cast<uint32_t>(step_n(s));
-          const uint32_t piece = n * 16u;                       // bytes of one CTA's half of a K16 slab
-          const uint32_t idesc1 = umma_idesc_f16(FP16 ? 0u : 1u, 128, n / 2);
-          const uint32_t idesc2 = umma_idesc_f16(FP16 ? 0u : 1u, 256, n);
+          const uint32_t piece = n * 16u;
+          const uint32_t idesc = umma_idesc_f16(FP16 ? 0u : 1u, 256, n);
+          const uint64_t b_lbo_sbo = umma_desc_kmajor(0, piece / 2, 128);
+#pragma unroll
           for (int slot = 0; slot < 2; ++slot) {
             if (s == 0) {
-              mbar_wait_cluster(&tail->enc_ready[slot], ce[slot]++ & 1u);
-              if (!first) mbar_wait_cluster(&tail->a_ready[slot], ca[slot]++ & 1u);
+              mbar_wait_lean(enc_ready_addr + slot * 8u, ce[slot]++ & 1u);
+              if (!first) mbar_wait_lean(a_ready_addr + slot * 8u, ca[slot]++ & 1u);
             } else {
-              mbar_wait_cluster(&tail->a_ready[slot], ca[slot]++ & 1u);
+              mbar_wait_lean(a_ready_addr + slot * 8u, ca[slot]++ & 1u);
             }
-            if (s == NSTEPS - 1) mbar_wait_cluster(&tail->view_ready[slot], cv[slot]++ & 1u);
+            if (s == NSTEPS - 1) mbar_wait_lean(view_ready_addr + slot * 8u, cv[slot]++ & 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + slot * 256u;
-            const uint32_t a_base = act_addr + slot * TILE_ACT_BYTES;
-            for (int k = 0; k < nk; ++k, ++it) {
-              const uint32_t stage = it % NSTAGE;
-              const uint32_t ph = (it / NSTAGE) & 1u;
-              mbar_wait(&tail->full[stage], ph);
+            const uint64_t a_base = umma_desc_kmajor(act_addr + slot * TILE_ACT_BYTES, KC_STRIDE, 128);
+            uint64_t a_desc = a_base + static_cast<uint64_t>(step_kb1(s)) * A_STEP;
+            for (int k2 = 0; k2 < n2; ++k2) {
+              if (k2 == n1) a_desc = a_base + static_cast<uint64_t>(step_kb2(s)) * A_STEP;
+              mbar_wait_lean(full_addr + stage * 8u, phase);
               tc_fence_after();
-              const int kb = k < nk1 ? kb1 + k : kb2 + (k - nk1);
-              const uint64_t a_desc = umma_desc_kmajor(a_base + kb * 2 * KC_STRIDE, KC_STRIDE, 128);
-              const uint32_t b_addr = ring_addr + stage * STAGE_BYTES;
-              if (NCTA == 2) {
-                tc_mma_f16_cg2(d_tmem, a_desc, umma_desc_kmajor(b_addr, piece / 2, 128), idesc2, k > 0 ? 1u : 0u);
-                tc_commit_cg2(&tail->empty[stage], 3);
-              } else {
-                tc_mma_bf16(d_tmem, a_desc, umma_desc_kmajor(b_addr, piece / 2, 128), idesc1, k > 0 ? 1u : 0u);
-                tc_mma_bf16(d_tmem + n / 2, a_desc, umma_desc_kmajor(b_addr + piece, piece / 2, 128), idesc1, k > 0 ? 1u : 0u);
-                tc_commit(&tail->empty[stage]);
+              const uint64_t b_desc = b_lbo_sbo + ((ring_addr + stage * STAGE_BYTES) >> 4);
+              if (elect_one()) {
+                if (k2 == 0) tc_mma_f16_cg2_imm<false>(d_tmem, a_desc, b_desc, idesc);
+                else tc_mma_f16_cg2_imm<true>(d_tmem, a_desc, b_desc, idesc);
+                tc_mma_f16_cg2_imm<true>(d_tmem, a_desc + A_STEP, b_desc + (piece >> 4), idesc);
+                tc_commit_cg2_addr(empty_addr + stage * 8u, 3);
+              }
+              __syncwarp();
+              a_desc += 2 * A_STEP;
+              if (++stage == NSTAGE) {
+                stage = 0;
+                phase ^= 1u;
               }
             }
-            if (NCTA == 2) {
-              tc_commit_cg2(&tail->acc_full[slot], 3);
-              if (s == 5) tc_commit_cg2(&tail->pts_free[slot], 3);
-              if (s == NSTEPS - 1) tc_commit_cg2(&tail->view_free[slot], 3);
-            } else {
-              tc_commit(&tail->acc_full[slot]);
-              if (s == 5) tc_commit(&tail->pts_free[slot]);
-              if (s == NSTEPS - 1) tc_commit(&tail->view_free[slot]);
+            if (elect_one()) {
+              tc_commit_cg2_addr(acc_full_addr + slot * 8u, 3);
+              if (s == 5) tc_commit_cg2_addr(pts_free_addr + slot * 8u, 3);
+              if (s == NSTEPS - 1) tc_commit_cg2_addr(view_free_addr + slot * 8u, 3);
             }
+            __syncwarp();
           }
         }
         first = false;
@@ -368,16 +367,14 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
     // ===================================================================== encoders (one tile ahead)
     const int row = (warp - PRO_WARP0) * 32 + lane;
     const int row_off = (row >> 3) * 128 + (row & 7) * 16;
+    const uint32_t pts_free_addr = tail_addr + offsetof(Tail, pts_free);
+    const uint32_t view_free_addr = tail_addr + offsetof(Tail, view_free);
+    const uint32_t enc_bar = mapa_u32(tail_addr + offsetof(Tail, enc_ready), 0);
+    const uint32_t view_bar = mapa_u32(tail_addr + offsetof(Tail, view_ready), 0);
     uint32_t cp[2] = {0, 0}, cw[2] = {0, 0};
     bool first = true;
-    uint32_t enc_bar[2], view_bar[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      enc_bar[i] = NCTA == 2 ? mapa_u32(smem_u32(&tail->enc_ready[i]), 0) : 0u;
-      view_bar[i] = NCTA == 2 ? mapa_u32(smem_u32(&tail->view_ready[i]), 0) : 0u;
-    }
     for (int u = cluster_id; u < n_units; u += n_clusters) {
-#pragma unroll 1
+#pragma unroll
       for (int slot = 0; slot < 2; ++slot) {
         const int grow = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + row;
         float x[3] = {0.f, 0.f, 0.f};
@@ -394,17 +391,15 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
           }
         }
         if (!first) {
-          mbar_wait(&tail->pts_free[slot], cp[slot]++ & 1u);   // the previous tile's skip layer has retired
+          mbar_wait_lean(pts_free_addr + slot * 8u, cp[slot]++ & 1u);   // the previous tile's skip layer has retired
           tc_fence_after();
         }
         encode_store<FP16, 10, 8>(x, act + slot * TILE_ACT_BYTES + ENC_KB * 2 * KC_STRIDE + row_off);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          if (NCTA == 2) mbar_arrive_cluster(enc_bar[slot]); else mbar_arrive(&tail->enc_ready[slot]);
-        }
+        if (lane == 0) mbar_arrive_remote(enc_bar + slot * 8u);
       }
-#pragma unroll 1
+#pragma unroll
       for (int slot = 0; slot < 2; ++slot) {
         const int grow = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + row;
         float v[3] = {0.f, 0.f, 0.f};
@@ -414,15 +409,13 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
           for (int t = 0; t < 3; ++t) v[t] = __ldg(p.viewdirs + ray * 3 + t);
         }
         if (!first) {
-          mbar_wait(&tail->view_free[slot], cw[slot]++ & 1u);  // the previous tile's view layer has retired
+          mbar_wait_lean(view_free_addr + slot * 8u, cw[slot]++ & 1u);  // the previous tile's view layer has retired
           tc_fence_after();
         }
         encode_store<FP16, 4, 4>(v, act + slot * TILE_ACT_BYTES + VIEW_KB * 2 * KC_STRIDE + row_off);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          if (NCTA == 2) mbar_arrive_cluster(view_bar[slot]); else mbar_arrive(&tail->view_ready[slot]);
-        }
+        if (lane == 0) mbar_arrive_remote(view_bar + slot * 8u);
       }
       first = false;
     }
@@ -433,10 +426,9 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
     const int row = q * 32 + lane;
     const int row_off = (row >> 3) * 128 + (row & 7) * 16;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t acc_full_addr = tail_addr + offsetof(Tail, acc_full);
+    const uint32_t rdy_bar = mapa_u32(tail_addr + offsetof(Tail, a_ready), 0);
     uint32_t cf[2] = {0, 0};
-    uint32_t rdy_bar[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) rdy_bar[i] = NCTA == 2 ? mapa_u32(smem_u32(&tail->a_ready[i]), 0) : 0u;
     float alpha_keep[2] = {0.f, 0.f}, eabs_keep[2] = {0.f, 0.f};
 
     for (int u = cluster_id; u < n_units; u += n_clusters) {
@@ -444,7 +436,7 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
       for (int s = 0; s < NSTEPS; ++s) {
 #pragma unroll
         for (int slot = 0; slot < 2; ++slot) {
-          mbar_wait(&tail->acc_full[slot], cf[slot]++ & 1u);
+          mbar_wait_lean(acc_full_addr + slot * 8u, cf[slot]++ & 1u);
           tc_fence_after();
           const uint32_t tacc = t_lane + slot * 256u;
           uint8_t* a_tile = act + slot * TILE_ACT_BYTES;
@@ -508,9 +500,7 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
           if (s < NSTEPS - 1) fence_proxy_async_smem();    // operand stores -> visible to the tensor core
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
-            if (NCTA == 2) mbar_arrive_cluster(rdy_bar[slot]); else mbar_arrive(&tail->a_ready[slot]);
-          }
+          if (lane == 0) mbar_arrive_remote(rdy_bar + slot * 8u);
         }
       }
     }
@@ -518,10 +508,8 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
 
   __syncwarp();
   tc_fence_before();
-  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
-  if (warp == 2) {
-    if (NCTA == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
-  }
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_cg2(tmem_base, 512);
 }
 
 }  // namespace fast
