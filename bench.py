@@ -32,6 +32,9 @@ DISTANCE = 0.1
 NERF_FLOP_PER_POINT = 1_186_816          # 2 * 593,408 MAC, literal network
 DEPTHNET_FLOP_PER_RAY = 6_660_608        # literal network (the folded inference form executes 1,309,184)
 COMPOSITE_BYTES_PER_RAY = 24 * S + 36
+# dram__bytes_read.sum + dram__bytes_write.sum of the NeRF MLP kernel, one 800x800x64 launch, from the committed
+# ncu --set full captures (profiles/r1b_ncu_summary.md, profiles/r1a_ncu_summary.md); algorithmic I/O is 819 MB
+NCU_DRAM_BYTES_PER_LAUNCH = {"fast": 797.4e6, "fp16": 797.4e6, "split": 816.3e6}
 
 
 def peaks():
@@ -340,7 +343,8 @@ def main():
                          "kernel": ("nerf_fast_kernel<2,fp16> (+ mlp_chain_kernel<SPLIT> over the guard band) via b200nerf_nerf_query"
                                     if prec in (PREC_FAST, PREC_FP16) else "mlp_chain_kernel<NERF> via b200nerf_nerf_query"),
                          "achieved": mlp_tflops,
-                         "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tf_sustained"], "traffic": None,
+                         "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tf_sustained"],
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.prec),
                          "peak_source": pk["src"] + ", sustained bf16", "ms_per_launch": k_ms[2],
                          "algorithmic_flop_per_point": NERF_FLOP_PER_POINT,
                          "executed_mma_tflops": mlp_tflops * (3 if prec == PREC_SPLIT else 1) * (1_187_840 / 1_186_816),

@@ -8,7 +8,7 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libb200nerf.so")
+LIB_PATH = os.environ.get("B200NERF_LIB") or os.path.join(PKG_DIR, "libb200nerf.so")
 SOURCES = ["b200nerf.cu", "sampling.cu"]
 HEADERS = ["ptx.cuh", "mlp_chain.cuh", "mlp_fast.cuh", "host_common.h", os.path.join("..", "..", "include", "b200nerf.h")]
 
@@ -34,17 +34,18 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str = None) -> str:
     """Compile the CUDA library if it is missing or older than its sources; returns its path."""
-    if not force and not is_stale():
+    out_path = out_path or LIB_PATH
+    if not force and not is_stale() and out_path == LIB_PATH:
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out_path] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out_path
 
 
 if __name__ == "__main__":

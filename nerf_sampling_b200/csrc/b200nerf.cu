@@ -706,6 +706,10 @@ static int launch_fast(const fast::FastParams& p, cudaStream_t st) {
   return 0;
 }
 
+static long long* g_timeline = nullptr;
+/* debug hook (only effective in -DB200NERF_TIMELINE builds): device buffer of 3*80*4 int64 clock stamps */
+extern "C" void b200nerf_debug_set_timeline(long long* dev_buf) { g_timeline = dev_buf; }
+
 extern "C" int b200nerf_nerf_mlp_fast_fwd(const void* wpack_fast, const float* aux, int prec, const float* rays_o,
                                           const float* rays_d, const float* viewdirs, const float* z, const float* pts,
                                           int n_rays, int S, float* out_raw, int* guard_count, int* guard_list, int guard_cap,
@@ -733,6 +737,7 @@ extern "C" int b200nerf_nerf_mlp_fast_fwd(const void* wpack_fast, const float* a
   p.guard_list = guard_list;
   p.guard_cap = guard_cap;
   p.guard_kappa = guard_kappa;
+  p.timeline = g_timeline;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return prec == B200NERF_PREC_FP16 ? launch_fast<true>(p, st) : launch_fast<false>(p, st);
 }

@@ -399,6 +399,24 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const __gri
             o4.y = gs + part[row * 4 + 1] + __ldg(rb + 1);
             o4.z = bs + part[row * 4 + 2] + __ldg(rb + 2);
             o4.w = tail->head_part[0][row] + tail->head_part[1][row] + __ldg(p.aux + p.head_b_off);
+            // fmaxf(NaN, 0) = 0 but torch.relu(NaN) = NaN: a sample whose position or view direction is not finite
+            // (a ray that missed the sphere has a NaN depth) yields NaN like the reference
+            {
+              const int ry = grow / p.S;
+              float m = 0.f;
+              if (p.pts != nullptr) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) m += fabsf(__ldg(p.pts + (size_t)grow * 3 + t));
+              } else {
+                const float zz = __ldg(p.z + grow);
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+                  m += fabsf(__fadd_rn(__ldg(p.rays_o + ry * 3 + t), __fmul_rn(__ldg(p.rays_d + ry * 3 + t), zz)));
+              }
+#pragma unroll
+              for (int t = 0; t < 3; ++t) m += fabsf(__ldg(p.viewdirs + ry * 3 + t));
+              if (!(m < __int_as_float(0x7f800000))) o4.x = o4.y = o4.z = o4.w = __int_as_float(0x7fc00000);
+            }
             reinterpret_cast<float4*>(p.out)[grow] = o4;
           }
           named_bar_sync(1, EPI_THREADS);  // partials consumed before the next prologue rewrites the buffer

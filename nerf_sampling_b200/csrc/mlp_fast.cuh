@@ -24,6 +24,8 @@
 // |sigma| < kappa * sum_i |h7_i * w_alpha_i| to a list; the caller re-evaluates those points with the
 // split-precision kernel (mlp_chain.cuh) and overwrites them.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace b200 {
@@ -80,7 +82,19 @@ struct FastParams {
   int* guard_list;        // [guard_cap] point indices to re-evaluate
   int guard_cap;
   float guard_kappa;
+  long long* timeline;    // debug builds (-DB200NERF_TIMELINE): clock64 stamps of cluster 0's first units
 };
+
+#ifdef B200NERF_TIMELINE
+#define TL_STAMP(role, idx, j)                                                                         \
+  do {                                                                                                 \
+    if (p.timeline != nullptr && blockIdx.x == 0 && (idx) < 80) p.timeline[((role) * 80 + (idx)) * 4 + (j)] = clock64(); \
+  } while (0)
+#else
+#define TL_STAMP(role, idx, j) \
+  do {                         \
+  } while (0)
+#endif
 
 constexpr int NSTAGE = 4;                             // ring stages; one stage = this CTA's half of two K16 slabs
 constexpr int STAGE_BYTES = RING_BYTES / NSTAGE;      // 8 KB
@@ -218,6 +232,23 @@ __device__ __forceinline__ void epi_rgb32(const uint32_t (&v)[32], const float* 
   }
 }
 
+// true when the sample position and view direction of point `grow` are finite (sum of magnitudes < inf)
+__device__ __forceinline__ bool input_is_finite(const FastParams& p, int grow) {
+  const int ray = grow / p.S;
+  float m = 0.f;
+  if (p.pts != nullptr) {
+#pragma unroll
+    for (int t = 0; t < 3; ++t) m += fabsf(__ldg(p.pts + static_cast<size_t>(grow) * 3 + t));
+  } else {
+    const float zz = __ldg(p.z + grow);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) m += fabsf(__fadd_rn(__ldg(p.rays_o + ray * 3 + t), __fmul_rn(__ldg(p.rays_d + ray * 3 + t), zz)));
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) m += fabsf(__ldg(p.viewdirs + ray * 3 + t));
+  return m < __int_as_float(0x7f800000);
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -230,9 +261,9 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
   float* saux = reinterpret_cast<float*>(ring + RING_BYTES);
   Tail* tail = reinterpret_cast<Tail*>(ring + RING_BYTES + AUX_FLOATS * 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x / NCTA;
   const int n_clusters = gridDim.x / NCTA;
@@ -262,7 +293,7 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = tail->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tail->tmem_base, 0);
   const uint32_t tail_addr = smem_u32(tail);
   const uint32_t full_addr = tail_addr + offsetof(Tail, full), empty_addr = tail_addr + offsetof(Tail, empty);
 
@@ -310,19 +341,42 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
       const uint32_t view_ready_addr = tail_addr + offsetof(Tail, view_ready);
       const uint32_t pts_free_addr = tail_addr + offsetof(Tail, pts_free);
       const uint32_t view_free_addr = tail_addr + offsetof(Tail, view_free);
-      constexpr uint64_t A_STEP = (2 * KC_STRIDE) >> 4;   // descriptor increment of one K16 block of the operand
+      constexpr uint32_t A_STEP = (2 * KC_STRIDE) >> 4;   // descriptor increment of one K16 block of the operand
+      // descriptors: the high word (SBO, version) is constant, the low word is (address >> 4) | LBO field
+      constexpr uint32_t DESC_HI = static_cast<uint32_t>(((128ull >> 4) << 32 | (1ull << 46)) >> 32);
+      constexpr uint32_t A_LBO = (KC_STRIDE >> 4) << 16;
       uint32_t stage = 0, phase = 0, ca[2] = {0, 0}, ce[2] = {0, 0}, cv[2] = {0, 0};
       bool first = true;
+
+      // one ring stage = two K16 blocks: wait for the weights, issue two MMAs, release the stage
+      auto issue_stage = [&](auto acc_first, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lbo, uint32_t piece16, uint32_t idesc) {
+        mbar_wait_lean(full_addr + stage * 8u, phase);
+        tc_fence_after();
+        const uint32_t b_lo = b_lbo | ((ring_addr + stage * STAGE_BYTES) >> 4);
+        if (elect_one()) {
+          const uint64_t a0 = (static_cast<uint64_t>(DESC_HI) << 32) | a_lo;
+          const uint64_t b0 = (static_cast<uint64_t>(DESC_HI) << 32) | b_lo;
+          tc_mma_f16_cg2_imm<decltype(acc_first)::value>(d_tmem, a0, b0, idesc);
+          tc_mma_f16_cg2_imm<true>(d_tmem, a0 + A_STEP, b0 + piece16, idesc);
+          tc_commit_cg2_addr(empty_addr + stage * 8u, 3);
+        }
+        stage = (stage + 1) & (NSTAGE - 1);
+        phase ^= (stage == 0);
+      };
+
       for (int u = cluster_id; u < n_units; u += n_clusters) {
 #pragma unroll 1
         for (int s = 0; s < NSTEPS; ++s) {
           const int n1 = step_nk1(s) / 2, n2 = step_nk(s) / 2;
           const uint32_t n = static_cast<uint32_t>(step_n(s));
-          const uint32_t piece = n * 16u;
+          const uint32_t piece16 = n;                        // (n * 16 bytes) >> 4
           const uint32_t idesc = umma_idesc_f16(FP16 ? 0u : 1u, 256, n);
-          const uint64_t b_lbo_sbo = umma_desc_kmajor(0, piece / 2, 128);
+          const uint32_t b_lbo = ((n * 8u) >> 4) << 16;      // LBO = bytes between the two K chunks of a piece
+          const uint32_t kb1 = step_kb1(s), kb2 = step_kb2(s);
 #pragma unroll
           for (int slot = 0; slot < 2; ++slot) {
+            [[maybe_unused]] const int tl_idx = ((u - cluster_id) / n_clusters * NSTEPS + s) * 2 + slot;
+            if (lane == 0) TL_STAMP(0, tl_idx, 0);
             if (s == 0) {
               mbar_wait_lean(enc_ready_addr + slot * 8u, ce[slot]++ & 1u);
               if (!first) mbar_wait_lean(a_ready_addr + slot * 8u, ca[slot]++ & 1u);
@@ -330,34 +384,26 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
               mbar_wait_lean(a_ready_addr + slot * 8u, ca[slot]++ & 1u);
             }
             if (s == NSTEPS - 1) mbar_wait_lean(view_ready_addr + slot * 8u, cv[slot]++ & 1u);
-            tc_fence_after();
+            if (lane == 0) TL_STAMP(0, tl_idx, 1);
             const uint32_t d_tmem = tmem_base + slot * 256u;
-            const uint64_t a_base = umma_desc_kmajor(act_addr + slot * TILE_ACT_BYTES, KC_STRIDE, 128);
-            uint64_t a_desc = a_base + static_cast<uint64_t>(step_kb1(s)) * A_STEP;
-            for (int k2 = 0; k2 < n2; ++k2) {
-              if (k2 == n1) a_desc = a_base + static_cast<uint64_t>(step_kb2(s)) * A_STEP;
-              mbar_wait_lean(full_addr + stage * 8u, phase);
-              tc_fence_after();
-              const uint64_t b_desc = b_lbo_sbo + ((ring_addr + stage * STAGE_BYTES) >> 4);
-              if (elect_one()) {
-                if (k2 == 0) tc_mma_f16_cg2_imm<false>(d_tmem, a_desc, b_desc, idesc);
-                else tc_mma_f16_cg2_imm<true>(d_tmem, a_desc, b_desc, idesc);
-                tc_mma_f16_cg2_imm<true>(d_tmem, a_desc + A_STEP, b_desc + (piece >> 4), idesc);
-                tc_commit_cg2_addr(empty_addr + stage * 8u, 3);
-              }
-              __syncwarp();
-              a_desc += 2 * A_STEP;
-              if (++stage == NSTAGE) {
-                stage = 0;
-                phase ^= 1u;
-              }
+            const uint32_t a_base = A_LBO | ((act_addr + slot * TILE_ACT_BYTES) >> 4);
+            uint32_t a_lo = a_base + kb1 * A_STEP;
+            issue_stage(std::false_type{}, d_tmem, a_lo, b_lbo, piece16, idesc);
+            for (int k2 = 1; k2 < n1; ++k2) {
+              a_lo += 2 * A_STEP;
+              issue_stage(std::true_type{}, d_tmem, a_lo, b_lbo, piece16, idesc);
+            }
+            a_lo = a_base + kb2 * A_STEP;
+            for (int k2 = n1; k2 < n2; ++k2) {
+              issue_stage(std::true_type{}, d_tmem, a_lo, b_lbo, piece16, idesc);
+              a_lo += 2 * A_STEP;
             }
             if (elect_one()) {
               tc_commit_cg2_addr(acc_full_addr + slot * 8u, 3);
               if (s == 5) tc_commit_cg2_addr(pts_free_addr + slot * 8u, 3);
               if (s == NSTEPS - 1) tc_commit_cg2_addr(view_free_addr + slot * 8u, 3);
             }
-            __syncwarp();
+            if (lane == 0) TL_STAMP(0, tl_idx, 2);
           }
         }
         first = false;
@@ -436,8 +482,11 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
       for (int s = 0; s < NSTEPS; ++s) {
 #pragma unroll
         for (int slot = 0; slot < 2; ++slot) {
+          [[maybe_unused]] const int tl_idx = ((u - cluster_id) / n_clusters * NSTEPS + s) * 2 + slot;
+          if (lane == 0 && q == 0) TL_STAMP(1 + hf, tl_idx, 0);
           mbar_wait_lean(acc_full_addr + slot * 8u, cf[slot]++ & 1u);
           tc_fence_after();
+          if (lane == 0 && q == 0) TL_STAMP(1 + hf, tl_idx, 1);
           const uint32_t tacc = t_lane + slot * 256u;
           uint8_t* a_tile = act + slot * TILE_ACT_BYTES;
           if (s < 8) {
@@ -478,8 +527,11 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
             epi_rgb32(vb, saux + AUX_BV + 96, saux + AUX_WR + 96, r, g, b);
             const int grow = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + row;
             const bool valid = grow < p.n_rows;
-            const float sigma = alpha_keep[slot] + tail->alpha_part[slot][row] + saux[AUX_BA];
+            float sigma = alpha_keep[slot] + tail->alpha_part[slot][row] + saux[AUX_BA];
             if (valid) {
+              // The hardware ReLU (cvt.relu / fmaxf) maps NaN to 0, torch.relu keeps it: a sample whose position or
+              // view direction is not finite (a ray that missed the sphere has a NaN depth) yields NaN like the reference.
+              if (!input_is_finite(p, grow)) r = g = b = sigma = __int_as_float(0x7fc00000);
               reinterpret_cast<float4*>(p.out)[grow] =
                   make_float4(r + saux[AUX_BR], g + saux[AUX_BR + 1], b + saux[AUX_BR + 2], sigma);
             }
@@ -501,6 +553,7 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(rdy_bar + slot * 8u);
+          if (lane == 0 && q == 0) TL_STAMP(1 + hf, tl_idx, 2);
         }
       }
     }

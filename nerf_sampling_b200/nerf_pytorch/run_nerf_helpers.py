@@ -2,7 +2,7 @@
 
 ``NeRF`` keeps the reference's constructor, attribute names and ``state_dict`` keys (so ``200000.tar`` loads
 verbatim) but owns no arithmetic: the positional encoding and all twelve linear layers run inside the fused
-tcgen05 kernel (``b200nerf_nerf_mlp_fwd``), fed from a packed weight image cached on the module.
+tcgen05 kernels (``b200nerf_nerf_query``), fed from a packed weight image cached on the module.
 """
 
 from __future__ import annotations
@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..packing import PREC_SPLIT, PackedNeRF
+from ..packing import PREC_FAST, PackedNeRF
 
 img2mse = lambda x, y: torch.mean((x - y) ** 2)  # noqa: E731  (run_nerf_helpers.py:9)
 mse2psnr = lambda x: -10.0 * torch.log(x) / torch.log(torch.tensor([10.0], device=x.device))  # noqa: E731
@@ -67,7 +67,7 @@ class NeRF(nn.Module):
             self.rgb_linear = nn.Linear(W // 2, 3)
         else:
             self.output_linear = nn.Linear(W, output_ch)
-        self.precision = PREC_SPLIT
+        self.precision = PREC_FAST  # fp16 single pass + split-precision guard band; PREC_SPLIT = split everywhere
         self._packed = None
         self._packed_key = None
 

@@ -60,11 +60,13 @@ def lib():
     return _lib.lib()
 
 
-@pytest.fixture(scope="session")
-def b200_models(oracle_models):
-    """The product's module shells loaded with the same weights, on the GPU."""
+@pytest.fixture(scope="session", params=["fast", "split"])
+def b200_models(request, oracle_models):
+    """The product's module shells loaded with the same weights, on the GPU, once per NeRF precision mode:
+    "fast" (fp16 single pass + split-precision guard band, the default) and "split" (bf16 hi+lo everywhere)."""
     from nerf_sampling_b200.depth_nets import DepthNet
     from nerf_sampling_b200.nerf_pytorch.run_nerf_helpers import NeRF
+    from nerf_sampling_b200.packing import PREC_FAST, PREC_SPLIT
 
     coarse, fine, dn = oracle_models
     dev = torch.device("cuda")
@@ -72,6 +74,7 @@ def b200_models(oracle_models):
     def nerf(sd):
         m = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
         m.load_state_dict(sd)
+        m.precision = PREC_FAST if request.param == "fast" else PREC_SPLIT
         return m.to(dev)
 
     d = DepthNet(hidden_sizes=[256] * 10, cat_hidden_sizes=[256] * 10, sphere_radius=2.0)
