@@ -202,8 +202,9 @@ extern "C" int b200nerf_nerf_pack_fast(const float* const* t, int prec, void* h_
     o = pack_step_fast(256, sg, 1, fp16, o);
   }
   {
-    const FastSeg sg[2] = {{Wv, 256, 283, 0, 256}, {Wv, 27, 283, 256, 32}};      // step 9: feature columns, then gamma(viewdir)
-    o = pack_step_fast(128, sg, 2, fp16, o);
+    // step 9: feature columns, gamma(viewdir), and two all-zero K16 blocks that fill the last ring stage
+    const FastSeg sg[3] = {{Wv, 256, 283, 0, 256}, {Wv, 27, 283, 256, 32}, {Wv, 0, 283, 0, 32}};
+    o = pack_step_fast(128, sg, 3, fp16, o);
   }
   if (static_cast<size_t>(o - static_cast<uint8_t*>(h_wpack)) != fast::WPACK_BYTES)
     return fail("b200nerf_nerf_pack_fast: internal size mismatch");
@@ -696,12 +697,10 @@ static int launch_fast(const fast::FastParams& p, cudaStream_t st) {
   int grid = units * NCTA;
   if (grid > grid_cap) grid = grid_cap;
   cfg.gridDim = dim3(grid);
-  fast::TMap tm_full, tm_half;
-  int rc = make_piece_tmap(p.wpack, 16, &tm_full);   // one ring stage of an N = 256 step: 2 pieces x 4 KB
+  fast::TMap tm_full;
+  const int rc = make_piece_tmap(p.wpack, 16, &tm_full);   // one ring stage: 8 KB of this CTA's weight pieces
   if (rc) return rc;
-  rc = make_piece_tmap(p.wpack, 8, &tm_half);        // ... of the N = 128 view layer: 2 pieces x 2 KB
-  if (rc) return rc;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, tm_full, tm_half));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, tm_full));
   LAUNCH_CHECK();
   return 0;
 }

@@ -42,7 +42,7 @@ constexpr int AUX_FLOATS = 3080;
 constexpr int THREADS = 512;
 constexpr int NSTEPS = 10;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, PRO_WARP0 = 12, PRO_WARPS = 4;
-constexpr size_t WPACK_BYTES = 1187840;               // 136 slabs x 8 KB + 18 slabs x 4 KB
+constexpr size_t WPACK_BYTES = 1196032;               // 136 slabs x 8 KB + 20 slabs x 4 KB (view layer padded to K = 320)
 
 // aux block (float offsets) -- same layout as the split-precision kernel's NeRF aux
 enum : uint32_t { AUX_B0 = 0, AUX_BF = 2048, AUX_BV = 2304, AUX_WA = 2432, AUX_BA = 2688, AUX_WR = 2692, AUX_BR = 3076 };
@@ -57,9 +57,12 @@ __host__ __device__ constexpr int step_kb2(int s) { return s == 5 ? ENC_KB : VIE
 __host__ __device__ constexpr int step_n(int s) { return s == 9 ? 128 : 256; }
 __host__ __device__ constexpr int step_nk(int s) { return step_nk1(s) + step_nk2(s); }
 __host__ __device__ constexpr uint32_t step_bias(int s) { return s < 8 ? AUX_B0 + 256u * s : (s == 8 ? AUX_BF : AUX_BV); }
-__host__ __device__ constexpr uint32_t step_woff(int s) {  // byte offset of the step's first slab in the pack
+// ring stages of a step: one stage = 8 KB per CTA = two K16 blocks at N = 256, four at N = 128 (the view layer,
+// whose 18 blocks are padded to 20 with zero weights)
+__host__ __device__ constexpr int step_stages(int s) { return s == 9 ? 5 : step_nk(s) / 2; }
+__host__ __device__ constexpr uint32_t step_woff(int s) {  // byte offset of the step's first stage in the pack
   uint32_t o = 0;
-  for (int i = 0; i < s; ++i) o += static_cast<uint32_t>(step_nk(i)) * step_n(i) * 32u;
+  for (int i = 0; i < s; ++i) o += static_cast<uint32_t>(step_stages(i)) * 16384u;
   return o;
 }
 
@@ -99,6 +102,8 @@ struct FastParams {
 constexpr int NSTAGE = 4;                             // ring stages; one stage = this CTA's half of two K16 slabs
 constexpr int STAGE_BYTES = RING_BYTES / NSTAGE;      // 8 KB
 constexpr int NCTA = 2;                               // CTAs per cluster (tcgen05 cta_group::2 pair)
+constexpr int STAGGER = 5;                            // slot 1 runs this many steps behind slot 0, so that one slot's
+                                                      // epilogue-heavy tile boundary (steps 9, 0) meets the other's MMA-heavy steps
 
 struct __align__(16) Tail {
   uint64_t full[NSTAGE];
@@ -113,6 +118,7 @@ struct __align__(16) Tail {
   uint32_t pad[3];
   float alpha_part[2][TILE_M];  // column half 1's part of the sigma head, per slot
   float eabs_part[2][TILE_M];   // ... and of sum |h7 * w_alpha|
+  float rgb_part[2][3][TILE_M]; // column half 1's part of the rgb head
 };
 
 __host__ __device__ constexpr int smem_bytes() {
@@ -254,7 +260,7 @@ __device__ __forceinline__ bool input_is_finite(const FastParams& p, int grow) {
 // ---------------------------------------------------------------------------------------------
 template <bool FP16>
 __global__ void __launch_bounds__(THREADS, 1)
-nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ TMap tm_full, const __grid_constant__ TMap tm_half) {
+nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ TMap tm_full) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* act = smem;
   uint8_t* ring = smem + 2 * TILE_ACT_BYTES;
@@ -269,6 +275,10 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
   const int n_clusters = gridDim.x / NCTA;
   const int num_tiles = (p.n_rows + TILE_M - 1) / TILE_M;
   const int n_units = (num_tiles + 2 * NCTA - 1) / (2 * NCTA);   // one unit = 2 slots x NCTA tiles
+  // units this cluster works through; every role walks the same schedule: tick i runs step (i % 10) of slot 0 and
+  // step ((i - STAGGER) % 10) of slot 1
+  const int my_units = cluster_id < n_units ? (n_units - cluster_id + n_clusters - 1) / n_clusters : 0;
+  const int n_ticks = my_units > 0 ? my_units * NSTEPS + STAGGER : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) {
@@ -299,33 +309,28 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
 
   if (warp == 0) {
     // ===================================================================== weight producer (whole warp, one lane issues)
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_full);
-      tma_prefetch_desc(&tm_half);
-    }
+    if (lane == 0) tma_prefetch_desc(&tm_full);
     const uint32_t ring_addr = smem_u32(ring);
     const uint32_t lead_full = mapa_u32(full_addr, 0);   // both halves complete_tx on the leader's barrier
     uint32_t stage = 0, phase = 0;
-    for (int u = cluster_id; u < n_units; u += n_clusters) {
-      for (int s = 0; s < NSTEPS; ++s) {
-        const int n2 = step_nk(s) / 2;                                          // stages of this step
-        const uint32_t piece = static_cast<uint32_t>(step_n(s)) * 16u;          // this CTA's half of one K16 slab
-        // this CTA's pieces of the step are contiguous in the pack: [step][rank][k16][piece]
-        const int row0 = static_cast<int>((step_woff(s) + rank * static_cast<uint32_t>(step_nk(s)) * piece) / 512u);
-        const int rows_per_stage = static_cast<int>(2u * piece / 512u);
-        const void* tm = s == NSTEPS - 1 ? static_cast<const void*>(&tm_half) : static_cast<const void*>(&tm_full);
-        for (int slot = 0; slot < 2; ++slot) {
-          for (int k2 = 0; k2 < n2; ++k2) {
-            mbar_wait_lean(empty_addr + stage * 8u, phase ^ 1u);
-            if (elect_one()) {
-              if (leader) mbar_arrive_expect_tx_addr(full_addr + stage * 8u, 4u * piece);
-              tma_load_2d_cg2(ring_addr + stage * STAGE_BYTES, tm, 0, row0 + k2 * rows_per_stage, lead_full + stage * 8u);
-            }
-            __syncwarp();
-            if (++stage == NSTAGE) {
-              stage = 0;
-              phase ^= 1u;
-            }
+    for (int i = 0; i < n_ticks; ++i) {
+      for (int slot = 0; slot < 2; ++slot) {
+        const int j = i - slot * STAGGER;
+        if (j < 0 || j >= my_units * NSTEPS) continue;
+        const int s = j % NSTEPS;
+        const int n2 = step_stages(s);
+        // this CTA's stages of the step are contiguous in the pack: [step][rank][stage][8 KB]
+        const int row0 = static_cast<int>((step_woff(s) + rank * static_cast<uint32_t>(n2) * STAGE_BYTES) / 512u);
+        for (int k2 = 0; k2 < n2; ++k2) {
+          mbar_wait_lean(empty_addr + stage * 8u, phase ^ 1u);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx_addr(full_addr + stage * 8u, 2u * STAGE_BYTES);
+            tma_load_2d_cg2(ring_addr + stage * STAGE_BYTES, &tm_full, 0, row0 + k2 * (STAGE_BYTES / 512), lead_full + stage * 8u);
+          }
+          __syncwarp();
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
@@ -346,7 +351,6 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
       constexpr uint32_t DESC_HI = static_cast<uint32_t>(((128ull >> 4) << 32 | (1ull << 46)) >> 32);
       constexpr uint32_t A_LBO = (KC_STRIDE >> 4) << 16;
       uint32_t stage = 0, phase = 0, ca[2] = {0, 0}, ce[2] = {0, 0}, cv[2] = {0, 0};
-      bool first = true;
 
       // one ring stage = two K16 blocks: wait for the weights, issue two MMAs, release the stage
       auto issue_stage = [&](auto acc_first, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lbo, uint32_t piece16, uint32_t idesc) {
@@ -364,30 +368,64 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
         phase ^= (stage == 0);
       };
 
-      for (int u = cluster_id; u < n_units; u += n_clusters) {
+      // view layer (N = 128): one stage = four K16 blocks; a_lo2 is the operand block of MMAs 2 and 3
+      auto issue_stage4 = [&](auto acc_first, uint32_t d_tmem, uint32_t a_lo, uint32_t a_lo2, uint32_t idesc) {
+        constexpr uint32_t B_LBO = ((128u * 8u) >> 4) << 16, PIECE16 = 128;
+        mbar_wait_lean(full_addr + stage * 8u, phase);
+        tc_fence_after();
+        const uint32_t b_lo = B_LBO | ((ring_addr + stage * STAGE_BYTES) >> 4);
+        if (elect_one()) {
+          const uint64_t a0 = (static_cast<uint64_t>(DESC_HI) << 32) | a_lo;
+          const uint64_t a2 = (static_cast<uint64_t>(DESC_HI) << 32) | a_lo2;
+          const uint64_t b0 = (static_cast<uint64_t>(DESC_HI) << 32) | b_lo;
+          tc_mma_f16_cg2_imm<decltype(acc_first)::value>(d_tmem, a0, b0, idesc);
+          tc_mma_f16_cg2_imm<true>(d_tmem, a0 + A_STEP, b0 + PIECE16, idesc);
+          tc_mma_f16_cg2_imm<true>(d_tmem, a2, b0 + 2 * PIECE16, idesc);
+          tc_mma_f16_cg2_imm<true>(d_tmem, a2 + A_STEP, b0 + 3 * PIECE16, idesc);
+          tc_commit_cg2_addr(empty_addr + stage * 8u, 3);
+        }
+        stage = (stage + 1) & (NSTAGE - 1);
+        phase ^= (stage == 0);
+      };
+
 #pragma unroll 1
-        for (int s = 0; s < NSTEPS; ++s) {
+      for (int i = 0; i < n_ticks; ++i) {
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+          const int j = i - slot * STAGGER;
+          if (j < 0 || j >= my_units * NSTEPS) continue;
+          const int s = j % NSTEPS;
+          const bool first = j < NSTEPS;
           const int n1 = step_nk1(s) / 2, n2 = step_nk(s) / 2;
           const uint32_t n = static_cast<uint32_t>(step_n(s));
           const uint32_t piece16 = n;                        // (n * 16 bytes) >> 4
           const uint32_t idesc = umma_idesc_f16(FP16 ? 0u : 1u, 256, n);
           const uint32_t b_lbo = ((n * 8u) >> 4) << 16;      // LBO = bytes between the two K chunks of a piece
           const uint32_t kb1 = step_kb1(s), kb2 = step_kb2(s);
-#pragma unroll
-          for (int slot = 0; slot < 2; ++slot) {
-            [[maybe_unused]] const int tl_idx = ((u - cluster_id) / n_clusters * NSTEPS + s) * 2 + slot;
-            if (lane == 0) TL_STAMP(0, tl_idx, 0);
-            if (s == 0) {
-              mbar_wait_lean(enc_ready_addr + slot * 8u, ce[slot]++ & 1u);
-              if (!first) mbar_wait_lean(a_ready_addr + slot * 8u, ca[slot]++ & 1u);
-            } else {
-              mbar_wait_lean(a_ready_addr + slot * 8u, ca[slot]++ & 1u);
+          [[maybe_unused]] const int tl_idx = j * 2 + slot;
+          if (lane == 0) TL_STAMP(0, tl_idx, 0);
+          if (s == 0) {
+            mbar_wait_lean(enc_ready_addr + slot * 8u, ce[slot]++ & 1u);
+            if (!first) mbar_wait_lean(a_ready_addr + slot * 8u, ca[slot]++ & 1u);
+          } else {
+            mbar_wait_lean(a_ready_addr + slot * 8u, ca[slot]++ & 1u);
+          }
+          if (s == NSTEPS - 1) mbar_wait_lean(view_ready_addr + slot * 8u, cv[slot]++ & 1u);
+          if (lane == 0) TL_STAMP(0, tl_idx, 1);
+          const uint32_t d_tmem = tmem_base + slot * 256u;
+          const uint32_t a_base = A_LBO | ((act_addr + slot * TILE_ACT_BYTES) >> 4);
+          uint32_t a_lo = a_base + kb1 * A_STEP;
+          if (s == NSTEPS - 1) {
+            // [feature 0..15 | gamma(viewdir) 20,21 | the same two blocks again under zero weights]
+            issue_stage4(std::false_type{}, d_tmem, a_lo, a_lo + 2 * A_STEP, idesc);
+#pragma unroll 1
+            for (int k4 = 1; k4 < 4; ++k4) {
+              a_lo += 4 * A_STEP;
+              issue_stage4(std::true_type{}, d_tmem, a_lo, a_lo + 2 * A_STEP, idesc);
             }
-            if (s == NSTEPS - 1) mbar_wait_lean(view_ready_addr + slot * 8u, cv[slot]++ & 1u);
-            if (lane == 0) TL_STAMP(0, tl_idx, 1);
-            const uint32_t d_tmem = tmem_base + slot * 256u;
-            const uint32_t a_base = A_LBO | ((act_addr + slot * TILE_ACT_BYTES) >> 4);
-            uint32_t a_lo = a_base + kb1 * A_STEP;
+            a_lo = a_base + VIEW_KB * A_STEP;
+            issue_stage4(std::true_type{}, d_tmem, a_lo, a_lo, idesc);
+          } else {
             issue_stage(std::false_type{}, d_tmem, a_lo, b_lbo, piece16, idesc);
             for (int k2 = 1; k2 < n1; ++k2) {
               a_lo += 2 * A_STEP;
@@ -398,19 +436,18 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
               issue_stage(std::true_type{}, d_tmem, a_lo, b_lbo, piece16, idesc);
               a_lo += 2 * A_STEP;
             }
-            if (elect_one()) {
-              tc_commit_cg2_addr(acc_full_addr + slot * 8u, 3);
-              if (s == 5) tc_commit_cg2_addr(pts_free_addr + slot * 8u, 3);
-              if (s == NSTEPS - 1) tc_commit_cg2_addr(view_free_addr + slot * 8u, 3);
-            }
-            if (lane == 0) TL_STAMP(0, tl_idx, 2);
           }
+          if (elect_one()) {
+            tc_commit_cg2_addr(acc_full_addr + slot * 8u, 3);
+            if (s == 5) tc_commit_cg2_addr(pts_free_addr + slot * 8u, 3);
+            if (s == NSTEPS - 1) tc_commit_cg2_addr(view_free_addr + slot * 8u, 3);
+          }
+          if (lane == 0) TL_STAMP(0, tl_idx, 2);
         }
-        first = false;
       }
     }
   } else if (warp >= PRO_WARP0) {
-    // ===================================================================== encoders (one tile ahead)
+    // ===================================================================== encoders (one tile ahead of the tensor core)
     const int row = (warp - PRO_WARP0) * 32 + lane;
     const int row_off = (row >> 3) * 128 + (row & 7) * 16;
     const uint32_t pts_free_addr = tail_addr + offsetof(Tail, pts_free);
@@ -444,10 +481,8 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(enc_bar + slot * 8u);
-      }
-#pragma unroll
-      for (int slot = 0; slot < 2; ++slot) {
-        const int grow = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + row;
+        // view encoding of the same tile (its region is released by the previous tile's last step; with the slots
+        // staggered the four waits of a unit complete in exactly this order)
         float v[3] = {0.f, 0.f, 0.f};
         if (grow < p.n_rows) {
           const int ray = grow / p.S;
@@ -477,12 +512,16 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
     uint32_t cf[2] = {0, 0};
     float alpha_keep[2] = {0.f, 0.f}, eabs_keep[2] = {0.f, 0.f};
 
-    for (int u = cluster_id; u < n_units; u += n_clusters) {
 #pragma unroll 1
-      for (int s = 0; s < NSTEPS; ++s) {
+    for (int i = 0; i < n_ticks; ++i) {
+      {
 #pragma unroll
         for (int slot = 0; slot < 2; ++slot) {
-          [[maybe_unused]] const int tl_idx = ((u - cluster_id) / n_clusters * NSTEPS + s) * 2 + slot;
+          const int j = i - slot * STAGGER;
+          if (j < 0 || j >= my_units * NSTEPS) continue;
+          const int s = j % NSTEPS;
+          const int u = cluster_id + (j / NSTEPS) * n_clusters;
+          [[maybe_unused]] const int tl_idx = j * 2 + slot;
           if (lane == 0 && q == 0) TL_STAMP(1 + hf, tl_idx, 0);
           mbar_wait_lean(acc_full_addr + slot * 8u, cf[slot]++ & 1u);
           tc_fence_after();
@@ -509,42 +548,47 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
             uint8_t* dst = a_tile + hf * 16 * KC_STRIDE + row_off;
             float hs = 0.f, ha = 0.f;
             epilogue_store<2, FP16>(tacc + hf * 128, saux + AUX_BF + hf * 128, nullptr, dst, hs, ha);
-          } else if (hf == 0) {
-            // view layer (128 columns) + rgb head; sigma = alpha head of layer 7 (both column halves)
+          } else {
+            // view layer (128 columns, 64 per column half) + rgb head; sigma = alpha head of layer 7
             float r = 0.f, g = 0.f, b = 0.f;
             uint32_t va[32], vb[32];
-            tmem_ld_32x32b_x32(tacc, va);
+            tmem_ld_32x32b_x32(tacc + hf * 64, va);
             tmem_ld_wait();
-            tmem_ld_32x32b_x32(tacc + 32, vb);
-            epi_rgb32(va, saux + AUX_BV, saux + AUX_WR, r, g, b);
+            tmem_ld_32x32b_x32(tacc + hf * 64 + 32, vb);
+            epi_rgb32(va, saux + AUX_BV + hf * 64, saux + AUX_WR + hf * 64, r, g, b);
             tmem_ld_wait();
-            tmem_ld_32x32b_x32(tacc + 64, va);
-            epi_rgb32(vb, saux + AUX_BV + 32, saux + AUX_WR + 32, r, g, b);
-            tmem_ld_wait();
-            tmem_ld_32x32b_x32(tacc + 96, vb);
-            epi_rgb32(va, saux + AUX_BV + 64, saux + AUX_WR + 64, r, g, b);
-            tmem_ld_wait();
-            epi_rgb32(vb, saux + AUX_BV + 96, saux + AUX_WR + 96, r, g, b);
-            const int grow = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + row;
-            const bool valid = grow < p.n_rows;
-            float sigma = alpha_keep[slot] + tail->alpha_part[slot][row] + saux[AUX_BA];
-            if (valid) {
-              // The hardware ReLU (cvt.relu / fmaxf) maps NaN to 0, torch.relu keeps it: a sample whose position or
-              // view direction is not finite (a ray that missed the sphere has a NaN depth) yields NaN like the reference.
-              if (!input_is_finite(p, grow)) r = g = b = sigma = __int_as_float(0x7fc00000);
-              reinterpret_cast<float4*>(p.out)[grow] =
-                  make_float4(r + saux[AUX_BR], g + saux[AUX_BR + 1], b + saux[AUX_BR + 2], sigma);
+            epi_rgb32(vb, saux + AUX_BV + hf * 64 + 32, saux + AUX_WR + hf * 64 + 32, r, g, b);
+            if (hf == 1) {
+              tail->rgb_part[slot][0][row] = r;
+              tail->rgb_part[slot][1][row] = g;
+              tail->rgb_part[slot][2][row] = b;
             }
-            if (p.guard_count != nullptr) {
-              const float eabs = eabs_keep[slot] + tail->eabs_part[slot][row] + fabsf(saux[AUX_BA]);
-              const bool flag = valid && (grow % p.S) == p.S - 1 && !(fabsf(sigma) >= p.guard_kappa * eabs);
-              const uint32_t m = __ballot_sync(0xffffffffu, flag);
-              if (m != 0) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(p.guard_count, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int idx = base + __popc(m & ((1u << lane) - 1u));
-                if (flag && idx < p.guard_cap) p.guard_list[idx] = grow;
+            named_bar_sync(2 + q, 64);   // the two warps of this lane quarter
+            if (hf == 0) {
+              r += tail->rgb_part[slot][0][row];
+              g += tail->rgb_part[slot][1][row];
+              b += tail->rgb_part[slot][2][row];
+              const int grow = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + row;
+              const bool valid = grow < p.n_rows;
+              float sigma = alpha_keep[slot] + tail->alpha_part[slot][row] + saux[AUX_BA];
+              if (valid) {
+                // The hardware ReLU (cvt.relu / fmaxf) maps NaN to 0, torch.relu keeps it: a sample whose position or
+                // view direction is not finite (a ray that missed the sphere has a NaN depth) yields NaN like the reference.
+                if (!input_is_finite(p, grow)) r = g = b = sigma = __int_as_float(0x7fc00000);
+                reinterpret_cast<float4*>(p.out)[grow] =
+                    make_float4(r + saux[AUX_BR], g + saux[AUX_BR + 1], b + saux[AUX_BR + 2], sigma);
+              }
+              if (p.guard_count != nullptr) {
+                const float eabs = eabs_keep[slot] + tail->eabs_part[slot][row] + fabsf(saux[AUX_BA]);
+                const bool flag = valid && (grow % p.S) == p.S - 1 && !(fabsf(sigma) >= p.guard_kappa * eabs);
+                const uint32_t m = __ballot_sync(0xffffffffu, flag);
+                if (m != 0) {
+                  int base = 0;
+                  if (lane == 0) base = atomicAdd(p.guard_count, __popc(m));
+                  base = __shfl_sync(0xffffffffu, base, 0);
+                  const int idx = base + __popc(m & ((1u << lane) - 1u));
+                  if (flag && idx < p.guard_cap) p.guard_list[idx] = grow;
+                }
               }
             }
           }
