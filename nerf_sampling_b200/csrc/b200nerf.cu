@@ -390,11 +390,14 @@ extern "C" int b200nerf_points(const float* rays_o, const float* rays_d, const f
 }
 
 // ------------------------------------------------------------------------------------------- compositing
-// raw2outputs (trainers/sampling_trainer.py:153-230).  LPR lanes cooperate on one ray: each lane owns one
-// sample per pass (float4 load of raw, coalesced), the exclusive transmittance product is a segmented warp
-// scan (double precision, like the CPU reference's cumprod), the three maps are reduced in registers.
-template <int LPR>
-__global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ raw, const float* __restrict__ z,
+// raw2outputs (trainers/sampling_trainer.py:153-230).  LPR lanes cooperate on one ray and every lane owns FOUR
+// consecutive samples per pass (four float4 loads of raw, one float4 of z, one float4 store of the weights, all
+// coalesced).  The exclusive transmittance product is a local 4-term product followed by a segmented warp scan over
+// the LPR lanes, carried in double and rounded per element exactly like the CPU reference's cumprod; the three maps
+// are reduced in registers.  One scan step serves four samples, which keeps the kernel bandwidth-bound.
+// FULL: S == 4 * LPR (one pass, every lane in range, rows 16-byte aligned) -- no bounds checks in the hot loop.
+template <int LPR, bool FULL>
+__global__ void __launch_bounds__(256, 4) composite_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                                                         const float* __restrict__ rays_d, const float* __restrict__ noise,
                                                         int n_rays, int S, int white, float* __restrict__ o_rgb,
                                                         float* __restrict__ o_disp, float* __restrict__ o_acc,
@@ -406,26 +409,55 @@ __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict_
   const bool live = ray < n_rays;
   if (!live) ray = n_rays - 1;
   const size_t base = static_cast<size_t>(ray) * S;
-  const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+  const float dx = __ldg(rays_d + ray * 3), dy = __ldg(rays_d + ray * 3 + 1), dz = __ldg(rays_d + ray * 3 + 2);
   const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const bool vec = FULL || (S & 3) == 0;   // rows of z / weights are 16-byte aligned
 
   double carry = 1.0;
   float s_r = 0.f, s_g = 0.f, s_b = 0.f, s_d = 0.f, s_a = 0.f;
-  for (int s0 = 0; s0 < S; s0 += LPR) {
-    const int s = s0 + lig;
-    const bool on = s < S;
-    float alpha = 0.f, zz = 0.f;
-    float4 rw = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (on) {
-      rw = __ldg(reinterpret_cast<const float4*>(raw) + base + s);
-      zz = __ldg(z + base + s);
-      const float dist = __fmul_rn(s + 1 < S ? __fadd_rn(__ldg(z + base + s + 1), -zz) : 1e10f, nrm);
-      float sg = rw.w;
-      if (noise) sg = __fadd_rn(sg, __ldg(noise + base + s));
-      alpha = __fadd_rn(1.0f, -expf(__fmul_rn(-fmaxf(sg, 0.f), dist)));
+  for (int s0 = 0; s0 < S; s0 += 4 * LPR) {
+    const int sb = s0 + lig * 4;
+    float zz[5];
+    float4 rw[4];
+    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec && (FULL || sb < S)) {
+      const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + base + sb));
+      zz[0] = z4.x; zz[1] = z4.y; zz[2] = z4.z; zz[3] = z4.w;
+      if (FULL) zz[4] = __shfl_down_sync(0xffffffffu, z4.x, 1, LPR);   // the next lane's first depth (unused on the last lane)
+      else zz[4] = sb + 4 < S ? __ldg(z + base + sb + 4) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rw[i] = __ldg(reinterpret_cast<const float4*>(raw) + base + sb + i);
+      if (noise) {
+        const float4 n4 = __ldg(reinterpret_cast<const float4*>(noise + base + sb));
+        nz[0] = n4.x; nz[1] = n4.y; nz[2] = n4.z; nz[3] = n4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) zz[i] = sb + i < S ? __ldg(z + base + sb + i) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rw[i] = sb + i < S ? __ldg(reinterpret_cast<const float4*>(raw) + base + sb + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (noise && sb + i < S) nz[i] = __ldg(noise + base + sb + i);
+      }
     }
-    const float f = on ? __fadd_rn(__fadd_rn(1.0f, -alpha), 1e-10f) : 1.0f;
-    double incl = static_cast<double>(f);
+    float alpha[4];
+    double ex[4];          // exclusive product inside this lane's four samples
+    double run = 1.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int sidx = sb + i;
+      ex[i] = run;
+      if (FULL || sidx < S) {
+        const bool last = FULL ? (i == 3 && lig == LPR - 1) : !(sidx + 1 < S);
+        const float dist = __fmul_rn(last ? 1e10f : __fadd_rn(zz[i + 1], -zz[i]), nrm);
+        const float sg = noise ? __fadd_rn(rw[i].w, nz[i]) : rw[i].w;
+        alpha[i] = __fadd_rn(1.0f, -expf(__fmul_rn(-fmaxf(sg, 0.f), dist)));
+        run *= static_cast<double>(__fadd_rn(__fadd_rn(1.0f, -alpha[i]), 1e-10f));
+      } else {
+        alpha[i] = 0.f;
+      }
+    }
+    double incl = run;
 #pragma unroll
     for (int off = 1; off < LPR; off <<= 1) {
       const double t = __shfl_up_sync(0xffffffffu, incl, off, LPR);
@@ -433,17 +465,35 @@ __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict_
     }
     double excl = __shfl_up_sync(0xffffffffu, incl, 1, LPR);
     if (lig == 0) excl = 1.0;
-    const float T = static_cast<float>(carry * excl);
+    excl *= carry;
     carry *= __shfl_sync(0xffffffffu, incl, LPR - 1, LPR);
-    if (on) {
-      const float w = __fmul_rn(alpha, T);
-      s_r = fmaf(w, 1.0f / (1.0f + expf(-rw.x)), s_r);
-      s_g = fmaf(w, 1.0f / (1.0f + expf(-rw.y)), s_g);
-      s_b = fmaf(w, 1.0f / (1.0f + expf(-rw.z)), s_b);
-      s_d = fmaf(w, zz, s_d);
-      s_a += w;
-      if (live && o_w) o_w[base + s] = w;
-      if (live && o_alpha) o_alpha[base + s] = alpha;
+    float w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float T = static_cast<float>(excl * ex[i]);
+      w[i] = (FULL || sb + i < S) ? __fmul_rn(alpha[i], T) : 0.f;
+      if (FULL || sb + i < S) {
+        // colours: fast exp / reciprocal (<= 3e-7 on a sigmoid); the alpha path above keeps the accurate expf because
+        // the weights also feed arg-max and inverse-CDF indices
+        s_r = fmaf(w[i], __fdividef(1.0f, 1.0f + __expf(-rw[i].x)), s_r);
+        s_g = fmaf(w[i], __fdividef(1.0f, 1.0f + __expf(-rw[i].y)), s_g);
+        s_b = fmaf(w[i], __fdividef(1.0f, 1.0f + __expf(-rw[i].z)), s_b);
+        s_d = fmaf(w[i], zz[i], s_d);
+        s_a += w[i];
+      }
+    }
+    if (live && (FULL || sb < S)) {
+      if (vec) {
+        if (o_w) *reinterpret_cast<float4*>(o_w + base + sb) = make_float4(w[0], w[1], w[2], w[3]);
+        if (o_alpha) *reinterpret_cast<float4*>(o_alpha + base + sb) = make_float4(alpha[0], alpha[1], alpha[2], alpha[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (sb + i < S) {
+            if (o_w) o_w[base + sb + i] = w[i];
+            if (o_alpha) o_alpha[base + sb + i] = alpha[i];
+          }
+      }
     }
   }
 #pragma unroll
@@ -494,8 +544,9 @@ static void launch_composite(const float* raw, const float* z, const float* rays
                              int white, float* o_rgb, float* o_disp, float* o_acc, float* o_depth, float* o_w,
                              float* o_alpha, cudaStream_t st) {
   const long long threads = static_cast<long long>(n_rays) * LPR;
-  composite_kernel<LPR><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(raw, z, rays_d, noise, n_rays, S, white, o_rgb, o_disp,
-                                                                                   o_acc, o_depth, o_w, o_alpha);
+  const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
+  if (S == 4 * LPR) composite_kernel<LPR, true><<<grid, 256, 0, st>>>(raw, z, rays_d, noise, n_rays, S, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha);
+  else composite_kernel<LPR, false><<<grid, 256, 0, st>>>(raw, z, rays_d, noise, n_rays, S, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha);
 }
 
 extern "C" int b200nerf_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays,
@@ -510,10 +561,12 @@ extern "C" int b200nerf_composite_fwd(const float* raw, const float* z, const fl
     LAUNCH_CHECK();
     return 0;
   }
-  if (S <= 2) launch_composite<2>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-  else if (S <= 4) launch_composite<4>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-  else if (S <= 8) launch_composite<8>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-  else if (S <= 16) launch_composite<16>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  // lanes per ray: four samples per lane and pass
+  if (S <= 4) launch_composite<1>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  else if (S <= 8) launch_composite<2>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  else if (S <= 16) launch_composite<4>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  else if (S <= 32) launch_composite<8>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  else if (S <= 64) launch_composite<16>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
   else launch_composite<32>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
   LAUNCH_CHECK();
   return 0;
