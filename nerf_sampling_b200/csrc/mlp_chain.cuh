@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const __gri
   uint8_t* wst = smem + ACT_BYTES;
   ChainSmemTail* tail = reinterpret_cast<ChainSmemTail*>(smem + ACT_BYTES + NUM_STAGES * W_STAGE_BYTES);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   int n_rows = p.n_rows;
   if (p.n_rows_dev != nullptr) n_rows = min(__ldg(p.n_rows_dev), p.n_rows);
@@ -185,48 +185,51 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
+  const uint32_t full_addr = smem_u32(&tail->full[0]), empty_addr = smem_u32(&tail->empty[0]);
   if (warp == 0) {
-    // ===================================================================== weight producer (TMA)
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const uint8_t* src = p.wpack;
-        for (int s = 0; s < p.n_steps; ++s) {
-          const uint32_t bytes = p.steps[s].n * (SPLIT ? 64u : 32u);
-          for (int k = 0; k < p.steps[s].n_k16; ++k, ++it) {
-            const uint32_t stage = it % NUM_STAGES;
-            const uint32_t ph = (it / NUM_STAGES) & 1u;
-            mbar_wait(&tail->empty[stage], ph ^ 1u);
+    // ===================================================================== weight producer (TMA; whole warp, one lane issues)
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint8_t* src = p.wpack;
+      for (int s = 0; s < p.n_steps; ++s) {
+        const uint32_t bytes = p.steps[s].n * (SPLIT ? 64u : 32u);
+        const int nk = p.steps[s].n_k16;
+        for (int k = 0; k < nk; ++k) {
+          mbar_wait_lean(empty_addr + stage * 8u, phase ^ 1u);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&tail->full[stage], bytes);
             tma_load_1d(wst + stage * W_STAGE_BYTES, src, bytes, &tail->full[stage]);
-            src += bytes;
+          }
+          __syncwarp();
+          src += bytes;
+          if (++stage == NUM_STAGES) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      uint32_t it = 0, a_cnt = 0;
-      const uint32_t act_addr = smem_u32(act);
-      const uint32_t wst_addr = smem_u32(wst);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int s = 0; s < p.n_steps; ++s) {
-          const Step st = p.steps[s];
-          if (st.wait_a) {
-            mbar_wait(&tail->a_ready, a_cnt & 1u);
-            ++a_cnt;
-            tc_fence_after();
-          }
-          const uint32_t idesc = umma_idesc_bf16(TILE_M, st.n);
-          const uint32_t d_tmem = tmem_base + st.acc_col;
-          const uint32_t b_lbo = st.n * 16u;  // bytes between the two K core-matrix columns of a slab
-          for (int k = 0; k < st.n_k16; ++k, ++it) {
-            const uint32_t stage = it % NUM_STAGES;
-            const uint32_t ph = (it / NUM_STAGES) & 1u;
-            mbar_wait(&tail->full[stage], ph);
-            tc_fence_after();
-            const uint32_t a_addr = act_addr + (st.a_k16_begin + k) * 2u * ACT_KC_STRIDE;
+    // ===================================================================== MMA issuer (whole warp, one lane issues)
+    uint32_t stage = 0, phase = 0, a_cnt = 0;
+    const uint32_t act_addr = smem_u32(act);
+    const uint32_t wst_addr = smem_u32(wst);
+    const uint32_t a_ready_addr = smem_u32(&tail->a_ready);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int s = 0; s < p.n_steps; ++s) {
+        const Step st = p.steps[s];
+        if (st.wait_a) {
+          mbar_wait_lean(a_ready_addr, a_cnt & 1u);
+          ++a_cnt;
+        }
+        const uint32_t idesc = umma_idesc_bf16(TILE_M, st.n);
+        const uint32_t d_tmem = tmem_base + st.acc_col;
+        const uint32_t b_lbo = st.n * 16u;  // bytes between the two K core-matrix columns of a slab
+        uint32_t a_addr = act_addr + st.a_k16_begin * 2u * ACT_KC_STRIDE;
+        for (int k = 0; k < st.n_k16; ++k) {
+          mbar_wait_lean(full_addr + stage * 8u, phase);
+          tc_fence_after();
+          if (elect_one()) {
             const uint32_t b_addr = wst_addr + stage * W_STAGE_BYTES;
             const uint64_t a_hi = umma_desc_kmajor(a_addr, ACT_KC_STRIDE, 128);
             const uint64_t b_hi = umma_desc_kmajor(b_addr, b_lbo, 128);
@@ -239,7 +242,16 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const __gri
             }
             tc_commit(&tail->empty[stage]);  // slab consumed once these MMAs retire
           }
-          if (st.epi != EPI_NONE) tc_commit(&tail->acc_full);
+          __syncwarp();
+          a_addr += 2u * ACT_KC_STRIDE;
+          if (++stage == NUM_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (st.epi != EPI_NONE) {
+          if (elect_one()) tc_commit(&tail->acc_full);
+          __syncwarp();
         }
       }
     }
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) mlp_chain_kernel(const __gri
       for (int s = 0; s < p.n_steps; ++s) {
         const Step st = p.steps[s];
         if (st.epi == EPI_NONE) continue;
-        mbar_wait(&tail->acc_full, acc_cnt & 1u);
+        mbar_wait_lean(smem_u32(&tail->acc_full), acc_cnt & 1u);
         ++acc_cnt;
         tc_fence_after();
 
