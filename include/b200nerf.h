@@ -188,6 +188,37 @@ int b200nerf_sample_pdf_merge(const float* z_coarse, const float* weights, const
 int b200nerf_argmax_gather(const float* weights, const float* z, const float* raw, int n_rays, int S, long long* out_idx,
                            float* out_z, float* out_w, float* out_rgb, void* stream);
 
+/* ---- training (config #5: Trainer.core_optimization_loop, trainers/Trainer.py:506-544) --------------------------- */
+
+/* DepthNet in its literal per-layer form with saved activations (depth_nets/depth_net.py:117-169), fp32.
+ * `params` = device pointers of the state_dict tensors in order: origin_layers.{i}.{weight,bias} (n_branch layers of
+ * widths hidden[]), direction_layers..., intersection_layers..., cat_layers.{2j}.{weight,bias} (n_cat layers of widths
+ * cat_hidden[]), to_depth.0.{weight,bias}: b200nerf_depthnet_n_params() pointers.  `ws` holds
+ * b200nerf_depthnet_train_ws_floats() floats and carries the activations from fwd to bwd.  out_z [n_rays]. */
+size_t b200nerf_depthnet_train_ws_floats(int n_rays, int n_branch, const int* hidden, int n_cat, const int* cat_hidden);
+int b200nerf_depthnet_n_params(int n_branch, int n_cat);
+int b200nerf_depthnet_train_fwd(const float* const* params, int n_branch, const int* hidden, int n_cat, const int* cat_hidden,
+                                const float* rays_o, const float* rays_d, int n_rays, float radius, float near_, float far_,
+                                float* ws, float* out_z, void* stream);
+/* Backward of the above: dz [n_rays] -> gradients of every parameter, written (not accumulated) to `grads` (same order
+ * and shapes as `params`).  Consumes the activations in `ws`. */
+int b200nerf_depthnet_train_bwd(const float* const* params, int n_branch, const int* hidden, int n_cat, const int* cat_hidden,
+                                int n_rays, float near_, float far_, float* ws, const float* dz, float* const* grads,
+                                void* stream);
+
+/* The frozen NeRF at ONE sample per ray, p = o + d z (nerf_utils.py:693-715), in fp32, together with d raw / d z
+ * (forward-mode derivative along the ray: what loss.backward() propagates from the colour into DepthNet's depth).
+ * `params` = the 24 fp32 device tensors in the order of b200nerf_nerf_pack; ws: b200nerf_nerf_point_ws_floats() floats;
+ * out_raw [n_rays,4], out_draw_dz [n_rays,4]. */
+size_t b200nerf_nerf_point_ws_floats(int n_rays);
+int b200nerf_nerf_point_jvp(const float* const* params, const float* rays_o, const float* rays_d, const float* viewdirs,
+                            const float* z, int n_rays, float* ws, float* out_raw, float* out_draw_dz, void* stream);
+
+/* torch.optim.Adam (no weight decay, no amsgrad) on one tensor; the gradient is multiplied by grad_scale first
+ * (1/world_size after a sum all-reduce).  step counts from 1. */
+int b200nerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                       float beta2, float eps, int step, float grad_scale, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------ */
 
 /* D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs (raw uint16), through the same shared-memory operand layout,

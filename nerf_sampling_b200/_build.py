@@ -9,7 +9,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("B200NERF_LIB") or os.path.join(PKG_DIR, "libb200nerf.so")
-SOURCES = ["b200nerf.cu", "sampling.cu"]
+SOURCES = ["b200nerf.cu", "sampling.cu", "train.cu"]
 HEADERS = ["ptx.cuh", "mlp_chain.cuh", "mlp_fast.cuh", "host_common.h", os.path.join("..", "..", "include", "b200nerf.h")]
 
 NVCC_FLAGS = [

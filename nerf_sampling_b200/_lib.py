@@ -49,6 +49,13 @@ SIGNATURES = {
     "b200nerf_sample_pdf_merge": (I, [P, P, P, I, I, I, I, P, P, P, P]),
     "b200nerf_argmax_gather": (I, [P, P, P, I, I, P, P, P, P, P]),
     "b200nerf_umma_selftest": (I, [P, P, P, I, I, P]),
+    "b200nerf_depthnet_train_ws_floats": (SZ, [I, I, P, I, P]),
+    "b200nerf_depthnet_n_params": (I, [I, I]),
+    "b200nerf_depthnet_train_fwd": (I, [P, I, P, I, P, P, P, I, F, F, F, P, P, P]),
+    "b200nerf_depthnet_train_bwd": (I, [P, I, P, I, P, I, F, F, P, P, P, P]),
+    "b200nerf_nerf_point_ws_floats": (SZ, [I]),
+    "b200nerf_nerf_point_jvp": (I, [P, P, P, P, P, I, P, P, P, P]),
+    "b200nerf_adam_step": (I, [P, P, P, P, SZ, F, F, F, F, I, F, P]),
 }
 
 

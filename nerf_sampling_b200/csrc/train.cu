@@ -1,0 +1,522 @@
+// Differentiable slice of the training render (config #5: Trainer.core_optimization_loop, trainers/Trainer.py:506-544
+// over nerf_utils.render_rays, nerf_pytorch/nerf_utils.py:614-733), in fp32:
+//
+//   * DepthNet in its literal per-layer form (depth_nets/depth_net.py:117-169) with saved activations, and its
+//     backward (input gradient chain + all 82 weight/bias gradients);
+//   * the frozen fine NeRF evaluated at ONE sample per ray together with its directional derivative d raw / d z
+//     (forward-mode: z is a scalar per ray, so a tangent row next to every primal row replaces a backward pass);
+//   * Adam on a list of tensors.
+//
+// The frozen hierarchical target (257 network evaluations per ray) stays on the tensor-core kernels; this part is
+// 512 rays per GPU and two evaluations per ray, i.e. latency- not throughput-bound, and fp32 CUDA-core GEMMs keep the
+// gradients at the reference's own precision.  Host loops over layers live here, behind one C call per pass.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/b200nerf.h"
+#include "host_common.h"
+
+// ------------------------------------------------------------------------------------------- strided SGEMM
+// C[M,N] (row-major, ldc) = (beta ? C : 0) + sum_k A(m,k) * B(k,n) [+ bias[n]] [then LeakyReLU(slope) if act]
+// A(m,k) = A[m*sAm + k*sAk], B(k,n) = B[k*sBk + n*sBn]: covers X*W^T (forward), dY*W (input gradient) and dY^T*X
+// (weight gradient) without transposes.  64x64x16 tiles, 256 threads, 4x4 outputs per thread.
+constexpr int GM = 64, GN = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long sAm, long sAk,
+                                                    const float* __restrict__ B, long sBk, long sBn, float* __restrict__ C,
+                                                    int ldc, int beta, const float* __restrict__ bias, int act, float slope) {
+  __shared__ float As[GK][GM + 4];
+  __shared__ float Bs[GK][GN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // element (r, c) of a 64 x 16 tile per thread and pass: walk the contiguous dimension with consecutive threads
+  const bool a_kfast = sAk == 1, b_nfast = sBn == 1;
+  for (int k0 = 0; k0 < K; k0 += GK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      int m, k;
+      if (a_kfast) { m = idx >> 4; k = idx & 15; } else { m = idx & 63; k = idx >> 6; }
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < M && gk < K) ? __ldg(A + gm * sAm + gk * sAk) : 0.f;
+      int n, kb;
+      if (b_nfast) { n = idx & 63; kb = idx >> 6; } else { n = idx >> 4; kb = idx & 15; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      Bs[kb][n] = (gn < N && gkb < K) ? __ldg(B + gkb * sBk + gn * sBn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      float* c = C + static_cast<size_t>(gm) * ldc + gn;
+      if (beta) v += *c;
+      if (bias) v += __ldg(bias + gn);
+      if (act) v = v > 0.f ? v : v * slope;
+      *c = v;
+    }
+  }
+}
+
+static int sgemm(cudaStream_t st, int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBk, long sBn,
+                 float* C, int ldc, int beta, const float* bias = nullptr, int act = 0, float slope = 0.f) {
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
+  sgemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, bias, act, slope);
+  LAUNCH_CHECK();
+  return 0;
+}
+// Y[n, M] (+)= X[n, K] * W[:, off:off+K]^T (+ bias) (+ LeakyReLU)       W is [M, ldw] row-major
+static int lin_fwd(cudaStream_t st, int n, int M, int K, const float* X, int ldx, const float* W, int ldw, int off, float* Y,
+                   int ldy, int beta, const float* bias, int act, float slope) {
+  return sgemm(st, n, M, K, X, ldx, 1, W + off, 1, ldw, Y, ldy, beta, bias, act, slope);
+}
+// dX[n, K] (+)= dY[n, M] * W[:, off:off+K]
+static int lin_dgrad(cudaStream_t st, int n, int M, int K, const float* dY, int ldy, const float* W, int ldw, int off, float* dX,
+                     int ldx, int beta) {
+  return sgemm(st, n, K, M, dY, ldy, 1, W + off, ldw, 1, dX, ldx, beta);
+}
+// dW[:, off:off+K] = dY[n, M]^T * X[n, K]
+static int lin_wgrad(cudaStream_t st, int n, int M, int K, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw,
+                     int off) {
+  return sgemm(st, M, K, n, dY, 1, ldy, X, ldx, 1, dW + off, ldw, 0);
+}
+
+// db[m] = sum_n dY[n, m]
+__global__ void colsum_kernel(const float* __restrict__ dY, int n, int M, int ldy, float* __restrict__ db) {
+  const int m = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int part = threadIdx.x >> 5;  // 8 row groups
+  __shared__ float red[8][33];
+  float s = 0.f;
+  if (m < M)
+    for (int r = part; r < n; r += 8) s += dY[static_cast<size_t>(r) * ldy + m];
+  red[part][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (part == 0 && m < M) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    db[m] = t;
+  }
+}
+static int colsum(cudaStream_t st, const float* dY, int n, int M, int ldy, float* db) {
+  colsum_kernel<<<(M + 31) / 32, 256, 0, st>>>(dY, n, M, ldy, db);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- encodings
+// gamma(x) of a C-vector: [x, sin(2^0 x), cos(2^0 x), ...] (run_nerf_helpers.py:15-63), C*(1+2F) wide
+__device__ __forceinline__ void embed_row(const float* x, int C, int F, float* out) {
+  for (int c = 0; c < C; ++c) out[c] = x[c];
+  for (int j = 0; j < F; ++j) {
+    const float f = static_cast<float>(1 << j);
+    for (int c = 0; c < C; ++c) {
+      float s, co;
+      sincosf(x[c] * f, &s, &co);
+      out[C + j * 2 * C + c] = s;
+      out[C + j * 2 * C + C + c] = co;
+    }
+  }
+}
+
+// E[n, 252] = [gamma(o) 63 | gamma(d) 63 | gamma([hit_near, hit_far]) 126]; sphere hits in the reference's op order
+// (nerf_pytorch/utils.py:159-217), NaN when the ray misses
+__global__ void depthnet_encode_kernel(const float* __restrict__ ro, const float* __restrict__ rd, int n, float radius,
+                                       float* __restrict__ E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float o[3], d[3];
+  for (int t = 0; t < 3; ++t) {
+    o[t] = ro[i * 3 + t];
+    d[t] = rd[i * 3 + t];
+  }
+  const float dot_do = __fadd_rn(__fadd_rn(__fmul_rn(d[0], o[0]), __fmul_rn(d[1], o[1])), __fmul_rn(d[2], o[2]));
+  const float b = __fmul_rn(2.f, dot_do);
+  const float on = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(o[0], o[0]), __fmul_rn(o[1], o[1])), __fmul_rn(o[2], o[2])));
+  const float cc = __fadd_rn(__fmul_rn(on, on), -__fmul_rn(radius, radius));
+  const float a = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
+  const float delta = __fadd_rn(__fmul_rn(b, b), -__fmul_rn(__fmul_rn(4.f, a), cc));
+  const float sq = __fsqrt_rn(delta);
+  const float two_a = __fmul_rn(2.f, a);
+  const float t0 = __fdiv_rn(__fadd_rn(-b, -sq), two_a), t1 = __fdiv_rn(__fadd_rn(-b, sq), two_a);
+  float hits[6];
+  for (int t = 0; t < 3; ++t) {
+    hits[t] = __fadd_rn(o[t], __fmul_rn(t0, d[t]));
+    hits[3 + t] = __fadd_rn(o[t], __fmul_rn(t1, d[t]));
+  }
+  float* e = E + static_cast<size_t>(i) * 252;
+  embed_row(o, 3, 10, e);
+  embed_row(d, 3, 10, e + 63);
+  embed_row(hits, 6, 10, e + 126);
+}
+
+// z = near*(1-s) + far*s, s = sigmoid(t)   (depth_net.py:165-168)
+__global__ void depth_head_kernel(const float* __restrict__ t, int n, float near_, float far_, float* __restrict__ s_out,
+                                  float* __restrict__ z) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = 1.0f / (1.0f + expf(-t[i]));
+  s_out[i] = s;
+  z[i] = __fadd_rn(__fmul_rn(near_, __fadd_rn(1.0f, -s)), __fmul_rn(far_, s));
+}
+// dt = dz * (far - near) * s * (1 - s)
+__global__ void depth_head_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ s, int n, float near_, float far_,
+                                      float* __restrict__ dt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dt[i] = dz[i] * (far_ - near_) * s[i] * (1.0f - s[i]);
+}
+// dpre = dpost * (post > 0 ? 1 : slope), in place
+__global__ void leaky_bwd_kernel(float* __restrict__ d, const float* __restrict__ post, size_t total, float slope) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (!(post[i] > 0.f)) d[i] *= slope;
+}
+
+// ------------------------------------------------------------------------------------------- DepthNet, literal form
+struct DnArch {
+  int nb;                 // layers per branch
+  int nc;                 // cat layers
+  std::vector<int> h;     // branch widths [nb]
+  std::vector<int> c;     // cat widths [nc]
+};
+struct DnWs {             // float offsets into the workspace
+  size_t E, s, t, total;
+  std::vector<size_t> xb[3];   // branch outputs
+  std::vector<size_t> a;       // cat layer outputs (post activation)
+  size_t g0, g1, g2;           // gradient scratch, [n, maxw] each
+};
+static DnWs dn_layout(const DnArch& ar, size_t n) {
+  DnWs w;
+  size_t o = 0;
+  auto take = [&](size_t f) { size_t r = o; o += (f + 63) & ~static_cast<size_t>(63); return r; };
+  w.E = take(n * 252);
+  for (int b = 0; b < 3; ++b)
+    for (int i = 0; i < ar.nb; ++i) w.xb[b].push_back(take(n * ar.h[i]));
+  for (int j = 0; j < ar.nc; ++j) w.a.push_back(take(n * ar.c[j]));
+  w.t = take(n);
+  w.s = take(n);
+  int maxw = 1;
+  for (int v : ar.h) maxw = v > maxw ? v : maxw;
+  for (int v : ar.c) maxw = v > maxw ? v : maxw;
+  w.g0 = take(n * maxw);
+  w.g1 = take(n * maxw);
+  w.g2 = take(n * maxw);
+  w.total = o;
+  return w;
+}
+static int dn_arch(int nb, const int* h, int nc, const int* c, DnArch* ar) {
+  if (nb < 1 || nc < 1 || !h || !c) return b200_fail("DepthNet architecture: bad arguments");
+  ar->nb = nb;
+  ar->nc = nc;
+  ar->h.assign(h, h + nb);
+  ar->c.assign(c, c + nc);
+  return 0;
+}
+// parameter order = state_dict order: origin_layers.{i}.{w,b}, direction_layers..., intersection_layers...,
+// cat_layers.{2j}.{w,b}, to_depth.0.{w,b}
+static inline int pidx_branch(const DnArch& ar, int b, int i) { return (b * ar.nb + i) * 2; }
+static inline int pidx_cat(const DnArch& ar, int j) { return (3 * ar.nb + j) * 2; }
+static inline int pidx_head(const DnArch& ar) { return (3 * ar.nb + ar.nc) * 2; }
+
+extern "C" size_t b200nerf_depthnet_train_ws_floats(int n_rays, int n_branch, const int* hidden, int n_cat, const int* cat_hidden) {
+  DnArch ar;
+  if (dn_arch(n_branch, hidden, n_cat, cat_hidden, &ar)) return 0;
+  return dn_layout(ar, static_cast<size_t>(n_rays)).total;
+}
+extern "C" int b200nerf_depthnet_n_params(int n_branch, int n_cat) { return (3 * n_branch + n_cat + 1) * 2; }
+
+extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_branch, const int* hidden, int n_cat,
+                                           const int* cat_hidden, const float* rays_o, const float* rays_d, int n_rays, float radius,
+                                           float near_, float far_, float* ws, float* out_z, void* stream) {
+  if (n_rays <= 0) return 0;
+  if (!params || !rays_o || !rays_d || !ws || !out_z) return b200_fail("b200nerf_depthnet_train_fwd: null argument");
+  DnArch ar;
+  if (dn_arch(n_branch, hidden, n_cat, cat_hidden, &ar)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = n_rays;
+  const DnWs w = dn_layout(ar, n);
+  float* E = ws + w.E;
+  depthnet_encode_kernel<<<(n + 127) / 128, 128, 0, st>>>(rays_o, rays_d, n, radius, E);
+  LAUNCH_CHECK();
+  const int ed[3] = {63, 63, 126}, eo[3] = {0, 63, 126};
+  for (int b = 0; b < 3; ++b) {
+    const float* e = E + eo[b];
+    for (int i = 0; i < ar.nb; ++i) {
+      const float* W = params[pidx_branch(ar, b, i)];
+      const float* bias = params[pidx_branch(ar, b, i) + 1];
+      float* y = ws + w.xb[b][i];
+      const int prev_w = i == 0 ? ed[b] : ar.h[i - 1];
+      const float* prev = i == 0 ? e : ws + w.xb[b][i - 1];
+      const int prev_ld = i == 0 ? 252 : ar.h[i - 1];
+      const int ldw = prev_w + ed[b];
+      // x = Linear(cat([x_prev, e])) -- no activation (depth_net.py:140,148,156 construct a module and drop it)
+      if (lin_fwd(st, n, ar.h[i], prev_w, prev, prev_ld, W, ldw, 0, y, ar.h[i], 0, nullptr, 0, 0.f)) return 1;
+      if (lin_fwd(st, n, ar.h[i], ed[b], e, 252, W, ldw, prev_w, y, ar.h[i], 1, bias, 0, 0.f)) return 1;
+    }
+  }
+  const int hl = ar.h[ar.nb - 1];
+  {
+    // cat_layers.0 over cat([x_o, x_d, x_i, e_o, e_d, e_i])
+    const float* W = params[pidx_cat(ar, 0)];
+    const float* bias = params[pidx_cat(ar, 0) + 1];
+    const int ldw = 3 * hl + 252;
+    float* y = ws + w.a[0];
+    for (int b = 0; b < 3; ++b)
+      if (lin_fwd(st, n, ar.c[0], hl, ws + w.xb[b][ar.nb - 1], hl, W, ldw, b * hl, y, ar.c[0], b > 0, nullptr, 0, 0.f)) return 1;
+    if (lin_fwd(st, n, ar.c[0], 252, E, 252, W, ldw, 3 * hl, y, ar.c[0], 1, bias, 1, 0.01f)) return 1;
+  }
+  for (int j = 1; j < ar.nc; ++j) {
+    if (lin_fwd(st, n, ar.c[j], ar.c[j - 1], ws + w.a[j - 1], ar.c[j - 1], params[pidx_cat(ar, j)], ar.c[j - 1], 0, ws + w.a[j],
+                ar.c[j], 0, params[pidx_cat(ar, j) + 1], 1, 0.01f))
+      return 1;
+  }
+  const int cl = ar.c[ar.nc - 1];
+  if (lin_fwd(st, n, 1, cl, ws + w.a[ar.nc - 1], cl, params[pidx_head(ar)], cl, 0, ws + w.t, 1, 0, params[pidx_head(ar) + 1], 0, 0.f))
+    return 1;
+  depth_head_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws + w.t, n, near_, far_, ws + w.s, out_z);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_branch, const int* hidden, int n_cat,
+                                           const int* cat_hidden, int n_rays, float near_, float far_, float* ws, const float* dz,
+                                           float* const* grads, void* stream) {
+  if (n_rays <= 0) return 0;
+  if (!params || !ws || !dz || !grads) return b200_fail("b200nerf_depthnet_train_bwd: null argument");
+  DnArch ar;
+  if (dn_arch(n_branch, hidden, n_cat, cat_hidden, &ar)) return 1;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = n_rays;
+  const DnWs w = dn_layout(ar, n);
+  const float* E = ws + w.E;
+  float* g = ws + w.g0;
+  float* g2 = ws + w.g1;
+  const int cl = ar.c[ar.nc - 1], hl = ar.h[ar.nb - 1];
+  // head: t = a_last . w + b, s = sigmoid(t), z = near + (far - near) s
+  float* dt = ws + w.t;  // t itself is no longer needed
+  depth_head_bwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(dz, ws + w.s, n, near_, far_, dt);
+  LAUNCH_CHECK();
+  const int ph = pidx_head(ar);
+  if (lin_wgrad(st, n, 1, cl, dt, 1, ws + w.a[ar.nc - 1], cl, grads[ph], cl, 0)) return 1;
+  if (colsum(st, dt, n, 1, 1, grads[ph + 1])) return 1;
+  if (lin_dgrad(st, n, 1, cl, dt, 1, params[ph], cl, 0, g, cl, 0)) return 1;
+  // cat layers, last to first: g holds d(post-activation output of layer j)
+  for (int j = ar.nc - 1; j >= 0; --j) {
+    const size_t tot = static_cast<size_t>(n) * ar.c[j];
+    leaky_bwd_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(g, ws + w.a[j], tot, 0.01f);
+    LAUNCH_CHECK();
+    const int pc = pidx_cat(ar, j);
+    if (colsum(st, g, n, ar.c[j], ar.c[j], grads[pc + 1])) return 1;
+    if (j > 0) {
+      if (lin_wgrad(st, n, ar.c[j], ar.c[j - 1], g, ar.c[j], ws + w.a[j - 1], ar.c[j - 1], grads[pc], ar.c[j - 1], 0)) return 1;
+      if (lin_dgrad(st, n, ar.c[j], ar.c[j - 1], g, ar.c[j], params[pc], ar.c[j - 1], 0, g2, ar.c[j - 1], 0)) return 1;
+      float* tmp = g;
+      g = g2;
+      g2 = tmp;
+    } else {
+      const int ldw = 3 * hl + 252;
+      for (int b = 0; b < 3; ++b)
+        if (lin_wgrad(st, n, ar.c[0], hl, g, ar.c[0], ws + w.xb[b][ar.nb - 1], hl, grads[pc], ldw, b * hl)) return 1;
+      if (lin_wgrad(st, n, ar.c[0], 252, g, ar.c[0], E, 252, grads[pc], ldw, 3 * hl)) return 1;
+    }
+  }
+  // g = d(pre-activation of cat_layers.0) [n, c0]; branches
+  const float* gc0 = g;
+  float* gb = g2;                       // gradient of the current branch layer's output ...
+  float* gb_alt = ws + w.g2;            // ... and of the layer below it
+  const int ed[3] = {63, 63, 126}, eo[3] = {0, 63, 126};
+  const int pc0 = pidx_cat(ar, 0);
+  const int ldw0 = 3 * hl + 252;
+  for (int b = 0; b < 3; ++b) {
+    const float* e = E + eo[b];
+    // d x_b,last = gc0 * W_cat0[:, b*hl : (b+1)*hl]
+    if (lin_dgrad(st, n, ar.c[0], hl, gc0, ar.c[0], params[pc0], ldw0, b * hl, gb, hl, 0)) return 1;
+    float* cur = gb;
+    for (int i = ar.nb - 1; i >= 0; --i) {
+      const int pb = pidx_branch(ar, b, i);
+      const int prev_w = i == 0 ? ed[b] : ar.h[i - 1];
+      const float* prev = i == 0 ? e : ws + w.xb[b][i - 1];
+      const int prev_ld = i == 0 ? 252 : ar.h[i - 1];
+      const int ldw = prev_w + ed[b];
+      if (colsum(st, cur, n, ar.h[i], ar.h[i], grads[pb + 1])) return 1;
+      if (lin_wgrad(st, n, ar.h[i], prev_w, cur, ar.h[i], prev, prev_ld, grads[pb], ldw, 0)) return 1;
+      if (lin_wgrad(st, n, ar.h[i], ed[b], cur, ar.h[i], e, 252, grads[pb], ldw, prev_w)) return 1;
+      if (i > 0) {
+        float* nxt = cur == gb ? gb_alt : gb;
+        if (lin_dgrad(st, n, ar.h[i], ar.h[i - 1], cur, ar.h[i], params[pb], ldw, 0, nxt, ar.h[i - 1], 0)) return 1;
+        cur = nxt;
+      }
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- NeRF at one sample per ray + d/dz
+// rows 0..n-1 = primal gamma(p), rows n..2n-1 = tangent d gamma(p) / dz, p = o + d z; view encoding [n, 27]
+__global__ void nerf_point_encode_kernel(const float* __restrict__ ro, const float* __restrict__ rd, const float* __restrict__ vd,
+                                         const float* __restrict__ z, int n, float* __restrict__ enc, float* __restrict__ venc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x[3], d[3], v[3];
+  for (int t = 0; t < 3; ++t) {
+    d[t] = rd[i * 3 + t];
+    x[t] = __fadd_rn(ro[i * 3 + t], __fmul_rn(d[t], z[i]));
+    v[t] = vd[i * 3 + t];
+  }
+  float* p = enc + static_cast<size_t>(i) * 63;
+  float* tg = enc + static_cast<size_t>(n + i) * 63;
+  for (int c = 0; c < 3; ++c) {
+    p[c] = x[c];
+    tg[c] = d[c];
+  }
+  for (int j = 0; j < 10; ++j) {
+    const float f = static_cast<float>(1 << j);
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(x[c] * f, &s, &co);
+      p[3 + j * 6 + c] = s;
+      p[3 + j * 6 + 3 + c] = co;
+      tg[3 + j * 6 + c] = f * co * d[c];
+      tg[3 + j * 6 + 3 + c] = -f * s * d[c];
+    }
+  }
+  embed_row(v, 3, 4, venc + static_cast<size_t>(i) * 27);
+}
+// primal rows: h = relu(y + b); tangent rows: t = (y_primal + b > 0) ? y_tangent : 0        (in place, Y is [2n, M])
+__global__ void relu_jvp_kernel(float* __restrict__ Y, const float* __restrict__ bias, int n, int M, int relu) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(n) * M) return;
+  const int m = static_cast<int>(i % M);
+  const float yp = Y[i] + bias[m];
+  const size_t it = i + static_cast<size_t>(n) * M;
+  if (relu) {
+    Y[i] = fmaxf(yp, 0.f);
+    if (!(yp > 0.f)) Y[it] = 0.f;
+  } else {
+    Y[i] = yp;
+  }
+}
+// raw = [rgb(3), alpha] primal + bias; draw = tangents
+__global__ void nerf_point_out_kernel(const float* __restrict__ rgb2, const float* __restrict__ al2, const float* __restrict__ b_rgb,
+                                      const float* __restrict__ b_al, int n, float* __restrict__ raw, float* __restrict__ draw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int c = 0; c < 3; ++c) {
+    raw[i * 4 + c] = rgb2[i * 3 + c] + b_rgb[c];
+    draw[i * 4 + c] = rgb2[(n + i) * 3 + c];
+  }
+  raw[i * 4 + 3] = al2[i] + b_al[0];
+  draw[i * 4 + 3] = al2[n + i];
+}
+
+extern "C" size_t b200nerf_nerf_point_ws_floats(int n_rays) {
+  const size_t n = static_cast<size_t>(n_rays);
+  return 2 * n * 64 + n * 32 + 3 * (2 * n * 256) + 2 * n * 4 + 2 * n + 256;
+}
+
+// params: the 24 fp32 device tensors of NeRF in state_dict order (see b200nerf_nerf_pack)
+extern "C" int b200nerf_nerf_point_jvp(const float* const* t, const float* rays_o, const float* rays_d, const float* viewdirs,
+                                       const float* z, int n_rays, float* ws, float* out_raw, float* out_draw_dz, void* stream) {
+  if (n_rays <= 0) return 0;
+  if (!t || !rays_o || !rays_d || !viewdirs || !z || !ws || !out_raw || !out_draw_dz) return b200_fail("b200nerf_nerf_point_jvp: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = n_rays, n2 = 2 * n_rays;
+  float* enc = ws;                                   // [2n, 63]
+  float* venc = enc + static_cast<size_t>(n2) * 64;  // [n, 27]
+  float* h0 = venc + static_cast<size_t>(n) * 32;    // [2n, 256]
+  float* h1 = h0 + static_cast<size_t>(n2) * 256;
+  float* h2 = h1 + static_cast<size_t>(n2) * 256;
+  float* rgb2 = h2 + static_cast<size_t>(n2) * 256;  // [2n, 3]
+  float* al2 = rgb2 + static_cast<size_t>(n2) * 4;   // [2n]
+  nerf_point_encode_kernel<<<(n + 127) / 128, 128, 0, st>>>(rays_o, rays_d, viewdirs, z, n, enc, venc);
+  LAUNCH_CHECK();
+  auto act = [&](float* Y, const float* bias, int M, int relu) -> int {
+    const size_t tot = static_cast<size_t>(n) * M;
+    relu_jvp_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(Y, bias, n, M, relu);
+    LAUNCH_CHECK();
+    return 0;
+  };
+  float* cur = h0;
+  float* nxt = h1;
+  // run_nerf_helpers.py:109-134: h = relu(L_i(h)); after layer 4, h = cat([input_pts, h])
+  if (lin_fwd(st, n2, 256, 63, enc, 63, t[0], 63, 0, cur, 256, 0, nullptr, 0, 0.f)) return 1;
+  if (act(cur, t[1], 256, 1)) return 1;
+  for (int i = 1; i < 8; ++i) {
+    if (i == 5) {
+      if (lin_fwd(st, n2, 256, 63, enc, 63, t[10], 319, 0, nxt, 256, 0, nullptr, 0, 0.f)) return 1;
+      if (lin_fwd(st, n2, 256, 256, cur, 256, t[10], 319, 63, nxt, 256, 1, nullptr, 0, 0.f)) return 1;
+    } else {
+      if (lin_fwd(st, n2, 256, 256, cur, 256, t[2 * i], 256, 0, nxt, 256, 0, nullptr, 0, 0.f)) return 1;
+    }
+    if (act(nxt, t[2 * i + 1], 256, 1)) return 1;
+    float* tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  // alpha_linear and feature_linear on h7 (no activation)
+  if (lin_fwd(st, n2, 1, 256, cur, 256, t[20], 256, 0, al2, 1, 0, nullptr, 0, 0.f)) return 1;
+  if (lin_fwd(st, n2, 256, 256, cur, 256, t[18], 256, 0, nxt, 256, 0, nullptr, 0, 0.f)) return 1;
+  if (act(nxt, t[19], 256, 0)) return 1;
+  // views_linears.0 on cat([feature, gamma(viewdir)]): the view part has no tangent
+  if (lin_fwd(st, n2, 128, 256, nxt, 256, t[16], 283, 0, h2, 128, 0, nullptr, 0, 0.f)) return 1;
+  if (lin_fwd(st, n, 128, 27, venc, 27, t[16], 283, 256, h2, 128, 1, nullptr, 0, 0.f)) return 1;
+  if (act(h2, t[17], 128, 1)) return 1;
+  if (lin_fwd(st, n2, 3, 128, h2, 128, t[22], 128, 0, rgb2, 3, 0, nullptr, 0, 0.f)) return 1;
+  nerf_point_out_kernel<<<(n + 255) / 256, 256, 0, st>>>(rgb2, al2, t[23], t[21], n, out_raw, out_draw_dz);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- Adam
+// torch.optim.Adam (no weight decay, no amsgrad) on one tensor:
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            size_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+extern "C" int b200nerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                                  float beta2, float eps, int step, float grad_scale, void* stream) {
+  if (n == 0) return 0;
+  if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return b200_fail("b200nerf_adam_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  adam_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  LAUNCH_CHECK();
+  return 0;
+}

@@ -13,8 +13,9 @@ class DepthNet(nn.Module):
     """Per-ray depth predictor (depth_nets/depth_net.py:10-169).
 
     Parameters are created in the reference's order (so a seeded init reproduces its weights) and registered under
-    the reference's names.  ``forward`` runs the fused tcgen05 kernel; the activation-free branch stacks are folded
-    into the first dense layer when the packed image is built (see packing.fold_depthnet)."""
+    the reference's names.  Under ``torch.no_grad()`` ``forward`` runs the fused tcgen05 kernel (the activation-free
+    branch stacks are folded into the first dense layer when the packed image is built, see packing.fold_depthnet);
+    with gradients enabled it runs the literal per-layer fp32 form whose backward yields every parameter gradient."""
 
     def __init__(self, hidden_sizes=[128 for _ in range(6)], cat_hidden_sizes=[128, 128, 128, 128, 256],
                  origin_channels: int = 3, direction_channels: int = 3, multires: int = 10, sphere_radius: float = 2.0,
@@ -63,7 +64,11 @@ class DepthNet(nn.Module):
     def forward(self, rays_o: torch.Tensor, rays_d: torch.Tensor) -> torch.Tensor:
         """[N,1] depth in [near, far] per ray."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "DepthNet training (backward through the kernel) is not built yet; call under torch.no_grad()")
+            # training: literal per-layer fp32 form with saved activations (csrc/train.cu), differentiable
+            from .. import training
+
+            return training.DepthNetTrainFn.apply(rays_o.contiguous().float(), rays_d.contiguous().float(),
+                                                  training.depthnet_arch(self), float(self.sphere_radius), float(self.near),
+                                                  float(self.far), *training.depthnet_params(self))
         return ops.depthnet_forward(self.packed(), rays_o, rays_d, float(self.sphere_radius), float(self.near),
                                     float(self.far))

@@ -155,19 +155,26 @@ def render_rays_test(ray_batch, network_fn, network_query_fn, N_samples, trainer
 
 def render_rays(ray_batch, network_fn, network_query_fn, N_samples, trainer, retraw=True, lindisp=False, perturb=0.0,
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0.0, verbose=False, pytest=False, **kwargs):
-    """Training render (nerf_utils.py:614-733): hierarchical target depth + DepthNet with one sample per ray.
-    Forward only for now (the DepthNet backward kernels are the next milestone)."""
+    """Training render (nerf_utils.py:614-733): hierarchical target depth from the frozen NeRFs (tensor-core kernels, no
+    gradient) + DepthNet with one sample per ray.  With gradients enabled ``depth_net_rgb_map`` and ``depth_net_z_vals``
+    are attached to a graph that reaches DepthNet's parameters (training.py)."""
     rays_o, rays_d = ray_batch[:, 0:3].contiguous(), ray_batch[:, 3:6].contiguous()
     viewdirs = ray_batch[:, -3:].contiguous() if ray_batch.shape[-1] > 8 else None
-    (_, fine_z, _, _, fine_weights, _, _, fine_raw) = sample_as_in_NeRF(
-        ray_batch=ray_batch, N_samples=N_samples, network_fn=network_fn, network_fine=network_fine,
-        network_query_fn=network_query_fn, trainer=trainer, perturb=perturb, raw_noise_std=raw_noise_std, lindisp=lindisp,
-        white_bkgd=white_bkgd, pytest=pytest, kwargs=kwargs)
-    _, max_z, _, _ = ops.argmax_gather(fine_weights, fine_z, fine_raw)
+    with torch.no_grad():
+        (_, fine_z, _, _, fine_weights, _, _, fine_raw) = sample_as_in_NeRF(
+            ray_batch=ray_batch, N_samples=N_samples, network_fn=network_fn, network_fine=network_fine,
+            network_query_fn=network_query_fn, trainer=trainer, perturb=perturb, raw_noise_std=raw_noise_std, lindisp=lindisp,
+            white_bkgd=white_bkgd, pytest=pytest, kwargs=kwargs)
+        _, max_z, _, _ = ops.argmax_gather(fine_weights, fine_z, fine_raw)
     z_dn = kwargs["depth_network"](rays_o, rays_d)
     net = network_fine if network_fine is not None else network_fn
     raw = net.query(viewdirs, rays_o=rays_o, rays_d=rays_d, z=z_dn)
-    rgb, disp, *_ = ops.composite(raw, z_dn, rays_d, white_bkgd=True)
+    if raw.requires_grad:
+        from .. import training
+
+        rgb, disp = training.CompositeSingleFn.apply(raw, z_dn, rays_d)
+    else:
+        rgb, disp, *_ = ops.composite(raw, z_dn, rays_d, white_bkgd=True)
     ret = {"depth_net_rgb_map": rgb, "depth_net_disp_map": disp, "depth_net_z_vals": z_dn, "max_z_vals": max_z,
            "depth_net_pts": ops.points(rays_o, rays_d, z_dn), "max_pts": ops.points(rays_o, rays_d, max_z)}
     if retraw:

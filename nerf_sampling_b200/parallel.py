@@ -44,3 +44,21 @@ def render_sharded(render_slice: Callable[[int, int], torch.Tensor], n_rays: int
     lo, hi = shard_bounds(n_rays, world, rank)
     tile = render_slice(lo, hi)
     return tile if world == 1 else gather_tiles(tile, n_rays, group)
+
+
+def allreduce_gradients(params, group=None) -> float:
+    """Data-parallel DepthNet training (BASELINE config #5): SUM all-reduce of every parameter gradient as ONE flat
+    buffer (3,340,545 fp32 = 13.4 MB for the 10x256 DepthNet) and return the scale 1/world that the optimizer applies
+    (``training.Adam.step(grad_scale=...)``), so that equal ray shards reproduce the single-process mean-loss gradient.
+    The frozen NeRFs need no communication."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return 1.0
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off : off + g.numel()].view_as(g))
+        off += g.numel()
+    return 1.0 / world

@@ -57,3 +57,37 @@ def test_sharded_render_gathers_identical_image_world2():
             p.join(timeout=60)
             assert p.exitcode == 0
         assert all(ok for _, ok, _ in res) and all(shape == (n_rays, 4) for _, _, shape in res)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nerf_sampling_b200.parallel import allreduce_gradients
+
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    params[2].grad = None  # a parameter without gradient is skipped
+    for i, p in enumerate(params[:2]):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    scale = allreduce_gradients(params)
+    ok = (scale == 0.5 and torch.equal(params[0].grad, torch.full((3, 5), 3.0)) and torch.equal(params[1].grad, torch.full((7,), 6.0))
+          and params[2].grad is None)
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2():
+    """Flat-buffer SUM all-reduce of DepthNet gradients + the 1/world scale handed to the optimizer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)

@@ -396,3 +396,108 @@ def test_training_render_forward_matches_golden(lib, b200_models):
     assert float((ex["max_z_vals"].cpu() - torch.from_numpy(g["max_z"])).abs().max()) <= 1e-4
     assert float((rgb.cpu() - torch.from_numpy(g["rgb"])).abs().max()) <= RGB_TOL
     assert float(disp.min()) == 1e10  # S == 1 quirk
+
+
+# --------------------------------------------------------------------------------------------- training step (config #5)
+def _train_setup(b200_models):
+    from nerf_sampling_b200.trainers import DepthNetTrainer
+
+    b_coarse, b_fine, b_dn = b200_models
+    tr = DepthNetTrainer(dataset_type="blender", basedir="/tmp", expname="x", no_batching=True, datadir="x", half_res=True,
+                         white_bkgd=True, device=DEV, n_layers=10, layer_width=256, N_importance=128, N_samples=64,
+                         input_dims_embed=3, perturb=0.0)
+    kw = dict(network_fn=b_coarse, network_fine=b_fine, depth_network=b_dn, network_query_fn=None, N_samples=64,
+              N_importance=128, trainer=tr, white_bkgd=True, raw_noise_std=0.0, perturb=0.0, lindisp=True, ndc=False, near=2.0,
+              far=6.0, use_viewdirs=True, model_mode="train")
+    return tr, kw
+
+
+def test_training_step_gradients_match_golden(lib, b200_models):
+    """core_optimization_loop (Trainer.py:506-544): both losses and the DepthNet gradients of the reference's own
+    backward pass on the same 96 rays / targets (fixture g5)."""
+    from nerf_sampling_b200.nerf_pytorch import nerf_utils
+
+    g = load_golden("g5")
+    _, _, b_dn = b200_models
+    tr, kw = _train_setup(b200_models)
+    for p in b_dn.parameters():
+        p.grad = None
+    rgb, disp, ex = nerf_utils.render(800, 800, O.intrinsics(800, 800), rays=(cu(g["rays_o"]), cu(g["rays_d"])), retraw=True, **kw)
+    assert rgb.requires_grad and ex["depth_net_z_vals"].requires_grad and not ex["max_z_vals"].requires_grad
+    target = cu(g["target"])
+    img_loss = torch.mean((rgb - target) ** 2)
+    dn_loss = torch.nn.functional.mse_loss(ex["depth_net_z_vals"], ex["max_z_vals"])
+    dn_loss.backward(retain_graph=True)
+    img_loss.backward()
+    assert abs(float(img_loss) - float(g["img_loss"])) <= 1e-5 * max(1.0, float(g["img_loss"]))
+    assert abs(float(dn_loss) - float(g["dn_loss"])) <= 1e-4 * max(1.0, float(g["dn_loss"]))
+    grads = {k: p.grad for k, p in b_dn.named_parameters()}
+    assert all(v is not None and bool(torch.isfinite(v).all()) for v in grads.values())
+    gnorm = float(torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())))
+    assert abs(gnorm - float(g["grad_norm"])) <= 2e-3 * float(g["grad_norm"]), (gnorm, float(g["grad_norm"]))
+    for key, name in (("grad_to_depth_w", "to_depth.0.weight"), ("grad_cat0_b", "cat_layers.0.bias"),
+                      ("grad_origin0_b", "origin_layers.0.bias"), ("grad_inter9_b", "intersection_layers.9.bias")):
+        want = torch.from_numpy(g[key])
+        got = grads[name].cpu()
+        assert got.shape == want.shape
+        assert float((got - want).abs().max()) <= 2e-3 * float(want.abs().max()) + 1e-9, name
+    for p in b_dn.parameters():
+        p.grad = None
+
+
+def test_depthnet_literal_forward_and_backward_vs_torch(lib, oracle_models):
+    """The fp32 training form of DepthNet against the oracle's literal forward differentiated by torch autograd."""
+    from nerf_sampling_b200.depth_nets import DepthNet
+
+    _, _, dn = oracle_models
+    m = DepthNet(hidden_sizes=[256] * 10, cat_hidden_sizes=[256] * 10, sphere_radius=2.0)
+    m.load_state_dict(dn)
+    m.to(DEV)
+    _, packed = scene_rays(9, 13)
+    ro, rd = packed[:, 0:3].contiguous().to(DEV), packed[:, 3:6].contiguous().to(DEV)
+    z = m(ro, rd)
+    w = torch.linspace(0.5, 1.5, z.numel(), device=DEV).reshape(z.shape)  # one sign: no cancellation in the bias sums
+    (z * w).sum().backward()
+    ref = {k: v.clone().to(DEV).requires_grad_(True) for k, v in dn.items()}
+    zr = O.depthnet_forward(ref, ro, rd)
+    (zr * w).sum().backward()
+    assert float((z - zr).abs().max()) <= 1e-5
+    for k, p in m.named_parameters():
+        want = ref[k].grad
+        assert float((p.grad - want).abs().max()) <= 2e-3 * float(want.abs().max()) + 1e-7, k  # sums with cancellation
+
+
+def test_nerf_point_jvp_vs_torch(lib, oracle_models, b200_models):
+    """raw and d raw / d z of the frozen NeRF at one sample per ray against torch autograd on the oracle."""
+    from nerf_sampling_b200 import training
+
+    _, fine, _ = oracle_models
+    _, b_fine, _ = b200_models
+    _, packed = scene_rays(8, 8)
+    ro, rd, vd = (packed[:, a:b].contiguous().to(DEV) for a, b in ((0, 3), (3, 6), (8, 11)))
+    z = (3.0 + torch.rand(ro.shape[0], 1, generator=torch.Generator().manual_seed(2))).to(DEV).requires_grad_(True)
+    raw = training.NerfPointFn.apply(z, ro, rd, vd, *training.nerf_params(b_fine))
+    fp = O.params_to(fine, DEV)
+    z2 = z.detach().clone().requires_grad_(True)
+    pts = ro[:, None, :] + rd[:, None, :] * z2[:, :, None]
+    want = O.run_network(pts, vd, fp)
+    assert float((raw - want).abs().max()) <= 1e-5
+    for c in range(4):
+        gw, = torch.autograd.grad(want[..., c].sum(), z2, retain_graph=True)
+        gg, = torch.autograd.grad(raw[..., c].sum(), z, retain_graph=True)
+        assert float((gg - gw).abs().max()) <= 1e-3 * float(gw.abs().max()) + 1e-6, c
+
+
+def test_adam_matches_torch(lib):
+    from nerf_sampling_b200 import training
+
+    torch.manual_seed(0)
+    p1 = torch.nn.Parameter(torch.randn(300, 70, device=DEV))
+    p2 = torch.nn.Parameter(p1.detach().clone())
+    ours, ref = training.Adam([p1], lr=1e-4), torch.optim.Adam([p2], lr=1e-4)
+    for step in range(5):
+        gr = torch.randn_like(p1) * (10.0 ** (step - 2))
+        p1.grad, p2.grad = gr.clone(), gr.clone()
+        ours.step()
+        ref.step()
+    assert float((p1 - p2).abs().max()) <= 1e-6  # one ulp at |p| ~ 2: torch orders the update differently
