@@ -20,7 +20,9 @@
 // ------------------------------------------------------------------------------------------- strided SGEMM
 // C[M,N] (row-major, ldc) = (beta ? C : 0) + sum_k A(m,k) * B(k,n) [+ bias[n]] [then LeakyReLU(slope) if act]
 // A(m,k) = A[m*sAm + k*sAk], B(k,n) = B[k*sBk + n*sBn]: covers X*W^T (forward), dY*W (input gradient) and dY^T*X
-// (weight gradient) without transposes.  64x64x16 tiles, 256 threads, 4x4 outputs per thread.
+// (weight gradient) without transposes.  64x64x16 tiles, 256 threads, 4x4 outputs per thread.  gridDim.z > 1 splits
+// the K range (the weight gradients reduce over thousands of rays into a 256 x ~300 output: without the split only
+// ~20 CTAs would run); the partial sums are then added atomically into a zeroed C.
 constexpr int GM = 64, GN = 64, GK = 16;
 
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long sAm, long sAk,
@@ -39,18 +41,22 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
 
   // element (r, c) of a 64 x 16 tile per thread and pass: walk the contiguous dimension with consecutive threads
   const bool a_kfast = sAk == 1, b_nfast = sBn == 1;
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  const int k_per = ((K + gridDim.z - 1) / gridDim.z + GK - 1) / GK * GK;
+  const int k_begin = blockIdx.z * k_per;
+  const int k_end = min(K, k_begin + k_per);
+  const bool split = gridDim.z > 1;
+  for (int k0 = k_begin; k0 < k_end; k0 += GK) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int idx = tid + e * 256;
       int m, k;
       if (a_kfast) { m = idx >> 4; k = idx & 15; } else { m = idx & 63; k = idx >> 6; }
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < M && gk < K) ? __ldg(A + gm * sAm + gk * sAk) : 0.f;
+      As[k][m] = (gm < M && gk < k_end) ? __ldg(A + gm * sAm + gk * sAk) : 0.f;
       int n, kb;
       if (b_nfast) { n = idx & 63; kb = idx >> 6; } else { n = idx >> 4; kb = idx & 15; }
       const int gn = n0 + n, gkb = k0 + kb;
-      Bs[kb][n] = (gn < N && gkb < K) ? __ldg(B + gkb * sBk + gn * sBn) : 0.f;
+      Bs[kb][n] = (gn < N && gkb < k_end) ? __ldg(B + gkb * sBk + gn * sBn) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -75,6 +81,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
       if (gn >= N) continue;
       float v = acc[i][j];
       float* c = C + static_cast<size_t>(gm) * ldc + gn;
+      if (split) {
+        if (bias && blockIdx.z == 0) v += __ldg(bias + gn);
+        atomicAdd(c, v);
+        continue;
+      }
       if (beta) v += *c;
       if (bias) v += __ldg(bias + gn);
       if (act) v = v > 0.f ? v : v * slope;
@@ -87,6 +98,16 @@ static int sgemm(cudaStream_t st, int M, int N, int K, const float* A, long sAm,
                  float* C, int ldc, int beta, const float* bias = nullptr, int act = 0, float slope = 0.f) {
   if (M <= 0 || N <= 0) return 0;
   dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
+  const int blocks = static_cast<int>(grid.x * grid.y);
+  if (!act && blocks < 120 && K >= 512) {
+    int splits = (296 + blocks - 1) / blocks;
+    const int max_splits = K / 128;
+    if (splits > max_splits) splits = max_splits;
+    if (splits > 1) {
+      grid.z = splits;
+      if (!beta) CUDA_TRY(cudaMemset2DAsync(C, static_cast<size_t>(ldc) * sizeof(float), 0, static_cast<size_t>(N) * sizeof(float), M, st));
+    }
+  }
   sgemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, bias, act, slope);
   LAUNCH_CHECK();
   return 0;

@@ -1,6 +1,6 @@
 """Mirror of ``nerf_pytorch/trainers/Trainer.py`` restricted to what the render_rays path reads:
-the constructor's config bag (:18-130), intrinsics (:136-146), ``run_network`` (:789-806) and the
-coarse / fine samplers (:553-710).  Data loading, logging and the training loop are caller context."""
+the constructor's config bag (:18-130), intrinsics (:136-146), ``core_optimization_loop`` (:506-544),
+``run_network`` (:789-806) and the coarse / fine samplers (:553-710).  Data loading and logging are caller context."""
 
 from __future__ import annotations
 
@@ -41,6 +41,44 @@ class Trainer:
             self.K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
         self.H, self.W = H, W
         return [H, W, focal]
+
+    # ------------------------------------------------------------------ one optimisation step (config #5)
+    def core_optimization_loop(self, sampling_optimizer, render_kwargs_train, batch_rays, i, target_s):
+        """Render a ray batch and back-propagate into DepthNet (Trainer.py:506-544): ``mse(z_dn, max_z)`` with
+        ``retain_graph`` first, then the colour loss; under ``torch.distributed`` the DepthNet gradients are
+        sum-all-reduced as one flat buffer and averaged by the optimizer (equal ray shards per rank reproduce the
+        single-process gradient)."""
+        import torch.nn.functional as F
+
+        from ... import parallel, training
+
+        depth_net_rgb, depth_net_disp, extras = nerf_utils.render(self.H, self.W, self.K, chunk=self.chunk, rays=batch_rays,
+                                                                  verbose=i < 10, retraw=True, **render_kwargs_train)
+        sampling_optimizer.zero_grad()
+        img_loss = nerf_utils.run_nerf_helpers.img2mse(depth_net_rgb, target_s)
+        loss = img_loss
+        psnr = nerf_utils.run_nerf_helpers.mse2psnr(img_loss)
+        psnr0 = None
+        depth_net_loss = F.mse_loss(extras["depth_net_z_vals"], extras["max_z_vals"])
+        depth_net_loss.backward(retain_graph=True)
+        loss.backward()
+        params = [p for g in sampling_optimizer.param_groups for p in g["params"]]
+        scale = parallel.allreduce_gradients(params)
+        if isinstance(sampling_optimizer, training.Adam):
+            sampling_optimizer.step(grad_scale=scale)
+        else:
+            if scale != 1.0:
+                for p in params:
+                    if p.grad is not None:
+                        p.grad.mul_(scale)
+            sampling_optimizer.step()
+        return loss, depth_net_loss, psnr, psnr0
+
+    def update_learning_rate(self, optimizer):
+        """Exponential decay of Trainer.py:546-551."""
+        new_lrate = self.lrate * (0.1 ** (self.global_step / (self.lrate_decay * 1000)))
+        for param_group in optimizer.param_groups:
+            param_group["lr"] = new_lrate
 
     # ------------------------------------------------------------------ operators on the hot path
     def run_network(self, inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):

@@ -40,7 +40,10 @@ class DepthNetTrainer(Blender.BlenderTrainer):
         depth_network = DepthNet(hidden_sizes=[self.layer_width] * self.n_layers,
                                  cat_hidden_sizes=[self.layer_width] * self.n_layers,
                                  sphere_radius=self.sphere_radius).to(self.device)
-        sampling_optimizer = torch.optim.Adam(params=list(depth_network.parameters()), lr=self.depth_net_lr)
+        from .. import training
+
+        # torch.optim.Adam semantics and state_dict keys, on the library's fused kernel
+        sampling_optimizer = training.Adam(params=list(depth_network.parameters()), lr=self.depth_net_lr)
         if self.depth_net_path is not None and self.depth_net_path != "None":
             ckpts = [self.depth_net_path]
         else:

@@ -501,3 +501,34 @@ def test_adam_matches_torch(lib):
         ours.step()
         ref.step()
     assert float((p1 - p2).abs().max()) <= 1e-6  # one ulp at |p| ~ 2: torch orders the update differently
+
+
+def test_core_optimization_loop_step(lib, oracle_models):
+    """One Trainer.core_optimization_loop step: losses of the reference, DepthNet moves, NeRFs stay frozen."""
+    from nerf_sampling_b200 import training
+    from nerf_sampling_b200.depth_nets import DepthNet
+    from nerf_sampling_b200.nerf_pytorch.run_nerf_helpers import NeRF
+
+    coarse, fine, dn = oracle_models
+
+    def nerf(sd):
+        m = NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+        m.load_state_dict(sd)
+        return m.to(DEV)
+
+    d = DepthNet(hidden_sizes=[256] * 10, cat_hidden_sizes=[256] * 10, sphere_radius=2.0)
+    d.load_state_dict(dn)
+    models = (nerf(coarse), nerf(fine), d.to(DEV))
+    tr, kw = _train_setup(models)
+    tr.H, tr.W, tr.K, tr.chunk = 800, 800, O.intrinsics(800, 800), 32768
+    g = load_golden("g5")
+    opt = training.Adam(list(models[2].parameters()), lr=1e-4)
+    before = [p.detach().clone() for p in models[2].parameters()]
+    fine_before = [p.detach().clone() for p in models[1].parameters()]
+    loss, dn_loss, psnr, psnr0 = tr.core_optimization_loop(opt, kw, (cu(g["rays_o"]), cu(g["rays_d"])), 0, cu(g["target"]))
+    assert abs(float(loss) - float(g["img_loss"])) <= 1e-5 and abs(float(dn_loss) - float(g["dn_loss"])) <= 1e-4 and psnr0 is None
+    moved = [float((a - b).abs().max()) for a, b in zip(before, models[2].parameters())]
+    assert all(0.0 < m <= 1.01e-4 for m in moved)   # first Adam step moves every weight by ~lr
+    assert all(torch.equal(a, b) for a, b in zip(fine_before, models[1].parameters()))
+    loss2, dn_loss2, _, _ = tr.core_optimization_loop(opt, kw, (cu(g["rays_o"]), cu(g["rays_d"])), 1, cu(g["target"]))
+    assert float(dn_loss2) < float(dn_loss)  # the depth loss goes down on the batch it was fitted to
