@@ -89,6 +89,106 @@ def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.0, fa
     return _finish(batchify_rays(packed, chunk, **kwargs), sh, rays_o, rays_d)
 
 
+def _write_png(path: str, rgb8) -> None:
+    """Minimal 8-bit RGB PNG encoder (zlib from the standard library; the reference uses imageio.imwrite)."""
+    import struct
+    import zlib
+
+    import numpy as np
+
+    h, w, c = rgb8.shape
+    assert c == 3 and rgb8.dtype == np.uint8
+    rows = np.concatenate([np.zeros((h, 1), np.uint8), rgb8.reshape(h, w * 3)], axis=1)  # filter type 0 per scanline
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0))
+                + chunk(b"IDAT", zlib.compress(rows.tobytes(), 3)) + chunk(b"IEND", b""))
+
+
+def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=False, save_scene_data=False, gt_imgs=None,
+                savedir=None, render_factor=0):
+    """Render a list of camera poses (nerf_utils.py:258-360) -> (rgbs [n,H,W,3], disps [n,H,W], mean PSNR) as numpy.
+
+    Same results as the reference's loop, different schedule: view k+1 is rendered while view k's rgb / disp travel to
+    pinned host memory on a side stream, and PNG encoding (``savedir``) runs in worker threads, so the GPU never waits
+    for ``.cpu().numpy()``, PSNR arithmetic or file I/O.  ``wandb_log`` is accepted and ignored (logging is caller
+    context); ``save_scene_data`` collects ``depth_net_pts`` / ``depth_net_weights`` like the reference."""
+    import concurrent.futures
+
+    import numpy as np
+
+    H, W, focal = hwf
+    H, W = int(H), int(W)
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    n = len(render_poses)
+    trainer = render_kwargs["trainer"]
+    if save_scene_data:
+        trainer.save_scene_data = True
+    dev = torch.device("cuda", torch.cuda.current_device())
+    h_rgb = torch.empty(n, H, W, 3, dtype=torch.float32).pin_memory()
+    h_disp = torch.empty(n, H, W, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    done = []
+    all_pts, all_weights, mses = [], [], []
+    pool = concurrent.futures.ThreadPoolExecutor(max_workers=4) if savedir is not None else None
+    jobs = []
+    if savedir is not None:
+        os.makedirs(savedir, exist_ok=True)
+
+    def save_png(i, ev):
+        ev.synchronize()
+        rgb8 = run_nerf_helpers.to8b(h_rgb[i].numpy())
+        _write_png(os.path.join(savedir, "{:03d}.png".format(i)), rgb8)
+
+    for i, c2w in enumerate(render_poses):
+        c2w = torch.as_tensor(c2w)
+        rgb, disp, extras = render_test(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ready)
+            h_rgb[i].copy_(rgb, non_blocking=True)
+            h_disp[i].copy_(disp, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        rgb.record_stream(copy_stream)
+        disp.record_stream(copy_stream)
+        done.append(ev)
+        if trainer.compare_nerf and extras.get("max_z_vals") is not None:
+            # F.mse_loss(max_z [H,W,1], z_vals [H,W,S]) broadcasts over the samples in the reference (:311-316)
+            mses.append(torch.mean((extras["max_z_vals"] - extras["depth_net_z_vals"]) ** 2))
+        if save_scene_data and savedir is not None:
+            all_pts.append(torch.flatten(extras["depth_net_pts"], end_dim=2))
+            all_weights.append(torch.flatten(extras["depth_net_weights"], end_dim=2))
+        if pool is not None:
+            jobs.append(pool.submit(save_png, i, ev))
+    copy_stream.synchronize()
+    for j in jobs:
+        j.result()
+    if pool is not None:
+        pool.shutdown()
+    rgbs, disps = h_rgb.numpy(), h_disp.numpy()
+    total_psnr = 0.0
+    if gt_imgs is not None and render_factor == 0:
+        lines = []
+        for i in range(n):
+            psnr = -10.0 * np.log10(np.mean(np.square(rgbs[i] - np.asarray(gt_imgs[i])[..., :3])))
+            total_psnr += psnr
+            lines.append(f"{i:03d}.png, PSNR: {psnr}" + (f", MSE: {float(mses[i])}" if i < len(mses) else ""))
+        if savedir is not None:
+            with open(os.path.join(savedir, "psnr.txt"), "a") as f:
+                f.write("\n".join(lines) + f"\nAvg of {n} images:\nPSNR: {total_psnr / n}\n")
+                if mses:
+                    f.write(f"MSE: {float(sum(mses)) / n}")
+    if save_scene_data and savedir is not None:
+        torch.save({"all_pts": torch.cat(all_pts), "all_weights": torch.cat(all_weights)}, os.path.join(savedir, "scene_data.pt"))
+    return rgbs, disps, total_psnr / max(n, 1)
+
+
 def sample_as_in_NeRF(ray_batch, network_fn, network_fine, network_query_fn, N_samples, trainer, perturb, raw_noise_std,
                       lindisp, white_bkgd, kwargs, pytest):
     """Vanilla coarse + fine pass (nerf_utils.py:497-611)."""

@@ -1,5 +1,7 @@
 """Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.  Needs a B200."""
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -532,3 +534,34 @@ def test_core_optimization_loop_step(lib, oracle_models):
     assert all(torch.equal(a, b) for a, b in zip(fine_before, models[1].parameters()))
     loss2, dn_loss2, _, _ = tr.core_optimization_loop(opt, kw, (cu(g["rays_o"]), cu(g["rays_d"])), 1, cu(g["target"]))
     assert float(dn_loss2) < float(dn_loss)  # the depth loss goes down on the batch it was fitted to
+
+
+def test_render_path_matches_single_views(lib, b200_models, tmp_path):
+    """render_path (nerf_utils.py:258-360): pipelined multi-pose render == the same poses rendered one by one;
+    PSNR bookkeeping and PNG output."""
+    import numpy as np
+
+    from nerf_sampling_b200.nerf_pytorch import nerf_utils
+    from nerf_sampling_b200.trainers import DepthNetTrainer
+
+    b_coarse, b_fine, b_dn = b200_models
+    tr = DepthNetTrainer(dataset_type="blender", basedir="/tmp", expname="x", no_batching=True, datadir="x", half_res=True,
+                         white_bkgd=True, device=DEV, n_layers=10, layer_width=256, N_importance=128, N_samples=64,
+                         input_dims_embed=3, distance=0.1, sampling_mode="uniform", n_depth_samples=16)
+    kw = dict(network_fn=b_coarse, network_fine=b_fine, depth_network=b_dn, network_query_fn=None, N_samples=64,
+              N_importance=128, trainer=tr, white_bkgd=True, raw_noise_std=0.0, perturb=False, lindisp=True, ndc=False,
+              near=2.0, far=6.0, use_viewdirs=True, model_mode="test")
+    H = W = 40
+    K = O.intrinsics(H, W)
+    poses = torch.stack([O.pose_spherical(a, -30.0, 4.0) for a in (0.0, 40.0, 80.0)])
+    gt = np.random.default_rng(0).random((3, H, W, 3), dtype=np.float32)
+    with torch.no_grad():
+        rgbs, disps, psnr = nerf_utils.render_path(poses, [H, W, float(K[0][0])], K, 32768, kw, gt_imgs=gt, savedir=str(tmp_path))
+        singles = [nerf_utils.render_test(H, W, K, chunk=32768, c2w=p[:3, :4], **kw) for p in poses]
+    assert rgbs.shape == (3, H, W, 3) and disps.shape == (3, H, W)
+    for i, (rgb, disp, _) in enumerate(singles):
+        assert np.array_equal(rgbs[i], rgb.cpu().numpy()) and np.array_equal(disps[i], disp.cpu().numpy())
+    want = np.mean([-10.0 * np.log10(np.mean(np.square(rgbs[i] - gt[i]))) for i in range(3)])
+    assert abs(psnr - want) < 1e-9
+    assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".png")) == ["000.png", "001.png", "002.png"]
+    assert "Avg of 3 images" in open(tmp_path / "psnr.txt").read()

@@ -267,3 +267,33 @@ def test_sphere_intersection_known_answers(impl, o, d, r, want):
     t, pts = fn(torch.tensor([o]), torch.tensor([d]), torch.tensor([r]))
     assert pts.shape == (1, 2, 3) and t.shape == (1, 2)
     assert nan_equal(pts[0], torch.tensor(want))
+
+
+def test_png_writer_roundtrip(tmp_path):
+    """The stdlib PNG encoder of render_path: decode the IDAT stream by hand and compare pixels."""
+    import struct
+    import zlib
+
+    import numpy as np
+
+    from nerf_sampling_b200.nerf_pytorch.nerf_utils import _write_png
+
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(13, 7, 3), dtype=np.uint8)
+    path = str(tmp_path / "x.png")
+    _write_png(path, img)
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, ihdr = 8, b"", None
+    while pos < len(data):
+        ln, tag = struct.unpack(">I", data[pos : pos + 4])[0], data[pos + 4 : pos + 8]
+        body = data[pos + 8 : pos + 8 + ln]
+        assert struct.unpack(">I", data[pos + 8 + ln : pos + 12 + ln])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF
+        if tag == b"IHDR":
+            ihdr = struct.unpack(">IIBBBBB", body)
+        if tag == b"IDAT":
+            idat += body
+        pos += 12 + ln
+    assert ihdr == (7, 13, 8, 2, 0, 0, 0)
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(13, 1 + 7 * 3)
+    assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(13, 7, 3), img)
