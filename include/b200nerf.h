@@ -80,6 +80,13 @@ int b200nerf_depthnet_pack(const float* h_w0, const float* h_b0, const float* co
 int b200nerf_get_rays(int H, int W, float fx, float fy, float cx, float cy, const float* h_c2w, float* rays_o,
                       float* rays_d, float* viewdirs, void* stream);
 
+/* The same rays for selected pixels only (flat row-major indices, int64): training batches
+ * (Trainer.sample_random_ray_batch, nerf_pytorch/trainers/Trainer.py:400-475) without materialising all H*W rays. */
+int b200nerf_get_rays_at(int H, int W, float fx, float fy, float cx, float cy, const float* h_c2w, const long long* pix, int n,
+                         float* rays_o, float* rays_d, float* viewdirs, void* stream);
+/* out[t, :] = image[pix[t], :] -- the target colours of those pixels; image [H*W, channels] on the device. */
+int b200nerf_gather_pixels(const float* image, const long long* pix, int n, int channels, float* out, void* stream);
+
 /* viewdirs = rays_d / ||rays_d||  (nerf_utils.py:173) */
 int b200nerf_normalize_dirs(const float* rays_d, int n_rays, float* viewdirs, void* stream);
 

@@ -30,6 +30,8 @@ SIGNATURES = {
     "b200nerf_depthnet_aux_floats": (SZ, [I]),
     "b200nerf_depthnet_pack": (I, [P, P, P, I, P, P, I, P, P]),
     "b200nerf_get_rays": (I, [I, I, F, F, F, F, P, P, P, P, P]),
+    "b200nerf_get_rays_at": (I, [I, I, F, F, F, F, P, P, I, P, P, P, P]),
+    "b200nerf_gather_pixels": (I, [P, P, I, I, P, P]),
     "b200nerf_normalize_dirs": (I, [P, I, P, P]),
     "b200nerf_depthnet_fwd": (I, [P, P, I, I, P, P, I, F, F, F, P, P]),
     "b200nerf_place_samples": (I, [P, P, I, I, I, F, F, P, P]),

@@ -273,6 +273,55 @@ extern "C" int b200nerf_get_rays(int H, int W, float fx, float fy, float cx, flo
   return 0;
 }
 
+// Rays of selected pixels only (training batches: Trainer.sample_random_ray_batch, trainers/Trainer.py:400-475, builds
+// all H*W rays and then indexes N_rand of them).  pix = flat row-major pixel indices.
+__global__ void get_rays_at_kernel(int W, float fx, float fy, float cx, float cy, Cam cam, const long long* __restrict__ pix, int n,
+                                   float* __restrict__ ro, float* __restrict__ rd, float* __restrict__ vd) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long idx = pix[t];
+  const float i = static_cast<float>(idx % W), j = static_cast<float>(idx / W);
+  const float d0 = __fdiv_rn(__fadd_rn(i, -cx), fx);
+  const float d1 = -__fdiv_rn(__fadd_rn(j, -cy), fy);
+  const float d2 = -1.f;
+  float d[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    d[a] = __fadd_rn(__fadd_rn(__fmul_rn(d0, cam.r[4 * a + 0]), __fmul_rn(d1, cam.r[4 * a + 1])), __fmul_rn(d2, cam.r[4 * a + 2]));
+  const float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (ro) ro[t * 3 + a] = cam.r[4 * a + 3];
+    if (rd) rd[t * 3 + a] = d[a];
+    if (vd) vd[t * 3 + a] = __fdiv_rn(d[a], nrm);
+  }
+}
+// out[t, :] = image[pix[t], :]   (target colours of the selected pixels)
+__global__ void gather_pixels_kernel(const float* __restrict__ image, const long long* __restrict__ pix, int n, int C,
+                                     float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * C) return;
+  out[t] = image[pix[t / C] * C + t % C];
+}
+
+extern "C" int b200nerf_get_rays_at(int H, int W, float fx, float fy, float cx, float cy, const float* h_c2w, const long long* pix,
+                                    int n, float* rays_o, float* rays_d, float* viewdirs, void* stream) {
+  if (H <= 0 || W <= 0 || !h_c2w || n < 0 || (n && !pix)) return fail("b200nerf_get_rays_at: bad arguments");
+  if (n == 0) return 0;
+  Cam cam;
+  memcpy(cam.r, h_c2w, sizeof(cam.r));
+  get_rays_at_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(W, fx, fy, cx, cy, cam, pix, n, rays_o, rays_d, viewdirs);
+  LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200nerf_gather_pixels(const float* image, const long long* pix, int n, int channels, float* out, void* stream) {
+  if (n < 0 || channels <= 0 || (n && (!image || !pix || !out))) return fail("b200nerf_gather_pixels: bad arguments");
+  if (n == 0) return 0;
+  gather_pixels_kernel<<<(n * channels + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(image, pix, n, channels, out);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void normalize_dirs_kernel(const float* __restrict__ rd, int n, float* __restrict__ vd) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

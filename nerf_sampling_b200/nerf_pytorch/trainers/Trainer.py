@@ -42,6 +42,43 @@ class Trainer:
         self.H, self.W = H, W
         return [H, W, focal]
 
+    # ------------------------------------------------------------------ training batches
+    def sample_random_ray_batch(self, rays_rgb, i_batch, i_train, images, poses, i):
+        """(rays_rgb, i_batch, batch_rays [2,N_rand,3], target_s [N_rand,3]) -- Trainer.py:400-475.
+
+        no_batching (the reference's lego configuration): pick a training image, pick N_rand pixels (centre crop while
+        ``i < precrop_iters``), and generate ONLY those rays on the device; the reference builds all H*W rays with
+        ``get_rays`` and draws the pixels with ``np.random.choice`` on the host (set ``self.reference_rng = True`` to draw
+        them the same way and consume the same NumPy random stream).  ``images`` may be a device tensor [n,H,W,3+]."""
+        if self.use_batching:
+            batch = torch.transpose(rays_rgb[i_batch : i_batch + self.N_rand], 0, 1)
+            batch_rays, target_s = batch[:2], batch[2]
+            i_batch += self.N_rand
+            if i_batch >= rays_rgb.shape[0]:
+                rays_rgb = rays_rgb[torch.randperm(rays_rgb.shape[0], device=rays_rgb.device)]
+                i_batch = 0
+            return rays_rgb, i_batch, batch_rays, target_s
+        img_i = 42 if self.single_image else int(np.random.choice(i_train))
+        dev = torch.device(self.device if str(self.device) != "cpu" else "cuda")
+        target = torch.as_tensor(images[img_i], dtype=torch.float32).to(dev)
+        self.c2w = torch.as_tensor(poses[img_i])[:3, :4].clone().detach()
+        if i < self.precrop_iters:
+            dH, dW = int(self.H // 2 * self.precrop_frac), int(self.W // 2 * self.precrop_frac)
+            h0, w0, hh, ww = self.H // 2 - dH, self.W // 2 - dW, 2 * dH, 2 * dW
+        else:
+            h0, w0, hh, ww = 0, 0, self.H, self.W
+        n_pix = hh * ww
+        if self.single_ray:
+            sel = torch.tensor([91], device=dev)
+        elif getattr(self, "reference_rng", False):
+            sel = torch.from_numpy(np.random.choice(n_pix, size=[self.N_rand], replace=False)).to(dev)
+        else:
+            sel = torch.randperm(n_pix, device=dev)[: self.N_rand]
+        pix = (h0 + sel // ww) * self.W + (w0 + sel % ww)   # flat index into the full image
+        rays_o, rays_d, _ = ops.get_rays_at(self.H, self.W, self.K, self.c2w, pix)
+        target_s = ops.gather_pixels(target[..., :3].contiguous(), pix)
+        return rays_rgb, i_batch, torch.stack([rays_o, rays_d], 0), target_s
+
     # ------------------------------------------------------------------ one optimisation step (config #5)
     def core_optimization_loop(self, sampling_optimizer, render_kwargs_train, batch_rays, i, target_s):
         """Render a ray batch and back-propagate into DepthNet (Trainer.py:506-544): ``mse(z_dn, max_z)`` with

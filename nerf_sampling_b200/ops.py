@@ -47,6 +47,31 @@ def get_rays(H: int, W: int, K, c2w, device=None) -> Tuple[torch.Tensor, torch.T
     return ro, rd, vd
 
 
+def get_rays_at(H: int, W: int, K, c2w, pix: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """rays_o, rays_d, viewdirs [n,3] of the pixels ``pix`` (flat row-major int64 indices on the device)."""
+    if not pix.is_cuda or pix.dtype != torch.int64:
+        raise _lib.B200NerfError("pix must be an int64 CUDA tensor")
+    pix = pix.contiguous()
+    c = torch.as_tensor(c2w, dtype=torch.float32, device="cpu")[:3, :4].contiguous()
+    n = pix.numel()
+    ro, rd, vd = (torch.empty(n, 3, device=pix.device) for _ in range(3))
+    with torch.cuda.device(pix.device):
+        _lib.check(_lib.lib().b200nerf_get_rays_at(H, W, float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]),
+                                                   c.data_ptr(), _p(pix), n, _p(ro), _p(rd), _p(vd), _stream()))
+    return ro, rd, vd
+
+
+def gather_pixels(image: torch.Tensor, pix: torch.Tensor) -> torch.Tensor:
+    """image.reshape(-1, C)[pix] for a device image [H,W,C] and int64 pixel indices."""
+    image = _dev(image, "image")
+    ch = image.shape[-1]
+    pix = pix.contiguous()
+    out = torch.empty(pix.numel(), ch, device=image.device)
+    with torch.cuda.device(image.device):
+        _lib.check(_lib.lib().b200nerf_gather_pixels(_p(image), _p(pix), pix.numel(), ch, _p(out), _stream()))
+    return out
+
+
 def normalize_dirs(rays_d: torch.Tensor) -> torch.Tensor:
     rays_d = _dev(rays_d, "rays_d").reshape(-1, 3)
     out = torch.empty_like(rays_d)

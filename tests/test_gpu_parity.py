@@ -565,3 +565,34 @@ def test_render_path_matches_single_views(lib, b200_models, tmp_path):
     assert abs(psnr - want) < 1e-9
     assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".png")) == ["000.png", "001.png", "002.png"]
     assert "Avg of 3 images" in open(tmp_path / "psnr.txt").read()
+
+
+def test_sample_random_ray_batch_matches_full_ray_grid(lib):
+    """Trainer.sample_random_ray_batch (Trainer.py:400-475): rays generated for the selected pixels only are bit-identical
+    to indexing the full get_rays grid; the reference RNG option reproduces np.random.choice; centre crop respected."""
+    from nerf_sampling_b200 import ops
+    from nerf_sampling_b200.trainers import DepthNetTrainer
+
+    H, W = 60, 80
+    tr = DepthNetTrainer(dataset_type="blender", basedir="/tmp", expname="x", no_batching=True, datadir="x", half_res=True,
+                         white_bkgd=True, device=DEV, N_rand=128, precrop_iters=5, precrop_frac=0.5)
+    tr.H, tr.W, tr.K = H, W, O.intrinsics(H, W)
+    images = torch.rand(3, H, W, 3, generator=torch.Generator().manual_seed(0))
+    poses = torch.stack([O.pose_spherical(a, -30.0, 4.0) for a in (0.0, 40.0, 80.0)])
+    tr.reference_rng = True
+    np.random.seed(7)
+    _, _, batch_rays, target = tr.sample_random_ray_batch(None, 0, [0, 1, 2], images, poses, i=10)
+    np.random.seed(7)
+    img_i = int(np.random.choice([0, 1, 2]))
+    sel = torch.from_numpy(np.random.choice(H * W, size=[128], replace=False))
+    ro, rd, _ = ops.get_rays(H, W, tr.K, poses[img_i][:3, :4])
+    assert torch.equal(batch_rays[0].cpu(), ro.cpu()[sel]) and torch.equal(batch_rays[1].cpu(), rd.cpu()[sel])
+    assert torch.equal(target.cpu(), images[img_i].reshape(-1, 3)[sel])
+    tr.reference_rng = False
+    _, _, batch_rays, target = tr.sample_random_ray_batch(None, 0, [1], images, poses, i=0)   # inside the pre-crop phase
+    ro, rd, _ = ops.get_rays(H, W, tr.K, poses[1][:3, :4])
+    crop = torch.zeros(H, W, dtype=torch.bool)
+    crop[H // 2 - 15 : H // 2 + 15, W // 2 - 20 : W // 2 + 20] = True
+    allowed = {tuple(r) for r in rd.cpu()[crop.reshape(-1)].tolist()}
+    assert batch_rays.shape == (2, 128, 3) and all(tuple(r) in allowed for r in batch_rays[1].cpu().tolist())
+    assert len({tuple(r) for r in batch_rays[1].cpu().tolist()}) == 128   # without replacement
