@@ -226,6 +226,12 @@ int b200nerf_nerf_point_jvp(const float* const* params, const float* rays_o, con
 int b200nerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                        float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* The same update over a list of tensors in one launch.  d_table: DEVICE array of n_tensors records
+ * {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; uint64 numel} (40 bytes each); all tensors share
+ * lr / betas / eps / step. */
+int b200nerf_adam_step_multi(const void* d_table, int n_tensors, float lr, float beta1, float beta2, float eps, int step,
+                             float grad_scale, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------ */
 
 /* D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs (raw uint16), through the same shared-memory operand layout,

@@ -128,25 +128,27 @@ static int lin_wgrad(cudaStream_t st, int n, int M, int K, const float* dY, int 
   return sgemm(st, M, K, n, dY, 1, ldy, X, ldx, 1, dW + off, ldw, 0);
 }
 
-// db[m] = sum_n dY[n, m]
+// db[m] = sum_n dY[n, m]: 32 columns x 256 rows per block, partial sums added atomically into a zeroed db
 __global__ void colsum_kernel(const float* __restrict__ dY, int n, int M, int ldy, float* __restrict__ db) {
   const int m = blockIdx.x * 32 + (threadIdx.x & 31);
   const int part = threadIdx.x >> 5;  // 8 row groups
   __shared__ float red[8][33];
+  const int r0 = blockIdx.y * 256, r1 = min(n, r0 + 256);
   float s = 0.f;
   if (m < M)
-    for (int r = part; r < n; r += 8) s += dY[static_cast<size_t>(r) * ldy + m];
+    for (int r = r0 + part; r < r1; r += 8) s += dY[static_cast<size_t>(r) * ldy + m];
   red[part][threadIdx.x & 31] = s;
   __syncthreads();
   if (part == 0 && m < M) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-    db[m] = t;
+    atomicAdd(db + m, t);
   }
 }
 static int colsum(cudaStream_t st, const float* dY, int n, int M, int ldy, float* db) {
-  colsum_kernel<<<(M + 31) / 32, 256, 0, st>>>(dY, n, M, ldy, db);
+  CUDA_TRY(cudaMemsetAsync(db, 0, static_cast<size_t>(M) * sizeof(float), st));
+  colsum_kernel<<<dim3((M + 31) / 32, (n + 255) / 256), 256, 0, st>>>(dY, n, M, ldy, db);
   LAUNCH_CHECK();
   return 0;
 }
@@ -530,6 +532,39 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
   p[i] -= (lr / bc1) * (mi / denom);
 }
+// The same update over a list of tensors in ONE launch: blockIdx.y walks the tensors of the table.
+struct AdamEntry {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  unsigned long long n;
+};
+__global__ void adam_multi_kernel(const AdamEntry* __restrict__ table, float lr, float b1, float b2, float eps, float bc1,
+                                  float bc2_sqrt, float gscale) {
+  const AdamEntry e = table[blockIdx.y];
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < e.n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gi = e.g[i] * gscale;
+    const float mi = b1 * e.m[i] + (1.f - b1) * gi;
+    const float vi = b2 * e.v[i] + (1.f - b2) * gi * gi;
+    e.m[i] = mi;
+    e.v[i] = vi;
+    e.p[i] -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+/* d_table: device array of n_tensors {param, grad, exp_avg, exp_avg_sq, numel} records (5 x 8 bytes each) */
+extern "C" int b200nerf_adam_step_multi(const void* d_table, int n_tensors, float lr, float beta1, float beta2, float eps, int step,
+                                        float grad_scale, void* stream) {
+  if (n_tensors <= 0) return 0;
+  if (!d_table || step < 1) return b200_fail("b200nerf_adam_step_multi: bad arguments");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  adam_multi_kernel<<<dim3(64, n_tensors), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const AdamEntry*>(d_table), lr, beta1,
+                                                                                      beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int b200nerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                                   float beta2, float eps, int step, float grad_scale, void* stream) {
   if (n == 0) return 0;

@@ -15,7 +15,10 @@ from .. import ops
 from ..packing import PREC_FAST, PackedNeRF
 
 img2mse = lambda x, y: torch.mean((x - y) ** 2)  # noqa: E731  (run_nerf_helpers.py:9)
-mse2psnr = lambda x: -10.0 * torch.log(x) / torch.log(torch.tensor([10.0], device=x.device))  # noqa: E731
+# run_nerf_helpers.py:10 divides by torch.log(torch.Tensor([10.])) created on the fly: on a GPU that is a pageable
+# host->device copy, i.e. a stream synchronisation in the middle of every training step.  Same value, no copy:
+_LOG10 = float(torch.log(torch.tensor([10.0])))
+mse2psnr = lambda x: -10.0 * torch.log(x) / _LOG10  # noqa: E731
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)  # noqa: E731
 
 

@@ -7,6 +7,7 @@ data path and no CPU fallback (CPU tensors are rejected).
 from __future__ import annotations
 
 import ctypes as C
+import functools
 from typing import Optional, Tuple
 
 import torch
@@ -91,10 +92,17 @@ def depthnet_forward(pk: PackedDepthNet, rays_o, rays_d, radius=2.0, near=2.0, f
     return out
 
 
+@functools.lru_cache(maxsize=64)
+def _device_linspace(lo: float, hi: float, steps: int, device: str) -> torch.Tensor:
+    """torch.linspace evaluated on the CPU exactly as the reference does (so grids are bit-identical), uploaded once per
+    (range, length, device): a pageable host->device copy per call would synchronise the stream every step."""
+    return torch.linspace(lo, hi, steps=steps, device="cpu").to(device)
+
+
 def uniform_grid(std: float, n_samples: int, device) -> torch.Tensor:
     """The S-1 offsets of uniform placement; computed by torch.linspace exactly as the reference does
     (nerf_pytorch/utils.py:232) so that the depths are bit-identical."""
-    return torch.linspace(-std, std, steps=n_samples - 1, device="cpu").to(device)
+    return _device_linspace(-float(std), float(std), n_samples - 1, str(torch.device(device)))
 
 
 def place_samples(mean, n_samples: int, mode: str, std: float, noise: Optional[torch.Tensor] = None,
@@ -209,7 +217,7 @@ def coarse_z(near, far, n_rays: int, n_samples: int, lindisp: bool, t_rand: Opti
     """Stratified coarse depths [N,S] (trainers/Trainer.py:603-627)."""
     near, far = _dev(near, "near").reshape(-1), _dev(far, "far").reshape(-1)
     dev = near.device
-    t = torch.linspace(0.0, 1.0, steps=n_samples, device="cpu").to(dev)  # the reference's own t grid
+    t = _device_linspace(0.0, 1.0, n_samples, str(dev))  # the reference's own t grid
     tr = None if t_rand is None else _dev(t_rand, "t_rand")
     z = torch.empty(n_rays, n_samples, device=dev)
     with torch.cuda.device(dev):
@@ -220,7 +228,7 @@ def coarse_z(near, far, n_rays: int, n_samples: int, lindisp: bool, t_rand: Opti
 
 def _u_grid(u, n_samples, dev):
     if u is None:  # det=True: u = linspace(0, 1, N_samples) shared by all rays (run_nerf_helpers.py:258-260)
-        return torch.linspace(0.0, 1.0, steps=n_samples, device="cpu").to(dev), 0
+        return _device_linspace(0.0, 1.0, n_samples, str(torch.device(dev))), 0
     return _dev(u, "u"), 1
 
 

@@ -147,6 +147,7 @@ class Adam(torch.optim.Optimizer):
         L = _lib.lib()
         for group in self.param_groups:
             b1, b2 = group["betas"]
+            rows, steps, dev = [], set(), None
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -156,9 +157,35 @@ class Adam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
                 st["step"] += 1
-                g = p.grad.contiguous()
-                with torch.cuda.device(p.device):
-                    _lib.check(L.b200nerf_adam_step(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                                                    p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                                    int(st["step"]), float(grad_scale), _stream()))
+                steps.add(int(st["step"]))
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                rows.append((p, g, st))
+                dev = p.device
+            if not rows:
+                continue
+            with torch.cuda.device(dev):
+                if len(steps) == 1:
+                    # one launch for the whole group: a small pointer table travels to the device every step (the
+                    # gradient tensors are new objects after every backward)
+                    # pinned staging buffers, two in rotation: a buffer is rewritten only after its previous upload ran
+                    ring = self.__dict__.setdefault("_table_ring", [])
+                    if len(ring) < 2 or ring[0][0].shape[0] != len(rows):
+                        ring[:] = [[torch.empty(len(rows), 5, dtype=torch.int64).pin_memory(), None] for _ in range(2)]
+                    self._table_turn = (getattr(self, "_table_turn", 0) + 1) % 2
+                    host, ev = ring[self._table_turn]
+                    if ev is not None:
+                        ev.synchronize()
+                    host.view(-1).numpy()[:] = [x for p, g, st in rows for x in
+                                                (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())]
+                    table = host.to(dev, non_blocking=True)
+                    ring[self._table_turn][1] = torch.cuda.Event()
+                    ring[self._table_turn][1].record()
+                    _lib.check(L.b200nerf_adam_step_multi(table.data_ptr(), len(rows), float(group["lr"]), float(b1), float(b2),
+                                                          float(group["eps"]), steps.pop(), float(grad_scale), _stream()))
+                    self._keep = (table, [g for _, g, _ in rows])  # alive until the next step: the launch is asynchronous
+                else:
+                    for p, g, st in rows:
+                        _lib.check(L.b200nerf_adam_step(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                                                        p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                                        int(st["step"]), float(grad_scale), _stream()))
         return None

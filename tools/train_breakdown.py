@@ -1,0 +1,47 @@
+"""Where a training step's time goes: host enqueue time vs device time, and the per-kernel device time list."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from nerf_sampling_b200 import _lib, ops, training  # noqa: E402
+from nerf_sampling_b200.packing import PREC_FAST, PREC_SPLIT  # noqa: E402
+from nerf_sampling_b200.trainers import DepthNetTrainer  # noqa: E402
+
+n_total = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+dev = torch.device("cuda", 0)
+coarse, fine, dn = bench.build_models(dev, PREC_FAST)
+dn.precision = PREC_SPLIT
+tr = DepthNetTrainer(dataset_type="blender", basedir="/tmp", expname="x", no_batching=True, datadir="x", half_res=False,
+                     white_bkgd=True, device=str(dev), n_layers=10, layer_width=256, N_importance=128, N_samples=64,
+                     input_dims_embed=3, perturb=0.0)
+tr.H, tr.W, tr.K, tr.chunk = bench.H, bench.W, bench.intrinsics(), 32768
+kw = dict(network_fn=coarse, network_fine=fine, depth_network=dn, network_query_fn=None, N_samples=64, N_importance=128,
+          trainer=tr, white_bkgd=True, raw_noise_std=0.0, perturb=0.0, lindisp=True, ndc=False, near=2.0, far=6.0,
+          use_viewdirs=True, model_mode="train")
+ro, rd, _ = ops.get_rays(bench.H, bench.W, bench.intrinsics(), bench.pose_for_step(0), dev)
+sel = torch.randperm(ro.shape[0], generator=torch.Generator().manual_seed(0))[:n_total].to(dev)
+rays = (ro[sel].contiguous(), rd[sel].contiguous())
+target = torch.rand(n_total, 3, generator=torch.Generator().manual_seed(1)).to(dev)
+opt = training.Adam(list(dn.parameters()), lr=1e-4)
+for i in range(3):
+    tr.core_optimization_loop(opt, kw, rays, i, target)
+torch.cuda.synchronize()
+l0 = _lib.launch_count()
+t0 = time.perf_counter()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for i in range(10):
+    tr.core_optimization_loop(opt, kw, rays, 3 + i, target)
+e1.record()
+t_host = (time.perf_counter() - t0) / 10
+torch.cuda.synchronize()
+print("rays %d: host enqueue %.2f ms/step, device %.2f ms/step, library launches/step %d" % (
+    n_total, 1e3 * t_host, e0.elapsed_time(e1) / 10, (_lib.launch_count() - l0) // 10))
+with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+    tr.core_optimization_loop(opt, kw, rays, 20, target)
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
