@@ -8,6 +8,7 @@
 #include "../../include/b200nerf.h"
 #include "host_common.h"
 #include "mlp_chain.cuh"
+#include "mlp_exact.cuh"
 #include "mlp_fast.cuh"
 #include <cuda.h>
 
@@ -81,7 +82,228 @@ enum : uint32_t {
   NERF_AUX_FLOATS = 3080
 };
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+
+
+// ------------------------------------------------------------------------------------------- pipelined exact kernel (mlp_exact.cuh)
+// A program = the layer steps the kernel walks + where each operand K16 block finds its weights.  The same description
+// drives packing and launching, so the stream order cannot diverge from the issue order.
+struct XSeg {            // operand blocks [kb, kb+nblk) multiply W[:, col0 : col0+K] (zero beyond K)
+  int kb, nblk;
+  const float* W;
+  int ldw, col0, K;
+};
+struct XLayer {
+  exact::XStep st;
+  int n_out;             // 256 or 128
+  XSeg segs[2];
+  int n_segs;
+};
+struct XProgram {
+  std::vector<XLayer> layers;
+  int stages_per_tile() const {
+    int n = 0;
+    for (const XLayer& l : layers) n += l.st.halves * (l.st.n1a + l.st.n1b + l.st.n2) / 2;
+    return n;
+  }
+  size_t pack_bytes() const { return static_cast<size_t>(stages_per_tile()) * 2 * exact::STAGE_BYTES; }
+};
+
+static exact::XStep xstep(int n1a, int kb1a, int n1b, int kb1b, int n2, int kb2, int halves, int epi, int act, uint32_t bias_off) {
+  exact::XStep s;
+  memset(&s, 0, sizeof(s));
+  s.n1a = n1a; s.kb1a = kb1a; s.n1b = n1b; s.kb1b = kb1b; s.n2 = n2; s.kb2 = kb2;
+  s.halves = halves; s.epi = epi; s.act = act; s.bias_off = static_cast<uint16_t>(bias_off);
+  return s;
+}
+
+// NeRF (run_nerf_helpers.py:109-134); t = the 24 tensors in state_dict order (may be null when only the steps are needed)
+static XProgram nerf_xprogram(const float* const* t) {
+  auto T = [&](int i) { return t ? t[i] : nullptr; };
+  XProgram pg;
+  auto add = [&](exact::XStep st, int n_out, XSeg a, XSeg b, int n_segs) {
+    XLayer l;
+    l.st = st; l.n_out = n_out; l.segs[0] = a; l.segs[1] = b; l.n_segs = n_segs;
+    pg.layers.push_back(l);
+  };
+  const XSeg none = {0, 0, nullptr, 0, 0, 0};
+  {
+    exact::XStep s0 = xstep(4, exact::ENC_KB, 0, 0, 0, 0, 2, exact::EPI_STORE, exact::ACT_RELU, NERF_B0);
+    s0.wait_p = 1;
+    add(s0, 256, XSeg{exact::ENC_KB, 4, T(0), 63, 0, 63}, none, 1);
+  }
+  for (int i = 1; i <= 7; ++i) {
+    if (i == 5) {
+      exact::XStep s5 = xstep(8, 0, 4, exact::ENC_KB, 8, 8, 2, exact::EPI_STORE, exact::ACT_RELU, NERF_B0 + 256 * 5);
+      s5.sig_p = 1;   // gamma(pts) is not read after the first range of the skip layer
+      add(s5, 256, XSeg{0, 16, T(10), 319, 63, 256}, XSeg{exact::ENC_KB, 4, T(10), 319, 0, 63}, 2);
+    } else {
+      add(xstep(8, 0, 0, 0, 8, 8, 2, i == 7 ? exact::EPI_STORE_ALPHA : exact::EPI_STORE, exact::ACT_RELU, NERF_B0 + 256 * i), 256,
+          XSeg{0, 16, T(2 * i), 256, 0, 256}, none, 1);
+    }
+  }
+  add(xstep(8, 0, 0, 0, 8, 8, 2, exact::EPI_STORE, exact::ACT_NONE, NERF_BF), 256, XSeg{0, 16, T(18), 256, 0, 256}, none, 1);
+  {
+    exact::XStep s9 = xstep(8, 0, 2, exact::VIEW_KB, 8, 8, 1, exact::EPI_NERF_OUT, exact::ACT_RELU, NERF_BV);
+    s9.wait_v = 1;
+    s9.sig_v = 1;
+    add(s9, 128, XSeg{0, 16, T(16), 283, 0, 256}, XSeg{exact::VIEW_KB, 2, T(16), 283, 256, 27}, 2);
+  }
+  return pg;
+}
+
+// folded DepthNet: n_hidden + 1 LeakyReLU layers of 256x256 (see b200nerf_depthnet_pack)
+static XProgram depthnet_xprogram(const float* w0, const float* const* hidden, int n_hidden) {
+  XProgram pg;
+  const XSeg none = {0, 0, nullptr, 0, 0, 0};
+  for (int i = 0; i <= n_hidden; ++i) {
+    XLayer l;
+    l.st = xstep(8, 0, 0, 0, 8, 8, 2, i == n_hidden ? exact::EPI_DEPTH_OUT : exact::EPI_STORE, exact::ACT_LEAKY, 256u * i);
+    if (i == 0) {
+      l.st.wait_p = 1;   // enc(o) | enc(d) in columns 0..127
+      l.st.wait_v = 2;   // enc(hits) in columns 128..255
+    }
+    if (i == n_hidden) {
+      l.st.sig_p = 1;
+      l.st.sig_v = 2;
+    }
+    l.n_out = 256;
+    l.segs[0] = XSeg{0, 16, i == 0 ? w0 : (hidden ? hidden[2 * (i - 1)] : nullptr), 256, 0, 256};
+    l.segs[1] = none;
+    l.n_segs = 1;
+    pg.layers.push_back(l);
+  }
+  return pg;
+}
+
+// pack layout [rank][stage][8 KB]; stage = two K16 blocks of one (layer, output half, K range) in issue order, each block =
+// hi piece | lo piece, one piece = this rank's 64 rows of the 128-row half as [2 k chunks][8 row groups][8 rows][8 k] bf16
+static int pack_xprogram(const XProgram& pg, uint8_t* out) {
+  const size_t per_rank = pg.pack_bytes() / 2;
+  for (int r = 0; r < 2; ++r) {
+    uint8_t* o = out + r * per_rank;
+    for (const XLayer& l : pg.layers) {
+      auto emit_block = [&](int half, int kb) {
+        const XSeg* sg = nullptr;
+        for (int i = 0; i < l.n_segs; ++i)
+          if (kb >= l.segs[i].kb && kb < l.segs[i].kb + l.segs[i].nblk) sg = &l.segs[i];
+        uint16_t* hi = reinterpret_cast<uint16_t*>(o);
+        uint16_t* lo = reinterpret_cast<uint16_t*>(o + 2048);
+        for (int kc = 0; kc < 2; ++kc)
+          for (int n = 0; n < 64; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int k = (kb - (sg ? sg->kb : 0)) * 16 + kc * 8 + e;
+              const int row = half * 128 + r * 64 + n;
+              float w = 0.f;
+              if (sg && sg->W && k < sg->K && row < l.n_out) w = sg->W[static_cast<size_t>(row) * sg->ldw + sg->col0 + k];
+              const size_t idx = static_cast<size_t>(kc) * 64 * 8 + static_cast<size_t>(n >> 3) * 64 + (n & 7) * 8 + e;
+              const uint16_t h = f2bf(w);
+              hi[idx] = h;
+              lo[idx] = f2bf(w - bf2f(h));
+            }
+        o += 4096;
+      };
+      auto emit_range = [&](int half, int kb, int nblk) {
+        for (int k = 0; k < nblk; ++k) emit_block(half, kb + k);
+      };
+      for (int half = 0; half < l.st.halves; ++half) {
+        emit_range(half, l.st.kb1a, l.st.n1a);
+        emit_range(half, l.st.kb1b, l.st.n1b);
+      }
+      for (int half = 0; half < l.st.halves; ++half) emit_range(half, l.st.kb2, l.st.n2);
+    }
+    if (static_cast<size_t>(o - (out + r * per_rank)) != per_rank) return fail("exact pack: internal size mismatch");
+  }
+  return 0;
+}
+
+static int make_exact_tmap(const void* wpack, size_t bytes, exact::TMap* out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t gdim[2] = {256, bytes / 512};
+  const cuuint64_t gstride[1] = {512};
+  const cuuint32_t box[2] = {256, 16};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(wpack), gdim,
+                         gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r));
+  return 0;
+}
+
+template <int INPUT>
+static int launch_exact(exact::ExactParams& p, const XProgram& pg, const void* wpack, cudaStream_t st) {
+  static int grid_cap = 0;
+  constexpr int smem = exact::smem_bytes();
+  auto kern = exact::mlp_exact_kernel<INPUT>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = exact::NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(exact::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (grid_cap == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int sms = sm_count();
+    if (sms <= 0) return fail("no CUDA device");
+    int cap = (sms / exact::NCTA) * exact::NCTA;
+    cfg.gridDim = dim3(cap);
+    int n_clusters = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg));
+    if (n_clusters <= 0) return fail("mlp_exact_kernel: no resident cluster fits");
+    if (n_clusters * exact::NCTA < cap) cap = n_clusters * exact::NCTA;
+    grid_cap = cap;
+  }
+  if (static_cast<int>(pg.layers.size()) > exact::MAX_STEPS) return fail("mlp_exact_kernel: too many layers");
+  p.n_steps = static_cast<int>(pg.layers.size());
+  for (int i = 0; i < p.n_steps; ++i) p.steps[i] = pg.layers[i].st;
+  p.stages_per_tile = pg.stages_per_tile();
+  const int tiles = (p.n_rows + exact::TILE_M - 1) / exact::TILE_M;
+  int grid = ((tiles + exact::NCTA - 1) / exact::NCTA) * exact::NCTA;
+  if (grid > grid_cap) grid = grid_cap;
+  cfg.gridDim = dim3(grid);
+  exact::TMap tm;
+  const int rc = make_exact_tmap(wpack, pg.pack_bytes(), &tm);
+  if (rc) return rc;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, tm));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+
+// SPLIT precision runs on the pipelined exact kernel (mlp_exact.cuh) and its pack layout; B200NERF_EXACT_LEGACY=1 keeps the
+// sequential kernel (mlp_chain.cuh), which also serves the legacy PREC_BF16 mode.
+static bool use_pipelined_exact() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200NERF_EXACT_LEGACY");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 extern "C" size_t b200nerf_nerf_wpack_bytes(int prec) {
+  if (prec == B200NERF_PREC_SPLIT && use_pipelined_exact()) return nerf_xprogram(nullptr).pack_bytes();
   // K16 slabs: skip part 4 + L0 4 + 7 trunk layers x 16 + feature 16 (N=256) and 18 view slabs (N=128)
   const size_t per256 = prec == B200NERF_PREC_SPLIT ? 16384 : 8192;
   return (4 + 4 + 7 * 16 + 16) * per256 + 18 * (per256 / 2);
@@ -99,16 +321,23 @@ extern "C" int b200nerf_nerf_pack(const float* const* t, int prec, void* h_wpack
     B[i] = t[2 * i + 1];
   }
   const float *Wv = t[16], *Bv = t[17], *Wf = t[18], *Bf = t[19], *Wa = t[20], *Ba = t[21], *Wr = t[22], *Br = t[23];
-  o = pack_linear(W[5], 256, 63, 319, 0, 64, split, o);   // skip-connection part of pts_linears.5 (input_pts columns)
-  o = pack_linear(W[0], 256, 63, 63, 0, 64, split, o);    // pts_linears.0
-  for (int i = 1; i <= 4; ++i) o = pack_linear(W[i], 256, 256, 256, 0, 256, split, o);
-  o = pack_linear(W[5], 256, 256, 319, 63, 256, split, o);  // hidden part of pts_linears.5
-  o = pack_linear(W[6], 256, 256, 256, 0, 256, split, o);
-  o = pack_linear(W[7], 256, 256, 256, 0, 256, split, o);
-  o = pack_linear(Wf, 256, 256, 256, 0, 256, split, o);
-  o = pack_linear(Wv, 128, 283, 283, 0, 288, split, o);   // [feature | view encoding] -> 128
-  if (static_cast<size_t>(o - static_cast<uint8_t*>(h_wpack)) != b200nerf_nerf_wpack_bytes(prec))
-    return fail("b200nerf_nerf_pack: internal size mismatch");
+  const bool pipelined = split && use_pipelined_exact();
+  if (pipelined) {
+    const int rc = pack_xprogram(nerf_xprogram(t), o);
+    if (rc) return rc;
+  }
+  if (!pipelined) {
+    o = pack_linear(W[5], 256, 63, 319, 0, 64, split, o);   // skip-connection part of pts_linears.5 (input_pts columns)
+    o = pack_linear(W[0], 256, 63, 63, 0, 64, split, o);    // pts_linears.0
+    for (int i = 1; i <= 4; ++i) o = pack_linear(W[i], 256, 256, 256, 0, 256, split, o);
+    o = pack_linear(W[5], 256, 256, 319, 63, 256, split, o);  // hidden part of pts_linears.5
+    o = pack_linear(W[6], 256, 256, 256, 0, 256, split, o);
+    o = pack_linear(W[7], 256, 256, 256, 0, 256, split, o);
+    o = pack_linear(Wf, 256, 256, 256, 0, 256, split, o);
+    o = pack_linear(Wv, 128, 283, 283, 0, 288, split, o);   // [feature | view encoding] -> 128
+    if (static_cast<size_t>(o - static_cast<uint8_t*>(h_wpack)) != b200nerf_nerf_wpack_bytes(prec))
+      return fail("b200nerf_nerf_pack: internal size mismatch");
+  }
   memset(h_aux, 0, NERF_AUX_FLOATS * sizeof(float));
   for (int i = 0; i < 8; ++i) memcpy(h_aux + NERF_B0 + 256 * i, B[i], 256 * sizeof(float));
   memcpy(h_aux + NERF_BF, Bf, 256 * sizeof(float));
@@ -211,7 +440,12 @@ extern "C" int b200nerf_nerf_pack_fast(const float* const* t, int prec, void* h_
   return 0;
 }
 
+// the pipelined kernel keeps all biases + the head in its 3080-float shared-memory block: up to 10 hidden layers
+static bool depthnet_pipelined(int n_hidden, int prec) {
+  return prec == B200NERF_PREC_SPLIT && use_pipelined_exact() && n_hidden <= 10;
+}
 extern "C" size_t b200nerf_depthnet_wpack_bytes(int n_hidden, int prec) {
+  if (depthnet_pipelined(n_hidden, prec)) return depthnet_xprogram(nullptr, nullptr, n_hidden).pack_bytes();
   return static_cast<size_t>(n_hidden + 1) * 16 * (prec == B200NERF_PREC_SPLIT ? 16384 : 8192);
 }
 extern "C" size_t b200nerf_depthnet_aux_floats(int n_hidden) { return static_cast<size_t>(n_hidden + 1) * 256 + 256 + 4; }
@@ -223,10 +457,16 @@ extern "C" int b200nerf_depthnet_pack(const float* h_w0, const float* h_b0, cons
   if (n_hidden < 0 || n_hidden + 1 > MAX_STEPS) return fail("b200nerf_depthnet_pack: n_hidden=%d out of range", n_hidden);
   const bool split = prec == B200NERF_PREC_SPLIT;
   uint8_t* o = static_cast<uint8_t*>(h_wpack);
-  o = pack_linear(h_w0, 256, 256, 256, 0, 256, split, o);
+  const bool pipelined = depthnet_pipelined(n_hidden, prec);
+  if (pipelined) {
+    const int rc = pack_xprogram(depthnet_xprogram(h_w0, h_hidden, n_hidden), o);
+    if (rc) return rc;
+  } else {
+    o = pack_linear(h_w0, 256, 256, 256, 0, 256, split, o);
+  }
   memcpy(h_aux, h_b0, 256 * sizeof(float));
   for (int i = 0; i < n_hidden; ++i) {
-    o = pack_linear(h_hidden[2 * i], 256, 256, 256, 0, 256, split, o);
+    if (!pipelined) o = pack_linear(h_hidden[2 * i], 256, 256, 256, 0, 256, split, o);
     memcpy(h_aux + 256 * (i + 1), h_hidden[2 * i + 1], 256 * sizeof(float));
   }
   memcpy(h_aux + 256 * (n_hidden + 1), h_head_w, 256 * sizeof(float));
@@ -657,6 +897,26 @@ static Step make_step(int a_begin, int n_k16, int n, int acc_col, int accumulate
 static int nerf_chain_launch(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,
                              const float* viewdirs, const float* z, const float* pts, int n_rays, int S, float* out_raw,
                              const int* row_index, const int* n_rows_dev, int list_cap, cudaStream_t st) {
+  if (prec == B200NERF_PREC_SPLIT && use_pipelined_exact()) {
+    exact::ExactParams xp;
+    memset(&xp, 0, sizeof(xp));
+    xp.aux = aux;
+    xp.n_rows = row_index ? list_cap : n_rays * S;
+    xp.S = S;
+    xp.rays_o = rays_o;
+    xp.rays_d = rays_d;
+    xp.viewdirs = viewdirs;
+    xp.z = z;
+    xp.pts = pts;
+    xp.out = out_raw;
+    xp.row_index = row_index;
+    xp.n_rows_dev = n_rows_dev;
+    xp.head_w_off = NERF_WA;
+    xp.head_b_off = NERF_BA;
+    xp.rgb_w_off = NERF_WR;
+    xp.rgb_b_off = NERF_BR;
+    return launch_exact<exact::IN_NERF>(xp, nerf_xprogram(nullptr), wpack, st);
+  }
   ChainParams p;
   memset(&p, 0, sizeof(p));
   p.wpack = static_cast<const uint8_t*>(wpack);
@@ -709,6 +969,22 @@ extern "C" int b200nerf_depthnet_fwd(const void* wpack, const float* aux, int n_
   if (n_rays == 0) return 0;
   if (!wpack || !aux || !rays_o || !rays_d || !out_z) return fail("b200nerf_depthnet_fwd: null argument");
   if (n_hidden < 0 || n_hidden + 1 > MAX_STEPS) return fail("b200nerf_depthnet_fwd: n_hidden=%d out of range", n_hidden);
+  if (depthnet_pipelined(n_hidden, prec)) {
+    exact::ExactParams xp;
+    memset(&xp, 0, sizeof(xp));
+    xp.aux = aux;
+    xp.n_rows = n_rays;
+    xp.S = 1;
+    xp.rays_o = rays_o;
+    xp.rays_d = rays_d;
+    xp.out = out_z;
+    xp.head_w_off = 256 * (n_hidden + 1);
+    xp.head_b_off = 256 * (n_hidden + 2);
+    xp.radius = radius;
+    xp.near = near_;
+    xp.far = far_;
+    return launch_exact<exact::IN_DEPTHNET>(xp, depthnet_xprogram(nullptr, nullptr, n_hidden), wpack, static_cast<cudaStream_t>(stream));
+  }
   ChainParams p;
   memset(&p, 0, sizeof(p));
   p.wpack = static_cast<const uint8_t*>(wpack);
@@ -732,21 +1008,6 @@ extern "C" int b200nerf_depthnet_fwd(const void* wpack, const float* aux, int n_
 
 
 // ------------------------------------------------------------------------------------------- fast NeRF MLP
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 // The weight pack viewed as [bytes/512, 256] 16-bit elements; a box of `rows` rows is a contiguous rows*512-byte piece.
 static int make_piece_tmap(const void* wpack, int rows, fast::TMap* out) {
   EncodeTiledFn enc = encode_tiled_fn();

@@ -55,7 +55,91 @@ def decode_slabs(buf: torch.Tensor, n: int, kpad: int, split: bool):
     return out_hi, out_lo
 
 
-@pytest.mark.parametrize("prec", [1, 0])
+def _piece(buf, n_rows):
+    """[2 k chunks][n_rows/8 groups][8 rows][8 k] 16-bit piece -> [n_rows, 16]."""
+    return buf.view(2, n_rows // 8, 8, 8).permute(1, 2, 0, 3).reshape(n_rows, 16)
+
+
+def test_nerf_pack_layout_pipelined_exact(lib, oracle_models):
+    """b200nerf_nerf_pack(PREC_SPLIT): [rank][layer][A first, B first, A second, B second][K16 block][hi piece | lo piece],
+    one piece = the rank's 64 rows of a 128-row output half (csrc/mlp_exact.cuh)."""
+    from nerf_sampling_b200.packing import NERF_KEYS
+
+    _, fine, _ = oracle_models
+    host = [fine[k].contiguous() for k in NERF_KEYS]
+    arr = (C.c_void_p * 24)(*[t.data_ptr() for t in host])
+    wpack = torch.zeros(lib.b200nerf_nerf_wpack_bytes(1), dtype=torch.uint8)
+    aux = torch.zeros(lib.b200nerf_nerf_aux_floats(), dtype=torch.float32)
+    assert lib.b200nerf_nerf_pack(C.cast(arr, C.c_void_p), 1, wpack.data_ptr(), aux.data_ptr()) == 0
+    u = wpack.view(torch.bfloat16)
+    w5, wv = fine["pts_linears.5.weight"], fine["views_linears.0.weight"]
+    # (weight as [n_out, K] over the operand blocks, operand block -> column block) per layer
+    def layer(n_out, first, second, cols):
+        return dict(n_out=n_out, first=first, second=second, cols=cols)
+
+    def pad(w, k):
+        out = torch.zeros(w.shape[0], k)
+        out[:, : w.shape[1]] = w
+        return out
+
+    enc, view = list(range(16, 20)), [20, 21]
+    layers = [layer(256, enc, [], {16: pad(fine["pts_linears.0.weight"], 64)})]
+    for i in (1, 2, 3, 4):
+        layers.append(layer(256, list(range(8)), list(range(8, 16)), {0: fine[f"pts_linears.{i}.weight"]}))
+    layers.append(layer(256, list(range(8)) + enc, list(range(8, 16)), {0: w5[:, 63:], 16: pad(w5[:, :63], 64)}))
+    for name in ("pts_linears.6.weight", "pts_linears.7.weight", "feature_linear.weight"):
+        layers.append(layer(256, list(range(8)), list(range(8, 16)), {0: fine[name]}))
+    layers.append(layer(128, list(range(8)) + view, list(range(8, 16)), {0: wv[:, :256], 20: pad(wv[:, 256:], 32)}))
+    per_rank = wpack.numel() // 2 // 2   # bf16 elements per rank
+    for r in range(2):
+        off = r * per_rank
+        for L in layers:
+            halves = L["n_out"] // 128
+            for rng in (L["first"], L["second"]):
+                for half in range(halves):
+                    for kb in rng:
+                        base = max(b for b in L["cols"] if b <= kb)
+                        w = L["cols"][base][half * 128 + r * 64 : half * 128 + r * 64 + 64, (kb - base) * 16 : (kb - base) * 16 + 16]
+                        rh, rl = bf16_split(w.contiguous())
+                        assert torch.equal(_piece(u[off : off + 1024], 64), rh), (r, kb, half)
+                        assert torch.equal(_piece(u[off + 1024 : off + 2048], 64), rl), (r, kb, half)
+                        off += 2048
+        assert off == (r + 1) * per_rank
+    assert torch.equal(aux[2432:2688], fine["alpha_linear.weight"][0])
+
+
+def test_nerf_pack_fast_layout(lib, oracle_models):
+    """b200nerf_nerf_pack_fast: [step][rank][K16 block][piece], piece = the rank's half of the output rows, fp16."""
+    from nerf_sampling_b200.packing import NERF_KEYS
+
+    _, fine, _ = oracle_models
+    host = [fine[k].contiguous() for k in NERF_KEYS]
+    arr = (C.c_void_p * 24)(*[t.data_ptr() for t in host])
+    wpack = torch.zeros(lib.b200nerf_nerf_fast_wpack_bytes(), dtype=torch.uint8)
+    assert lib.b200nerf_nerf_pack_fast(C.cast(arr, C.c_void_p), 2, wpack.data_ptr()) == 0
+    u = wpack.view(torch.float16)
+    w5, wv = fine["pts_linears.5.weight"], fine["views_linears.0.weight"]
+
+    def pad(w, k):
+        out = torch.zeros(w.shape[0], k)
+        out[:, : w.shape[1]] = w
+        return out
+
+    steps = [pad(fine["pts_linears.0.weight"], 64)] + [fine[f"pts_linears.{i}.weight"] for i in (1, 2, 3, 4)]
+    steps += [torch.cat([w5[:, 63:], pad(w5[:, :63], 64)], 1), fine["pts_linears.6.weight"], fine["pts_linears.7.weight"],
+              fine["feature_linear.weight"], torch.cat([wv[:, :256], pad(wv[:, 256:], 32), torch.zeros(128, 32)], 1)]
+    off = 0
+    for w in steps:
+        half = w.shape[0] // 2
+        for r in range(2):
+            for kb in range(w.shape[1] // 16):
+                want = w[r * half : (r + 1) * half, kb * 16 : kb * 16 + 16].to(torch.float16)
+                assert torch.equal(_piece(u[off : off + half * 16], half), want)
+                off += half * 16
+    assert off == u.numel()
+
+
+@pytest.mark.parametrize("prec", [0])
 def test_nerf_pack_layout(lib, oracle_models, prec):
     from nerf_sampling_b200.packing import NERF_KEYS
 
@@ -140,11 +224,26 @@ def test_depthnet_pack_roundtrip(lib):
     dn = O.init_depthnet([256] * 3, [256] * 3)
     pk = PackedDepthNet(dn, "cpu", prec=1)
     assert pk.n_hidden == 2
-    assert pk.wpack.numel() == 3 * 16 * 16384
-    hi, lo = decode_slabs(pk.wpack[: 16 * 16384], 256, 256, True)
+    # pipelined exact layout: 3 layers x 32 stages x 8 KB per rank, two ranks
+    assert pk.wpack.numel() == 2 * 3 * 16 * 8192   # two ranks x 3 layers x 16 ring stages of 8 KB
+    u = pk.wpack.view(torch.bfloat16)
     w0 = pk.folded[0]
-    assert torch.equal(hi, bf16_split(w0)[0]) and torch.equal(lo, bf16_split(w0)[1])
+    per_rank = u.numel() // 2
+    for r in range(2):
+        off = r * per_rank   # layer 0: A first (blocks 0..7), B first, A second (8..15), B second
+        for rng in (range(0, 8), range(8, 16)):
+            for half in range(2):
+                for kb in rng:
+                    w = w0[half * 128 + r * 64 : half * 128 + r * 64 + 64, kb * 16 : kb * 16 + 16].contiguous()
+                    assert torch.equal(_piece(u[off : off + 1024], 64), bf16_split(w)[0])
+                    assert torch.equal(_piece(u[off + 1024 : off + 2048], 64), bf16_split(w)[1])
+                    off += 2048
     assert torch.equal(pk.aux[768:1024], pk.folded[3])  # head weights after 3 bias rows
+    # the legacy (sequential kernel) slab layout is still produced for PREC_BF16
+    pk0 = PackedDepthNet(dn, "cpu", prec=0)
+    assert pk0.wpack.numel() == 3 * 16 * 8192
+    hi, _ = decode_slabs(pk0.wpack[: 16 * 8192], 256, 256, False)
+    assert torch.equal(hi, bf16_split(w0)[0])
 
 
 # --------------------------------------------------------------------------------------------- module shells
