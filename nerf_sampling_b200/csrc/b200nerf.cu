@@ -275,6 +275,15 @@ static int launch_exact(exact::ExactParams& p, const XProgram& pg, const void* w
     grid_cap = cap;
   }
   if (static_cast<int>(pg.layers.size()) > exact::MAX_STEPS) return fail("mlp_exact_kernel: too many layers");
+  if (INPUT == exact::IN_DEPTHNET) {
+    // per-CTA staging image of the next tile's encoded rays (128 KB per CTA, ~19 MB): library-owned, allocated once per device
+    static uint8_t* scratch[64] = {nullptr};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail("mlp_exact_kernel: device index %d out of range", dev);
+    if (!scratch[dev]) CUDA_TRY(cudaMalloc(&scratch[dev], static_cast<size_t>(grid_cap) * 2 * 32 * exact::KC_STRIDE));
+    p.scratch = scratch[dev];
+  }
   p.n_steps = static_cast<int>(pg.layers.size());
   for (int i = 0; i < p.n_steps; ++i) p.steps[i] = pg.layers[i].st;
   p.stages_per_tile = pg.stages_per_tile();

@@ -82,6 +82,7 @@ struct ExactParams {
   float* out;             // raw [rows,4] (NeRF) or z [rows] (DepthNet)
   const int* row_index;   // NeRF, optional: row i evaluates sample point row_index[i] and writes it in place
   const int* n_rows_dev;  // optional: actual row count on the device
+  uint8_t* scratch;       // DepthNet: per-CTA staging image of the next tile's encoded input (2 planes x 64 KB)
   uint32_t head_w_off, head_b_off;   // sigma head (NeRF) / depth head (DepthNet): 256 weights + bias
   uint32_t rgb_w_off, rgb_b_off;     // rgb head [3,128] + bias
   float radius, near, far;
@@ -95,6 +96,7 @@ struct __align__(16) Tail {
   uint64_t tmem_free_b;     // half B's accumulator has been read (its stores may still be in flight)
   uint64_t ready_p, ready_v;
   uint64_t free_p, free_v;
+  uint64_t in_full[2];      // DepthNet: the staged input halves have landed in the operand planes (TMA bytes)
   uint32_t tmem_base;
   uint32_t pad[3];
   float head_part[4][TILE_M];     // N = 1 head: partial sums per (half, column quarter)
@@ -143,6 +145,38 @@ __device__ __forceinline__ void encode_store(const float (&x)[3], uint8_t* dst) 
       else v[i] = 0.f;
     }
     store_split8(dst + ch * KC_STRIDE, v);
+  }
+}
+
+// the same encoding written to a staging image whose lo plane sits `lo_off` bytes after the hi plane
+template <int NF, int NCHUNK>
+__device__ __forceinline__ void encode_store_img(const float (&x)[3], uint8_t* dst, int lo_off) {
+  constexpr int NCOL = 3 + 6 * NF;
+  float sn[NF][3], cs[NF][3];
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+    const float f = static_cast<float>(1 << j);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) sincosf(x[t] * f, &sn[j][t], &cs[j][t]);
+  }
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int cc = ch * 8 + 2 * i + e;
+        if (cc < 3) v[e] = x[cc];
+        else if (cc < NCOL) v[e] = ((cc - 3) % 6) < 3 ? sn[(cc - 3) / 6][(cc - 3) % 6] : cs[(cc - 3) / 6][(cc - 3) % 6 - 3];
+        else v[e] = 0.f;
+      }
+      h[i] = pack_bf16x2(v[0], v[1]);
+      l[i] = pack_bf16x2(v[0] - __uint_as_float(h[i] << 16), v[1] - __uint_as_float(h[i] & 0xffff0000u));
+    }
+    *reinterpret_cast<uint4*>(dst + ch * KC_STRIDE) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(dst + ch * KC_STRIDE + lo_off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -223,8 +257,10 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
       mbar_init(&tail->a_ready[i], EPI_WARPS * NCTA);
     }
     mbar_init(&tail->tmem_free_b, EPI_WARPS * NCTA);
-    mbar_init(&tail->ready_p, PRO_WARPS * NCTA);
-    mbar_init(&tail->ready_v, PRO_WARPS * NCTA);
+    mbar_init(&tail->ready_p, (INPUT == IN_DEPTHNET ? 1 : PRO_WARPS) * NCTA);
+    mbar_init(&tail->ready_v, (INPUT == IN_DEPTHNET ? 1 : PRO_WARPS) * NCTA);
+    mbar_init(&tail->in_full[0], 1);
+    mbar_init(&tail->in_full[1], 1);
     mbar_init(&tail->free_p, 1);
     mbar_init(&tail->free_v, 1);
     fence_mbar_init();
@@ -411,7 +447,11 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(rv_bar);
       } else {
-        // DepthNet: enc(o) | enc(d) -> blocks 0..7 (part 1), enc(hit_near) | enc(hit_far) -> blocks 8..15 (part 2)
+        // DepthNet: 120 accurate sincosf per ray are far too slow to sit between two tiles, so the encoders work one
+        // tile AHEAD into a per-CTA staging image in global memory (L2-resident, already in the operand layout); when the
+        // previous tile releases the operand columns, one lane pulls the image in with two bulk TMA copies per half.
+        //   part 1 = enc(o) | enc(d) -> K chunks 0..15, part 2 = enc(hit_near) | enc(hit_far) -> K chunks 16..31
+        uint8_t* stage_img = p.scratch + static_cast<size_t>(blockIdx.x) * (2 * 32 * KC_STRIDE);   // hi 64 KB | lo 64 KB
         float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
         if (valid) {
 #pragma unroll
@@ -420,15 +460,6 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
             d[t] = __ldg(p.rays_d + static_cast<size_t>(lrow) * 3 + t);
           }
         }
-        if (u > 0) {
-          mbar_wait_lean(free_p_addr, (u - 1) & 1u);    // the previous tile's last layer has read columns 0..127
-          tc_fence_after();
-        }
-        encode_store<10, 8>(o, act + row_off);
-        encode_store<10, 8>(d, act + 8 * KC_STRIDE + row_off);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(rp_bar);
         // ray / sphere(0, radius) intersection, op order of nerf_pytorch/utils.py:159-217 (NaN when the ray misses)
         const float dot_do = __fadd_rn(__fadd_rn(__fmul_rn(d[0], o[0]), __fmul_rn(d[1], o[1])), __fmul_rn(d[2], o[2]));
         const float b = __fmul_rn(2.f, dot_do);
@@ -445,15 +476,30 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
           p0[t] = __fadd_rn(o[t], __fmul_rn(t0, d[t]));
           p1[t] = __fadd_rn(o[t], __fmul_rn(t1, d[t]));
         }
-        if (u > 0) {
-          mbar_wait_lean(free_v_addr, (u - 1) & 1u);    // ... and columns 128..255
-          tc_fence_after();
+        encode_store_img<10, 8>(o, stage_img + row_off, 32 * KC_STRIDE);
+        encode_store_img<10, 8>(d, stage_img + 8 * KC_STRIDE + row_off, 32 * KC_STRIDE);
+        encode_store_img<10, 8>(p0, stage_img + 16 * KC_STRIDE + row_off, 32 * KC_STRIDE);
+        encode_store_img<10, 8>(p1, stage_img + 24 * KC_STRIDE + row_off, 32 * KC_STRIDE);
+        __threadfence();
+        fence_proxy_async_all();                       // generic-proxy global writes -> visible to the bulk copy engine
+        named_bar_sync(6, PRO_WARPS * 32);
+        if (warp == PRO_WARP0 && lane == 0) {
+          const uint32_t in_full_addr = tail_addr + offsetof(Tail, in_full);
+          constexpr uint32_t HALF = 16 * KC_STRIDE;     // 32 KB: K chunks 0..15 (or 16..31) of one plane
+          if (u > 0) mbar_wait_lean(free_p_addr, (u - 1) & 1u);    // the previous tile's last layer has read columns 0..127
+          mbar_arrive_expect_tx(&tail->in_full[0], 2 * HALF);
+          tma_load_1d(act, stage_img, HALF, &tail->in_full[0]);
+          tma_load_1d(act + PLANE_BYTES, stage_img + 32 * KC_STRIDE, HALF, &tail->in_full[0]);
+          mbar_wait_lean(in_full_addr, u & 1u);
+          mbar_arrive_remote(rp_bar);
+          if (u > 0) mbar_wait_lean(free_v_addr, (u - 1) & 1u);    // ... and columns 128..255
+          mbar_arrive_expect_tx(&tail->in_full[1], 2 * HALF);
+          tma_load_1d(act + HALF, stage_img + HALF, HALF, &tail->in_full[1]);
+          tma_load_1d(act + PLANE_BYTES + HALF, stage_img + 32 * KC_STRIDE + HALF, HALF, &tail->in_full[1]);
+          mbar_wait_lean(in_full_addr + 8u, u & 1u);
+          mbar_arrive_remote(rv_bar);
         }
-        encode_store<10, 8>(p0, act + 16 * KC_STRIDE + row_off);
-        encode_store<10, 8>(p1, act + 24 * KC_STRIDE + row_off);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(rv_bar);
+        named_bar_sync(6, PRO_WARPS * 32);               // the image is free again
       }
     }
   } else if (warp >= EPI_WARP0) {
