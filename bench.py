@@ -5,8 +5,8 @@
     python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU (oracle port)
 
 One step = one 800x800 synthetic Blender-style view per GPU (640,000 rays): DepthNet -> 64 uniform samples around the
-predicted depth -> positional encoding + 8x256 skip@4 NeRF MLP -> raw2outputs, random-init weights (seed 42), parity
-precision (bf16 hi+lo split).  With N > 1 every rank renders its own contiguous 640,000-ray slice of an N-view batch
+predicted depth -> positional encoding + 8x256 skip@4 NeRF MLP -> raw2outputs, random-init weights (seed 42), default
+precision (fp16 single pass + split-precision guard band: meets the 1e-3 max-abs contract; --prec selects the others).  With N > 1 every rank renders its own contiguous 640,000-ray slice of an N-view batch
 (weak scaling) and the image tiles are all-gathered with NCCL inside the timed region.  Prints ONE JSON line.
 """
 
@@ -85,10 +85,22 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def pose_for_step(i: int):
-    from oracle import nerf_oracle as O  # scene helper only (pose matrix); no arithmetic of the hot path
+def pose_spherical(theta: float, phi: float, radius: float) -> torch.Tensor:
+    """Camera-to-world matrix of the Blender test orbit (the reference's load_blender.py:8-43): translate along z,
+    rotate by phi about x, by theta about y, then the Blender axis flip."""
+    import numpy as np
 
-    return O.pose_spherical(-180.0 + 1.8 * (i % 200), -30.0, 4.031)[:3, :4].contiguous()
+    ph, th = phi / 180.0 * np.pi, theta / 180.0 * np.pi
+    t = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, radius], [0, 0, 0, 1]], dtype=np.float32)
+    rp = np.array([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0], [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1]], dtype=np.float32)
+    rt = np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1]], dtype=np.float32)
+    flip = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.float32)
+    return torch.from_numpy(flip @ (rt @ (rp @ t)))
+
+
+def pose_for_step(i: int):
+    """Pose i of the 200-view test orbit (theta = -180 + 1.8 i, phi = -30, r = 4.031), 3x4."""
+    return pose_spherical(-180.0 + 1.8 * (i % 200), -30.0, 4.031)[:3, :4].contiguous()
 
 
 def intrinsics():
