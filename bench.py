@@ -33,8 +33,9 @@ NERF_FLOP_PER_POINT = 1_186_816          # 2 * 593,408 MAC, lite
 DEPTHNET_FLOP_PER_RAY = 6_660_608        # literal network (the folded inference form executes 1,309,184)
 COMPOSITE_BYTES_PER_RAY = 24 * S + 36
 # dram__bytes_read.sum + dram__bytes_write.sum of the NeRF MLP kernel, one 800x800x64 launch, from the committed
-# ncu --set full captures (profiles/r1b_ncu_summary.md, profiles/r1a_ncu_summary.md); algorithmic I/O is 819 MB
-NCU_DRAM_BYTES_PER_LAUNCH = {"fast": 797.4e6, "fp16": 797.4e6, "split": 816.3e6}
+# ncu --set full captures (profiles/r1c_ncu_summary.md: fast kernel 195.1 MB read + 604.0 MB written, guard-band launch
+# 30.9 + 1.1 MB; profiles/r1a_ncu_summary.md for the split mode); algorithmic I/O is 819 MB (z in, raw out)
+NCU_DRAM_BYTES_PER_LAUNCH = {"fast": 831.2e6, "fp16": 799.2e6, "split": 816.3e6}
 
 
 def peaks():
@@ -352,8 +353,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor",
-                         "kernel": ("nerf_fast_kernel<2,fp16> (+ mlp_chain_kernel<SPLIT> over the guard band) via b200nerf_nerf_query"
-                                    if prec in (PREC_FAST, PREC_FP16) else "mlp_chain_kernel<NERF> via b200nerf_nerf_query"),
+                         "kernel": ("fast::nerf_fast_kernel<fp16> (+ exact::mlp_exact_kernel over the guard band) via b200nerf_nerf_query"
+                                    if prec in (PREC_FAST, PREC_FP16) else
+                                    ("exact::mlp_exact_kernel<NERF> via b200nerf_nerf_query" if prec == PREC_SPLIT
+                                     else "mlp_chain_kernel<BF16,NERF> via b200nerf_nerf_query")),
                          "achieved": mlp_tflops,
                          "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tf_sustained"],
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.prec),
@@ -361,7 +364,7 @@ def main():
                          "algorithmic_flop_per_point": NERF_FLOP_PER_POINT,
                          "executed_mma_tflops": mlp_tflops * (3 if prec == PREC_SPLIT else 1) * (1_187_840 / 1_186_816),
                          "guard_band_points_last_step": int(guard[0]) if prec == PREC_FAST else None},
-            "roofline_composite": {"bound": "hbm", "kernel": "composite_kernel<32>", "achieved": comp_gbs, "peak": pk["hbm"], "unit": "GB/s",
+            "roofline_composite": {"bound": "hbm", "kernel": "composite_kernel<16,FULL>", "achieved": comp_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                    "frac": comp_gbs / pk["hbm"], "ms_per_launch": k_ms[3], "bytes_per_ray": COMPOSITE_BYTES_PER_RAY},
             "kernel_ms": {"depthnet": k_ms[0], "place": k_ms[1], "nerf_mlp": k_ms[2], "composite": k_ms[3]},
         }
