@@ -90,7 +90,10 @@ int b200nerf_gather_pixels(const float* image, const long long* pix, int n, int 
 /* viewdirs = rays_d / ||rays_d||  (nerf_utils.py:173) */
 int b200nerf_normalize_dirs(const float* rays_d, int n_rays, float* viewdirs, void* stream);
 
-/* DepthNet.forward: one depth in [near, far] per ray (depth_nets/depth_net.py:117-169).  out_z [n_rays]. */
+/* DepthNet.forward: one depth in [near, far] per ray (depth_nets/depth_net.py:117-169).  out_z [n_rays].
+ * The split-precision kernel encodes the rays one tile ahead into a library-owned staging buffer (~19 MB per device,
+ * allocated by the first call on that device -- call once before capturing a CUDA graph); launches of this entry point
+ * on the same device must therefore be stream-ordered with respect to each other. */
 int b200nerf_depthnet_fwd(const void* wpack, const float* aux, int n_hidden, int prec, const float* rays_o,
                           const float* rays_d, int n_rays, float radius, float near_, float far_, float* out_z,
                           void* stream);

@@ -322,7 +322,7 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
         // this CTA's stages of the step are contiguous in the pack: [step][rank][stage][8 KB]
         const int row0 = static_cast<int>((step_woff(s) + rank * static_cast<uint32_t>(n2) * STAGE_BYTES) / 512u);
         for (int k2 = 0; k2 < n2; ++k2) {
-          mbar_wait_lean(empty_addr + stage * 8u, phase ^ 1u);
+          mbar_wait_sleepy(empty_addr + stage * 8u, phase ^ 1u, 100);
           if (elect_one()) {
             if (leader) mbar_arrive_expect_tx_addr(full_addr + stage * 8u, 2u * STAGE_BYTES);
             tma_load_2d_cg2(ring_addr + stage * STAGE_BYTES, &tm_full, 0, row0 + k2 * (STAGE_BYTES / 512), lead_full + stage * 8u);
@@ -474,7 +474,7 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
           }
         }
         if (!first) {
-          mbar_wait_lean(pts_free_addr + slot * 8u, cp[slot]++ & 1u);   // the previous tile's skip layer has retired
+          mbar_wait_sleepy(pts_free_addr + slot * 8u, cp[slot]++ & 1u, 500);   // the previous tile's skip layer has retired
           tc_fence_after();
         }
         encode_store<FP16, 10, 8>(x, act + slot * TILE_ACT_BYTES + ENC_KB * 2 * KC_STRIDE + row_off);
@@ -490,7 +490,7 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
           for (int t = 0; t < 3; ++t) v[t] = __ldg(p.viewdirs + ray * 3 + t);
         }
         if (!first) {
-          mbar_wait_lean(view_free_addr + slot * 8u, cw[slot]++ & 1u);  // the previous tile's view layer has retired
+          mbar_wait_sleepy(view_free_addr + slot * 8u, cw[slot]++ & 1u, 500);  // the previous tile's view layer has retired
           tc_fence_after();
         }
         encode_store<FP16, 4, 4>(v, act + slot * TILE_ACT_BYTES + VIEW_KB * 2 * KC_STRIDE + row_off);

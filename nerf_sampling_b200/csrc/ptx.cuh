@@ -277,6 +277,30 @@ __device__ __forceinline__ void mbar_wait_lean(uint32_t bar_addr, uint32_t parit
     }
   }
 }
+// The same for waits that are expected to be long (encoder warps waiting for a region to be released, producers waiting for
+// a ring slot): back off with nanosleep between polls so that idle warps do not burn issue slots and power.
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar_addr, uint32_t parity, uint32_t ns) {
+  uint32_t polls = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    __nanosleep(ns);
+    if (++polls > (1u << 24)) {
+      printf("b200nerf: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar_addr, parity);
+      __trap();
+    }
+  }
+}
+
 // remote arrive in the form CUTLASS's ClusterBarrier uses (default semantics), address from mapa_u32
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
