@@ -49,12 +49,20 @@ def prepare_rays(c2w, c2w_staticcam, use_viewdirs, ndc, H, W, K, near, far, rays
     return packed, rays_o, rays_d, sh
 
 
+# The reference bounds memory with a 32,768-ray chunk loop (nerf_utils.py:58-85).  On a 180 GB part a whole 800x800 view is
+# one pass (raw for 640,000 rays x 192 samples is 2 GB) and the result is chunk-invariant (tested), so consecutive chunks are
+# coalesced up to this many rays per pass: fewer launches, no tail effects.  Set to 0 to honour `chunk` literally.
+COALESCE_RAYS = 1 << 20
+
+
 def _batchify(fn, rays_flat, chunk, **kwargs):
     out = {}
+    if COALESCE_RAYS and chunk < rays_flat.shape[0]:
+        chunk = max(chunk, min(rays_flat.shape[0], COALESCE_RAYS))
     for i in range(0, rays_flat.shape[0], chunk):
         for k, v in fn(rays_flat[i : i + chunk], **kwargs).items():
             out.setdefault(k, []).append(v)
-    return {k: torch.cat(v, 0) for k, v in out.items()}
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in out.items()}
 
 
 def batchify_rays_test(rays_flat, chunk=1024 * 32, **kwargs):
@@ -108,6 +116,12 @@ def _write_png(path: str, rgb8) -> None:
                 + chunk(b"IDAT", zlib.compress(rows.tobytes(), 3)) + chunk(b"IEND", b""))
 
 
+def _pinned_views(n, H, W):
+    """Page-locked host slabs for n rendered views from torch's caching host allocator: the first call pays cudaHostAlloc
+    (~10 MB per view), later calls of the same size reuse the block once the previous results have been dropped."""
+    return torch.empty(n, H, W, 3, dtype=torch.float32, pin_memory=True), torch.empty(n, H, W, dtype=torch.float32, pin_memory=True)
+
+
 def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=False, save_scene_data=False, gt_imgs=None,
                 savedir=None, render_factor=0):
     """Render a list of camera poses (nerf_utils.py:258-360) -> (rgbs [n,H,W,3], disps [n,H,W], mean PSNR) as numpy.
@@ -129,8 +143,7 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
     if save_scene_data:
         trainer.save_scene_data = True
     dev = torch.device("cuda", torch.cuda.current_device())
-    h_rgb = torch.empty(n, H, W, 3, dtype=torch.float32).pin_memory()
-    h_disp = torch.empty(n, H, W, dtype=torch.float32).pin_memory()
+    h_rgb, h_disp = _pinned_views(n, H, W)
     copy_stream = torch.cuda.Stream(device=dev)
     done = []
     all_pts, all_weights, mses = [], [], []
@@ -171,7 +184,7 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
         j.result()
     if pool is not None:
         pool.shutdown()
-    rgbs, disps = h_rgb.numpy(), h_disp.numpy()
+    rgbs, disps = h_rgb.numpy(), h_disp.numpy()   # views of the pinned slabs (kept alive by the arrays)
     total_psnr = 0.0
     if gt_imgs is not None and render_factor == 0:
         lines = []
