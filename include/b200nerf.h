@@ -235,6 +235,10 @@ int b200nerf_adam_step(float* param, const float* grad, float* exp_avg, float* e
 int b200nerf_adam_step_multi(const void* d_table, int n_tensors, float lr, float beta1, float beta2, float eps, int step,
                              float grad_scale, void* stream);
 
+/* CUDA-graph friendly form: the step counter (*d_step, incremented by the call) and {lr, beta1, beta2, eps, grad_scale}
+ * (d_hyper, 5 floats) live in device memory, so a captured launch stays valid while they change. */
+int b200nerf_adam_step_multi_dev(const void* d_table, int n_tensors, const float* d_hyper, int* d_step, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------ */
 
 /* D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs (raw uint16), through the same shared-memory operand layout,

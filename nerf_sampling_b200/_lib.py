@@ -59,6 +59,7 @@ SIGNATURES = {
     "b200nerf_nerf_point_jvp": (I, [P, P, P, P, P, I, P, P, P, P]),
     "b200nerf_adam_step": (I, [P, P, P, P, SZ, F, F, F, F, I, F, P]),
     "b200nerf_adam_step_multi": (I, [P, I, F, F, F, F, I, F, P]),
+    "b200nerf_adam_step_multi_dev": (I, [P, I, P, P, P]),
 }
 
 

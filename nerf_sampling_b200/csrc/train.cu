@@ -565,6 +565,34 @@ extern "C" int b200nerf_adam_step_multi(const void* d_table, int n_tensors, floa
   return 0;
 }
 
+// CUDA-graph friendly variant: the step counter lives on the device and the hyper-parameters are read from device memory
+// (d_hyper = {lr, beta1, beta2, eps, grad_scale}), so a captured launch stays valid while lr / step change.
+__global__ void adam_tick_kernel(int* step) { *step += 1; }
+__global__ void adam_multi_dev_kernel(const AdamEntry* __restrict__ table, const float* __restrict__ hyper, const int* __restrict__ step) {
+  const AdamEntry e = table[blockIdx.y];
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], gscale = hyper[4];
+  const float t = static_cast<float>(*step);
+  const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < e.n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gi = e.g[i] * gscale;
+    const float mi = b1 * e.m[i] + (1.f - b1) * gi;
+    const float vi = b2 * e.v[i] + (1.f - b2) * gi * gi;
+    e.m[i] = mi;
+    e.v[i] = vi;
+    e.p[i] -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+extern "C" int b200nerf_adam_step_multi_dev(const void* d_table, int n_tensors, const float* d_hyper, int* d_step, void* stream) {
+  if (n_tensors <= 0) return 0;
+  if (!d_table || !d_hyper || !d_step) return b200_fail("b200nerf_adam_step_multi_dev: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  adam_tick_kernel<<<1, 1, 0, st>>>(d_step);
+  LAUNCH_CHECK();
+  adam_multi_dev_kernel<<<dim3(64, n_tensors), 256, 0, st>>>(static_cast<const AdamEntry*>(d_table), d_hyper, d_step);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int b200nerf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
                                   float beta2, float eps, int step, float grad_scale, void* stream) {
   if (n == 0) return 0;

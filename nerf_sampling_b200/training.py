@@ -136,56 +136,149 @@ def nerf_params(module) -> List[torch.nn.Parameter]:
 
 
 class Adam(torch.optim.Optimizer):
-    """torch.optim.Adam semantics (no weight decay, no amsgrad) on the library's fused kernel, one launch per tensor.
-    ``grad_scale`` multiplies every gradient first (1 / world_size after a sum all-reduce)."""
+    """torch.optim.Adam semantics (no weight decay, no amsgrad) on the library's fused kernel: ONE launch updates every
+    tensor of a parameter group.  ``grad_scale`` multiplies every gradient first (1 / world_size after a sum all-reduce).
+
+    The step counter and the hyper-parameters live in device memory (like ``torch.optim.Adam(capturable=True)``), so
+    ``step()`` can be captured in a CUDA graph: the graph re-reads ``lr`` / ``grad_scale`` from a pinned host buffer on every
+    replay.  ``state[p]["step"]`` is a 0-dim device tensor shared by the tensors of a group."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
 
+    def _group_buffers(self, gi: int, group, dev):
+        bufs = self.__dict__.setdefault("_b200_bufs", {})
+        buf = bufs.get(gi)
+        if buf is None:
+            n = len(group["params"])
+            buf = dict(step=torch.zeros((), dtype=torch.int32, device=dev), hyper_host=torch.zeros(5).pin_memory(),
+                       hyper=torch.zeros(5, device=dev), ptrs=None, table=None, table_host=None,
+                       # used only while a CUDA graph is being captured (no page-locked allocation may happen then, and the
+                       # graph's memcpy node re-reads this buffer on every replay, so eager steps must never touch it)
+                       graph_table_host=torch.zeros(n, 5, dtype=torch.int64).pin_memory(),
+                       graph_table=torch.zeros(n, 5, dtype=torch.int64, device=dev))
+            bufs[gi] = buf
+        return buf
+
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         L = _lib.lib()
-        for group in self.param_groups:
+        capturing = torch.cuda.is_current_stream_capturing()
+        for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
-            rows, steps, dev = [], set(), None
+            rows, dev = [], None
             for p in group["params"]:
                 if p.grad is None:
                     continue
+                dev = p.device
                 st = self.state[p]
-                if not st:
-                    st["step"] = 0
+                if "exp_avg" not in st:
                     st["exp_avg"] = torch.zeros_like(p)
                     st["exp_avg_sq"] = torch.zeros_like(p)
-                st["step"] += 1
-                steps.add(int(st["step"]))
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 rows.append((p, g, st))
-                dev = p.device
             if not rows:
                 continue
+            buf = self._group_buffers(gi, group, dev)
+            for p, g, st in rows:
+                prev = st.get("step")
+                if prev is not buf["step"]:
+                    if prev is not None and int(prev) > int(buf["step"]):   # state loaded from a torch checkpoint
+                        buf["step"].fill_(int(prev))
+                    st["step"] = buf["step"]
             with torch.cuda.device(dev):
-                if len(steps) == 1:
-                    # one launch for the whole group: a small pointer table travels to the device every step (the
-                    # gradient tensors are new objects after every backward)
-                    # pinned staging buffers, two in rotation: a buffer is rewritten only after its previous upload ran
-                    ring = self.__dict__.setdefault("_table_ring", [])
-                    if len(ring) < 2 or ring[0][0].shape[0] != len(rows):
-                        ring[:] = [[torch.empty(len(rows), 5, dtype=torch.int64).pin_memory(), None] for _ in range(2)]
-                    self._table_turn = (getattr(self, "_table_turn", 0) + 1) % 2
-                    host, ev = ring[self._table_turn]
-                    if ev is not None:
-                        ev.synchronize()
-                    host.view(-1).numpy()[:] = [x for p, g, st in rows for x in
-                                                (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())]
-                    table = host.to(dev, non_blocking=True)
-                    ring[self._table_turn][1] = torch.cuda.Event()
-                    ring[self._table_turn][1].record()
-                    _lib.check(L.b200nerf_adam_step_multi(table.data_ptr(), len(rows), float(group["lr"]), float(b1), float(b2),
-                                                          float(group["eps"]), steps.pop(), float(grad_scale), _stream()))
-                    self._keep = (table, [g for _, g, _ in rows])  # alive until the next step: the launch is asynchronous
+                ptrs = [x for p, g, st in rows for x in (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())]
+                if capturing:
+                    host = buf["graph_table_host"][: len(rows)]
+                    host.view(-1).numpy()[:] = ptrs
+                    table = buf["graph_table"][: len(rows)]
+                    table.copy_(host, non_blocking=True)
                 else:
-                    for p, g, st in rows:
-                        _lib.check(L.b200nerf_adam_step(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                                                        p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                                        int(st["step"]), float(grad_scale), _stream()))
+                    if ptrs != buf["ptrs"]:
+                        # gradients are new tensors after an eager backward: refresh the pointer table (a fresh pinned buffer
+                        # per refresh: the previous upload may still be in flight)
+                        host = torch.tensor(ptrs, dtype=torch.int64).reshape(len(rows), 5).pin_memory()
+                        buf["table_host"], buf["ptrs"] = host, ptrs
+                        buf["table"] = host.to(dev, non_blocking=True)
+                        buf["keep"] = [g for _, g, _ in rows]
+                    table = buf["table"]
+                hh = buf["hyper_host"]
+                hh[0], hh[1], hh[2], hh[3], hh[4] = float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(grad_scale)
+                buf["hyper"].copy_(hh, non_blocking=True)   # in a captured graph: a memcpy node that re-reads the host values
+                _lib.check(L.b200nerf_adam_step_multi_dev(table.data_ptr(), len(rows), buf["hyper"].data_ptr(),
+                                                          buf["step"].data_ptr(), _stream()))
         return None
+
+    def set_hyper(self, grad_scale: float = 1.0):
+        """Refresh the pinned hyper-parameter block before replaying a captured step (lr may have been changed on the group)."""
+        for gi, group in enumerate(self.param_groups):
+            buf = self.__dict__.get("_b200_bufs", {}).get(gi)
+            if buf is not None:
+                b1, b2 = group["betas"]
+                hh = buf["hyper_host"]
+                hh[0], hh[1], hh[2], hh[3], hh[4] = float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(grad_scale)
+
+
+class GraphedTrainStep:
+    """``Trainer.core_optimization_loop`` captured in ONE CUDA graph (render, both backward passes, gradient all-reduce, Adam):
+    the step is ~450 small launches, so on 512 rays per GPU it is launch-bound when enqueued from Python.
+
+        step = GraphedTrainStep(trainer, sampling_optimizer, render_kwargs_train, n_rays)
+        loss, depth_net_loss, psnr = step(batch_rays, target_s)      # tensors (no host sync)
+
+    Batch shape is fixed at construction; ``perturb`` must be 0 (random draws would be frozen into the graph)."""
+
+    def __init__(self, trainer, optimizer, render_kwargs_train, n_rays: int, warmup: int = 3):
+        dev = next(p for g in optimizer.param_groups for p in g["params"]).device
+        self.trainer, self.opt, self.kw = trainer, optimizer, render_kwargs_train
+        self.rays = torch.zeros(2, n_rays, 3, device=dev)
+        self.rays[1, :, 2] = -1.0   # a valid placeholder direction for the warm-up steps
+        self.rays[0, :, 2] = 4.0
+        self.target = torch.zeros(n_rays, 3, device=dev)
+        self.graph = None
+        self.warmup = warmup
+        self.out = None
+
+    def _capture(self):
+        import torch.distributed as dist
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        backup = [p.detach().clone() for g in self.opt.param_groups for p in g["params"]]
+        state_backup = None
+        with torch.cuda.stream(side):
+            for i in range(self.warmup):   # lazy initialisation (function attributes, scratch buffers, NCCL) must not be captured
+                self.trainer.core_optimization_loop(self.opt, self.kw, (self.rays[0], self.rays[1]), i, self.target)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        # the warm-up steps must leave no trace: restore parameters and optimizer state
+        with torch.no_grad():
+            for p, b in zip((p for g in self.opt.param_groups for p in g["params"]), backup):
+                p.copy_(b)
+                st = self.opt.state[p]
+                st["exp_avg"].zero_()
+                st["exp_avg_sq"].zero_()
+            for buf in self.opt.__dict__.get("_b200_bufs", {}).values():
+                buf["step"].zero_()
+        del state_backup
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            loss, dn_loss, psnr, _ = self.trainer.core_optimization_loop(self.opt, self.kw, (self.rays[0], self.rays[1]), 100, self.target)
+            self.out = (loss.detach(), dn_loss.detach(), psnr.detach())
+        if dist.is_initialized():
+            dist.barrier()
+
+    def __call__(self, batch_rays, target_s):
+        self.rays[0].copy_(batch_rays[0])
+        self.rays[1].copy_(batch_rays[1])
+        self.target.copy_(target_s)
+        if self.graph is None:
+            self._capture()
+            self.rays[0].copy_(batch_rays[0])
+            self.rays[1].copy_(batch_rays[1])
+            self.target.copy_(target_s)
+        import torch.distributed as dist
+
+        self.opt.set_hyper(1.0 / dist.get_world_size() if dist.is_initialized() else 1.0)
+        self.graph.replay()
+        return self.out

@@ -16,6 +16,7 @@ from nerf_sampling_b200.packing import PREC_FAST, PREC_SPLIT  # noqa: E402
 from nerf_sampling_b200.trainers import DepthNetTrainer  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+use_graph = "--graph" in sys.argv
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
@@ -37,15 +38,20 @@ sel = torch.randperm(ro.shape[0], generator=torch.Generator().manual_seed(0))[:n
 rays = (ro[sel].contiguous(), rd[sel].contiguous())
 target = torch.rand(n_total, 3, generator=torch.Generator().manual_seed(1))[rank * per:(rank + 1) * per].to(dev)
 opt = training.Adam(list(dn.parameters()), lr=1e-4)
+if use_graph:
+    graphed = training.GraphedTrainStep(tr, opt, kw, per)
+    run = lambda i: graphed(rays, target)  # noqa: E731
+else:
+    run = lambda i: tr.core_optimization_loop(opt, kw, rays, i, target)  # noqa: E731
 for i in range(3):
-    out = tr.core_optimization_loop(opt, kw, rays, i, target)
+    out = run(i)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for i in range(steps):
-    out = tr.core_optimization_loop(opt, kw, rays, 3 + i, target)
+    out = run(3 + i)
 e1.record()
 torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
@@ -53,7 +59,7 @@ if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"metric": "train_steps_per_sec", "value": 1e3 / float(ms), "ms_per_step": float(ms), "rays_per_step": n_total,
-                      "rays_per_sec": n_total * 1e3 / float(ms), "n_gpus": world, "loss": float(out[0]), "depth_net_loss": float(out[1]),
+                      "rays_per_sec": n_total * 1e3 / float(ms), "n_gpus": world, "cuda_graph": use_graph, "loss": float(out[0]), "depth_net_loss": float(out[1]),
                       "config": "DepthNet training step, 4096 rays/batch, 64+128 hierarchical target, data parallel (BASELINE config #5)"}))
 if world > 1:
     dist.destroy_process_group()
