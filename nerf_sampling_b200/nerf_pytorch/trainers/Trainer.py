@@ -85,9 +85,14 @@ class Trainer:
         ``retain_graph`` first, then the colour loss; under ``torch.distributed`` the DepthNet gradients are
         sum-all-reduced as one flat buffer and averaged by the optimizer (equal ray shards per rank reproduce the
         single-process gradient)."""
-        import torch.nn.functional as F
+        loss, depth_net_loss, psnr, psnr0 = self.render_and_backward(sampling_optimizer, render_kwargs_train, batch_rays, i, target_s)
+        self.reduce_and_step(sampling_optimizer)
+        return loss, depth_net_loss, psnr, psnr0
 
-        from ... import parallel, training
+    def render_and_backward(self, sampling_optimizer, render_kwargs_train, batch_rays, i, target_s):
+        """First half of core_optimization_loop: render, zero_grad, both backward passes (Trainer.py:515-538).  Pure device
+        work on the current stream -- this is the part ``training.GraphedTrainStep`` captures in a CUDA graph."""
+        import torch.nn.functional as F
 
         depth_net_rgb, depth_net_disp, extras = nerf_utils.render(self.H, self.W, self.K, chunk=self.chunk, rays=batch_rays,
                                                                   verbose=i < 10, retraw=True, **render_kwargs_train)
@@ -95,10 +100,15 @@ class Trainer:
         img_loss = nerf_utils.run_nerf_helpers.img2mse(depth_net_rgb, target_s)
         loss = img_loss
         psnr = nerf_utils.run_nerf_helpers.mse2psnr(img_loss)
-        psnr0 = None
         depth_net_loss = F.mse_loss(extras["depth_net_z_vals"], extras["max_z_vals"])
         depth_net_loss.backward(retain_graph=True)
         loss.backward()
+        return loss, depth_net_loss, psnr, None
+
+    def reduce_and_step(self, sampling_optimizer):
+        """Second half: data-parallel gradient all-reduce (one flat buffer) and the optimizer step (Trainer.py:542)."""
+        from ... import parallel, training
+
         params = [p for g in sampling_optimizer.param_groups for p in g["params"]]
         scale = parallel.allreduce_gradients(params)
         if isinstance(sampling_optimizer, training.Adam):
@@ -109,7 +119,6 @@ class Trainer:
                     if p.grad is not None:
                         p.grad.mul_(scale)
             sampling_optimizer.step()
-        return loss, depth_net_loss, psnr, psnr0
 
     def update_learning_rate(self, optimizer):
         """Exponential decay of Trainer.py:546-551."""

@@ -220,8 +220,9 @@ class Adam(torch.optim.Optimizer):
 
 
 class GraphedTrainStep:
-    """``Trainer.core_optimization_loop`` captured in ONE CUDA graph (render, both backward passes, gradient all-reduce, Adam):
-    the step is ~450 small launches, so on 512 rays per GPU it is launch-bound when enqueued from Python.
+    """``Trainer.core_optimization_loop`` with its device work captured in ONE CUDA graph (render, zero_grad, both backward
+    passes: ~440 small launches, launch-bound from Python at 512 rays per GPU); the gradient all-reduce and the two-launch
+    Adam step follow eagerly, so no collective is ever captured.
 
         step = GraphedTrainStep(trainer, sampling_optimizer, render_kwargs_train, n_rays)
         loss, depth_net_loss, psnr = step(batch_rays, target_s)      # tensors (no host sync)
@@ -232,53 +233,32 @@ class GraphedTrainStep:
         dev = next(p for g in optimizer.param_groups for p in g["params"]).device
         self.trainer, self.opt, self.kw = trainer, optimizer, render_kwargs_train
         self.rays = torch.zeros(2, n_rays, 3, device=dev)
-        self.rays[1, :, 2] = -1.0   # a valid placeholder direction for the warm-up steps
-        self.rays[0, :, 2] = 4.0
+        self.rays[0, :, 2] = 4.0    # placeholder rays for the warm-up steps: straight at the unit sphere
+        self.rays[1, :, 2] = -1.0
         self.target = torch.zeros(n_rays, 3, device=dev)
         self.graph = None
         self.warmup = warmup
         self.out = None
 
     def _capture(self):
-        import torch.distributed as dist
-
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        backup = [p.detach().clone() for g in self.opt.param_groups for p in g["params"]]
-        state_backup = None
         with torch.cuda.stream(side):
-            for i in range(self.warmup):   # lazy initialisation (function attributes, scratch buffers, NCCL) must not be captured
-                self.trainer.core_optimization_loop(self.opt, self.kw, (self.rays[0], self.rays[1]), i, self.target)
+            for i in range(self.warmup):   # lazy initialisation (function attributes, cached grids) must not be captured
+                self.trainer.render_and_backward(self.opt, self.kw, (self.rays[0], self.rays[1]), i, self.target)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        # the warm-up steps must leave no trace: restore parameters and optimizer state
-        with torch.no_grad():
-            for p, b in zip((p for g in self.opt.param_groups for p in g["params"]), backup):
-                p.copy_(b)
-                st = self.opt.state[p]
-                st["exp_avg"].zero_()
-                st["exp_avg_sq"].zero_()
-            for buf in self.opt.__dict__.get("_b200_bufs", {}).values():
-                buf["step"].zero_()
-        del state_backup
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            loss, dn_loss, psnr, _ = self.trainer.core_optimization_loop(self.opt, self.kw, (self.rays[0], self.rays[1]), 100, self.target)
+            loss, dn_loss, psnr, _ = self.trainer.render_and_backward(self.opt, self.kw, (self.rays[0], self.rays[1]), 100, self.target)
             self.out = (loss.detach(), dn_loss.detach(), psnr.detach())
-        if dist.is_initialized():
-            dist.barrier()
 
     def __call__(self, batch_rays, target_s):
+        if self.graph is None:
+            self._capture()
         self.rays[0].copy_(batch_rays[0])
         self.rays[1].copy_(batch_rays[1])
         self.target.copy_(target_s)
-        if self.graph is None:
-            self._capture()
-            self.rays[0].copy_(batch_rays[0])
-            self.rays[1].copy_(batch_rays[1])
-            self.target.copy_(target_s)
-        import torch.distributed as dist
-
-        self.opt.set_hyper(1.0 / dist.get_world_size() if dist.is_initialized() else 1.0)
-        self.graph.replay()
+        self.graph.replay()                       # gradients land in the tensors the capture allocated (static addresses)
+        self.trainer.reduce_and_step(self.opt)    # flat NCCL all-reduce + fused Adam, eager
         return self.out
