@@ -364,7 +364,7 @@ def main():
                          "algorithmic_flop_per_point": NERF_FLOP_PER_POINT,
                          "executed_mma_tflops": mlp_tflops * (3 if prec == PREC_SPLIT else 1) * (1_187_840 / 1_186_816),
                          "guard_band_points_last_step": int(guard[0]) if prec == PREC_FAST else None},
-            "roofline_composite": {"bound": "hbm", "kernel": "composite_kernel<16,FULL>", "achieved": comp_gbs, "peak": pk["hbm"], "unit": "GB/s",
+            "roofline_composite": {"bound": "hbm", "kernel": "comp::composite_tma_kernel<16> (TMA-staged, persistent)", "achieved": comp_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                    "frac": comp_gbs / pk["hbm"], "ms_per_launch": k_ms[3], "bytes_per_ray": COMPOSITE_BYTES_PER_RAY},
             "kernel_ms": {"depthnet": k_ms[0], "place": k_ms[1], "nerf_mlp": k_ms[2], "composite": k_ms[3]},
         }

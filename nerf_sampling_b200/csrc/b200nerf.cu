@@ -10,6 +10,7 @@
 #include "mlp_chain.cuh"
 #include "mlp_exact.cuh"
 #include "mlp_fast.cuh"
+#include "composite_tma.cuh"
 #include <cuda.h>
 
 using namespace b200;
@@ -847,6 +848,49 @@ static void launch_composite(const float* raw, const float* z, const float* rays
   else composite_kernel<LPR, false><<<grid, 256, 0, st>>>(raw, z, rays_d, noise, n_rays, S, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha);
 }
 
+// S = 32 / 64 / 128 without a noise input: the TMA-staged persistent kernel (composite_tma.cuh).  raw viewed as
+// [n_rays*S/8 rows, 128 B]; one box = 256 rows = one 2048-sample tile, 128-byte swizzle.
+template <int LPR>
+static int launch_composite_tma(const float* raw, const float* z, const float* rays_d, int n_rays, int white, float* o_rgb,
+                                float* o_disp, float* o_acc, float* o_depth, float* o_w, float* o_alpha, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = comp::composite_tma_kernel<LPR>;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, comp::SMEM_BYTES));
+    configured = true;
+  }
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  static_assert(sizeof(CUtensorMap) == sizeof(comp::TMap), "tensor map size");
+  const long long total = static_cast<long long>(n_rays) * (4 * LPR);
+  comp::TMap tm;
+  const cuuint64_t gdim[2] = {32, static_cast<cuuint64_t>(total / 8)};
+  const cuuint64_t gstride[1] = {128};
+  const cuuint32_t box[2] = {32, comp::RAW_BYTES / 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(reinterpret_cast<CUtensorMap*>(&tm), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(raw), gdim, gstride,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled(raw) failed (%d)", static_cast<int>(r));
+  const long long tiles = (total + comp::TILE_SAMPLES - 1) / comp::TILE_SAMPLES;
+  const int sms = sm_count();
+  if (sms <= 0) return fail("no CUDA device");
+  const int grid = static_cast<int>(tiles < 2LL * sms ? tiles : 2LL * sms);
+  kern<<<grid, comp::THREADS, comp::SMEM_BYTES, st>>>(tm, z, rays_d, n_rays, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static bool composite_force_ldg() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200NERF_COMPOSITE_LDG");   // A/B switch for measurements: 1 = register-staged kernel everywhere
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 extern "C" int b200nerf_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays,
                                       int S, int white_bkgd, float* out_rgb, float* out_disp, float* out_acc,
                                       float* out_depth, float* out_weights, float* out_alphas, void* stream) {
@@ -858,6 +902,12 @@ extern "C" int b200nerf_composite_fwd(const float* raw, const float* z, const fl
     composite_single_kernel<<<(n_rays + 255) / 256, 256, 0, st>>>(raw, n_rays, out_rgb, out_disp, out_acc, out_depth);
     LAUNCH_CHECK();
     return 0;
+  }
+  if ((S == 32 || S == 64 || S == 128) && !noise && static_cast<long long>(n_rays) * S >= comp::TILE_SAMPLES && aligned16(raw) &&
+      aligned16(z) && aligned16(out_weights) && aligned16(out_alphas) && !composite_force_ldg()) {
+    if (S == 32) return launch_composite_tma<8>(raw, z, rays_d, n_rays, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+    if (S == 64) return launch_composite_tma<16>(raw, z, rays_d, n_rays, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+    return launch_composite_tma<32>(raw, z, rays_d, n_rays, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
   }
   // lanes per ray: four samples per lane and pass
   if (S <= 4) launch_composite<1>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);

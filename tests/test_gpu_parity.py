@@ -76,7 +76,9 @@ def test_placement_bit_exact(lib):
     assert bool(torch.isnan(z[0]).all()) and not bool(torch.isnan(z[1:]).any())
 
 
-@pytest.mark.parametrize("n,S", [(1, 2), (5, 3), (33, 8), (100, 32), (257, 64), (64, 192), (19, 1), (40, 70)])
+@pytest.mark.parametrize("n,S", [(1, 2), (5, 3), (33, 8), (100, 32), (257, 64), (64, 192), (19, 1), (40, 70),
+                                 # TMA-staged kernel (S = 32 / 64 / 128, >= one 2048-sample tile): ragged last tile, several tiles per CTA
+                                 (4097, 64), (70001, 64), (3001, 32), (40000, 32), (1501, 128)])
 def test_composite_matches_oracle(lib, n, S):
     from nerf_sampling_b200 import ops
 

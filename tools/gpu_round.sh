@@ -12,10 +12,11 @@ python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/plain.log 2>
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?" | tee -a gpurun_out/summary.txt
 python tools/profile_step.py > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"nerf_fast|composite_kernel|mlp_exact" -c 8 -f -o gpurun_out/prof_step python tools/profile_step.py > gpurun_out/ncu_step.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"nerf_fast|composite|mlp_exact" -c 8 -f -o gpurun_out/prof_step python tools/profile_step.py > gpurun_out/ncu_step.log 2>&1
 echo "ncu step rc=$?" | tee -a gpurun_out/summary.txt
 timeout 300 python tools/bench_hierarchical.py 5 > gpurun_out/bench_hier.json 2> gpurun_out/bench_hier.err; echo "bench hierarchical rc=$?" | tee -a gpurun_out/summary.txt
 timeout 300 python tools/bench_train.py 20 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err; echo "bench train rc=$?" | tee -a gpurun_out/summary.txt
-timeout 300 python tools/profile_composite.py 64 > gpurun_out/bench_composite.txt 2>&1; echo "composite rc=$?" | tee -a gpurun_out/summary.txt
+(timeout 300 python tools/profile_composite.py 64; B200NERF_COMPOSITE_LDG=1 timeout 300 python tools/profile_composite.py 64; timeout 300 python tools/profile_composite.py 32; timeout 300 python tools/profile_composite.py 128) > gpurun_out/bench_composite.txt 2>&1; echo "composite rc=$?" | tee -a gpurun_out/summary.txt
+timeout 300 python tools/train_breakdown.py 4096 > gpurun_out/train_breakdown.txt 2>&1; echo "train breakdown rc=$?" | tee -a gpurun_out/summary.txt
 tail -n 4 gpurun_out/t_gpu.log gpurun_out/smoke.log
 cat gpurun_out/bench.json gpurun_out/bench_split.json gpurun_out/bench_fp16.json gpurun_out/bench_ref.json gpurun_out/bench_hier.json gpurun_out/bench_train.json gpurun_out/bench_composite.txt
