@@ -245,6 +245,13 @@ int b200nerf_adam_step_multi_dev(const void* d_table, int n_tensors, const float
  * UMMA descriptors and TMEM read-back as the MLP kernels.  K % 16 == 0, K <= 128, N % 16 == 0, N <= 256. */
 int b200nerf_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int K, int N, void* stream);
 
+/* The strided fp32 GEMM of the training slice, C[M,N] = (beta ? C : 0) + sum_k A[m*sAm + k*sAk] * B[k*sBk + n*sBn] (+ bias[n])
+ * (then LeakyReLU(slope) if act): covers X*W^T (Linear forward, depth_net.py:117-169), dY*W and dY^T*X (its backward) without
+ * transposes.  Runs as an error-compensated 3xTF32 product on the tcgen05 tensor cores (csrc/tgemm.cuh) unless
+ * force_fp32 != 0 or B200NERF_TRAIN_GEMM=fp32 (CUDA-core fp32 kernel).  Exposed for the parity tests. */
+int b200nerf_debug_sgemm(int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBk, long sBn, float* C,
+                         int ldc, int beta, const float* bias, int act, float slope, int force_fp32, void* stream);
+
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 unsigned long long b200nerf_launch_count(void);
 

@@ -1,0 +1,285 @@
+// Grouped, K-segmented fp32 GEMM on the tcgen05 tensor cores for the training slice (train.cu): 3xTF32 error-compensated.
+//
+// One problem:  C[M,N] (row-major, ldc) = (beta ? C : 0) + sum_seg sum_k A_s(m,k) * B_s(k,n) [+ bias[n]] [LeakyReLU] [* dact]
+//   A_s(m,k) = A_s[m*sAm + k*sAk], B_s(k,n) = B_s[k*sBk + n*sBn]
+// The strides cover X*W^T (Linear forward), dY*W (input gradient) and dY^T*X (weight gradient) without transposes; the K
+// SEGMENTS are the pieces of a concatenated input (`Linear(cat([x, e]))`, depth_net.py:139-157, is two segments of one
+// product: no cat, no second launch); a GROUP is up to nine independent problems in one launch (the three DepthNet
+// branches advance together; a layer's weight gradients and its input gradient share a launch).  The CUDA-core kernel this
+// replaces (sgemm_kernel) took 9.5 of the 12.9 ms of a 4096-ray training step, in ~320 launches.
+//
+// Precision: every fp32 operand x is split in registers into hi = x with the low 13 mantissa bits cleared (exactly a
+// TF32 value) and lo = x - hi (exact in fp32); the tile product is accumulated in TMEM as  lo*hi + hi*lo + hi*hi  with
+// `tcgen05.mma.kind::tf32`.  Relative error ~2^-20 per product (the dropped lo*lo and the hardware's truncation of lo):
+// measured against fp64 it is within 4x of the fp32 FMA kernel's own rounding error, so the gradients stay fp32-grade.
+//
+// One CTA = one 128 x 64 output tile (optionally one K slice of it: split K for the weight gradients, which reduce over
+// thousands of rays into a 256 x ~300 output; partial sums are added atomically into a pre-zeroed C).  K is walked in
+// chunks of 32: all 256 threads load the A (128 x 32) and B (64 x 32) pieces with lanes along the operand's contiguous
+// dimension -- one chunk AHEAD, into registers -- split them and store 16-byte k-quads into the K-major no-swizzle UMMA
+// layout (core matrix = 8 rows x 16 B = 8 x 4 TF32; LBO padded by 16 B so that a warp's stores spread over all bank
+// groups) and arrive on the stage's `full` barrier; a ninth warp waits for it, issues 4 K8 steps x 3 MMAs and commits to the
+// stage's `mma_done` barrier.  Two smem stages: the loaders never wait for the MMA issue of the chunk they just stored.  Epilogue: tcgen05.ld (8 warps = 4 lane quarters x 2 column halves), + bias,
+// LeakyReLU, optional multiplication by the LeakyReLU derivative of a saved activation (fuses the backward's activation
+// step into the input-gradient product), store / atomicAdd.  `colsum` (weight-gradient problems): the bias gradient
+// db[m] = sum_k A(m,k) falls out of the A loads for free.
+#pragma once
+#include <cstdint>
+
+#include "ptx.cuh"
+
+namespace b200 {
+namespace tg {
+
+constexpr int BM = 128, BN = 64, KC = 32, THREADS = 256;   // THREADS = the loader / epilogue warps
+constexpr int CTA_THREADS = THREADS + 32;                   // + one warp that owns TMEM and issues the MMAs
+constexpr int LBO_A = BM * 16 + 16;            // bytes between consecutive k-quads (4 TF32 = 16 B) of the A plane
+constexpr int LBO_B = BN * 16 + 16;
+constexpr int PLANE_A = (KC / 4) * LBO_A;      // 16,512 B
+constexpr int PLANE_B = (KC / 4) * LBO_B;      //  8,320 B
+constexpr int STAGE_BYTES = 2 * PLANE_A + 2 * PLANE_B;   // hi + lo of both operands: 49,664 B
+constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 128;
+constexpr uint32_t TMEM_COLS = 64;
+constexpr int MAX_SEG = 4, MAX_PROB = 9;
+constexpr int QA = BM * (KC / 4) / THREADS;    // k-quads per thread and chunk: 4 of A ...
+constexpr int QB = BN * (KC / 4) / THREADS;    // ... 2 of B
+
+struct Seg {
+  const float* A;
+  const float* B;
+  long sAm, sAk, sBk, sBn;
+  int K;
+  int vecA, vecB;   // k-contiguous operand with 16-byte aligned rows: float4 loads
+  int pad_;
+};
+struct Prob {
+  Seg seg[MAX_SEG];
+  float* C;
+  const float* bias;
+  float* colsum;        // db[m] += sum_k A(m,k) (A must be k-strided, i.e. sAm == 1); pre-zeroed by the caller
+  const float* dact;    // epilogue *= (dact[m*ld_dact + n] > 0 ? 1 : slope)
+  int M, N, nseg, ldc, beta, act, ld_dact;
+  float slope;
+  int tiles_x, tiles_y, splits, k_per, cta_begin;   // splits > 1 only with nseg == 1; k_per a multiple of KC
+};
+struct Group {
+  int nprob;
+  Prob prob[MAX_PROB];
+};
+static_assert(sizeof(Group) <= 4000, "kernel parameter space");
+
+// kind::tf32 instruction descriptor: D = f32, A = B = TF32 (format 2), both K-major
+__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// R rows x KC k of one operand into registers: element (row, k) = src[row*srow + k*sk]; rows >= row_lim, k >= k_end -> 0.
+template <int R, int Q>
+__device__ __forceinline__ void load_quads(const float* __restrict__ src, long srow, long sk, int row0, int row_lim, int k0, int k_end,
+                                           int vec, int tid, float (&v)[Q][4]) {
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    const int qi = tid + i * THREADS;
+    int r, kq;
+    if (sk == 1) { r = qi >> 3; kq = qi & 7; } else { r = qi & (R - 1); kq = qi / R; }   // lanes along the contiguous dimension
+    const int gr = row0 + r, gk = k0 + kq * 4;
+    const float* s = src + gr * srow + gk * sk;
+    if (gr < row_lim && vec && gk + 3 < k_end) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(s));
+      v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[i][j] = (gr < row_lim && gk + j < k_end) ? __ldg(s + j * sk) : 0.f;
+    }
+  }
+}
+// hi / lo split and 16-byte stores into the UMMA planes; `kfast` = the mapping load_quads used (sk == 1)
+template <int R, int Q>
+__device__ __forceinline__ void split_store(const float (&v)[Q][4], bool kfast, uint8_t* hi_plane, uint8_t* lo_plane, int lbo, int tid) {
+#pragma unroll
+  for (int i = 0; i < Q; ++i) {
+    const int qi = tid + i * THREADS;
+    int r, kq;
+    if (kfast) { r = qi >> 3; kq = qi & 7; } else { r = qi & (R - 1); kq = qi / R; }
+    const int off = r * 16 + kq * lbo;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __float_as_uint(v[i][j]) & 0xffffe000u;
+      l[j] = __float_as_uint(v[i][j] - __uint_as_float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_constant__ Group g) {
+  extern __shared__ __align__(128) uint8_t tg_smem_[];
+  __shared__ uint64_t mma_done[2];   // stage s: its MMAs have retired (tcgen05.commit)
+  __shared__ uint64_t full[2];       // stage s: all eight loader warps have stored (and proxy-fenced) their quads
+  __shared__ uint32_t tmem_slot;
+  __shared__ float colsum_red[THREADS];
+  uint8_t* smem = tg_smem_ + ((128u - (smem_u32(tg_smem_) & 127u)) & 127u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  int pi = 0;
+  while (pi + 1 < g.nprob && static_cast<int>(blockIdx.x) >= g.prob[pi + 1].cta_begin) ++pi;
+  const Prob& P = g.prob[pi];
+  const int local = blockIdx.x - P.cta_begin;
+  const int tx = local % P.tiles_x, ty = (local / P.tiles_x) % P.tiles_y, sz = local / (P.tiles_x * P.tiles_y);
+  const int m0 = ty * BM, n0 = tx * BN;
+  const bool split = P.splits > 1;
+
+  // chunk walk: segment `cs`, k range [ck, ce) of it; a split-K CTA owns one slice of segment 0
+  int cs = 0;
+  int ck = split ? sz * P.k_per : 0;
+  int ce = split ? min(P.seg[0].K, ck + P.k_per) : P.seg[0].K;
+  int nchunks = 0;
+  if (split) {
+    nchunks = (ce - ck + KC - 1) / KC;
+  } else {
+    for (int s = 0; s < P.nseg; ++s) nchunks += (P.seg[s].K + KC - 1) / KC;
+  }
+  if (nchunks <= 0) return;   // uniform over the CTA (an empty split-K slice adds nothing)
+
+  constexpr int MMA_WARP = THREADS / 32;
+  if (tid == 0) {
+    mbar_init(&mma_done[0], 1);
+    mbar_init(&mma_done[1], 1);
+    mbar_init(&full[0], THREADS / 32);
+    mbar_init(&full[1], THREADS / 32);
+    fence_mbar_init();
+  }
+  if (warp == MMA_WARP) {
+    tmem_alloc(&tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  constexpr uint32_t idesc = idesc_tf32(BM, BN);
+
+  if (warp == MMA_WARP) {
+    // ---- MMA issue: decoupled from the loaders, which never wait for the issue of the chunk they just stored
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c & 1;
+        const uint32_t a_hi = smem_u32(smem) + s * STAGE_BYTES, a_lo = a_hi + PLANE_A, b_hi = a_lo + PLANE_A, b_lo = b_hi + PLANE_B;
+        mbar_wait(&full[s], static_cast<uint32_t>(c >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < KC / 8; ++j) {
+          // one K8 step = two k-quads of each plane
+          const uint64_t dah = umma_desc_kmajor(a_hi + j * 2 * LBO_A, LBO_A, 128);
+          const uint64_t dal = umma_desc_kmajor(a_lo + j * 2 * LBO_A, LBO_A, 128);
+          const uint64_t dbh = umma_desc_kmajor(b_hi + j * 2 * LBO_B, LBO_B, 128);
+          const uint64_t dbl = umma_desc_kmajor(b_lo + j * 2 * LBO_B, LBO_B, 128);
+          mma_tf32(tmem_base, dal, dbh, idesc, (c > 0 || j > 0) ? 1u : 0u);
+          mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        tc_commit(&mma_done[s]);
+      }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+    return;
+  }
+
+  // ---- loader warps
+  float va[QA][4], vb[QB][4];
+  bool a_kfast, b_kfast;
+  auto prefetch = [&]() {   // loads chunk (cs, ck) into registers and advances the walk
+    const Seg& S = P.seg[cs];
+    a_kfast = S.sAk == 1;
+    b_kfast = S.sBk == 1;
+    load_quads<BM, QA>(S.A, S.sAm, S.sAk, m0, P.M, ck, ce, S.vecA, tid, va);
+    load_quads<BN, QB>(S.B, S.sBn, S.sBk, n0, P.N, ck, ce, S.vecB, tid, vb);
+    ck += KC;
+    if (ck >= ce && !split && cs + 1 < P.nseg) {
+      ++cs;
+      ck = 0;
+      ce = P.seg[cs].K;
+    }
+  };
+  prefetch();
+  float csum = 0.f;
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1;
+    uint8_t* a_hi = smem + s * STAGE_BYTES;
+    uint8_t* a_lo = a_hi + PLANE_A;
+    uint8_t* b_hi = a_lo + PLANE_A;
+    uint8_t* b_lo = b_hi + PLANE_B;
+    if (c >= 2) mbar_wait(&mma_done[s], static_cast<uint32_t>((c >> 1) - 1) & 1u);   // the MMAs that read this stage have retired
+    split_store<BM, QA>(va, a_kfast, a_hi, a_lo, LBO_A, tid);
+    split_store<BN, QB>(vb, b_kfast, b_hi, b_lo, LBO_B, tid);
+    if (P.colsum) {
+#pragma unroll
+      for (int i = 0; i < QA; ++i) csum += (va[i][0] + va[i][1]) + (va[i][2] + va[i][3]);
+    }
+    if (c + 1 < nchunks) prefetch();   // in flight while the MMA warp works and the next stage is waited for
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[s]);
+  }
+
+  if (P.colsum) {   // k-strided A: a thread's quads all belong to row (tid & 127)
+    colsum_red[tid] = csum;
+    named_bar_sync(1, THREADS);
+    if (tid < BM && tx == 0 && m0 + tid < P.M) atomicAdd(P.colsum + m0 + tid, colsum_red[tid] + colsum_red[tid + BM]);
+  }
+
+  const int last = nchunks - 1;
+  mbar_wait(&mma_done[last & 1], static_cast<uint32_t>(last >> 1) & 1u);
+  tc_fence_after();
+
+  // epilogue: warp w reads TMEM lanes 32*(w&3).. (its sub-partition) and columns 32*(w>>2)..
+  {
+    const int lq = warp & 3, ch = warp >> 2;
+    const int gm = m0 + lq * 32 + lane;
+    const int gn0 = n0 + ch * 32;
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + static_cast<uint32_t>(ch * 32), v);
+    tmem_ld_wait();
+    if (gm < P.M) {
+      float* crow = P.C + static_cast<size_t>(gm) * P.ldc;
+      const float* drow = P.dact ? P.dact + static_cast<size_t>(gm) * P.ld_dact : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int gn = gn0 + j;
+        if (gn < P.N) {
+          float x = __uint_as_float(v[j]);
+          if (split) {
+            if (P.bias && sz == 0) x += __ldg(P.bias + gn);
+            atomicAdd(crow + gn, x);
+          } else {
+            if (P.beta) x += crow[gn];
+            if (P.bias) x += __ldg(P.bias + gn);
+            if (P.act) x = x > 0.f ? x : x * P.slope;
+            if (drow) x = __ldg(drow + gn) > 0.f ? x : x * P.slope;
+            crow[gn] = x;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();   // pairs with the MMA warp's: it frees the accumulator after every epilogue warp has read it
+}
+
+}  // namespace tg
+}  // namespace b200

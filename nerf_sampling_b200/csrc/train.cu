@@ -11,11 +11,13 @@
 // 512 rays per GPU and two evaluations per ray, i.e. latency- not throughput-bound, and fp32 CUDA-core GEMMs keep the
 // gradients at the reference's own precision.  Host loops over layers live here, behind one C call per pass.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "../../include/b200nerf.h"
 #include "host_common.h"
+#include "tgemm.cuh"
 
 // ------------------------------------------------------------------------------------------- strided SGEMM
 // C[M,N] (row-major, ldc) = (beta ? C : 0) + sum_k A(m,k) * B(k,n) [+ bias[n]] [then LeakyReLU(slope) if act]
@@ -94,9 +96,133 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
   }
 }
 
+// The tensor-core path (tgemm.cuh: 3xTF32 on tcgen05).  B200NERF_TRAIN_GEMM=fp32 keeps every product on the CUDA-core
+// kernel above (A/B measurements, and the reference point of the precision tests).
+static bool tgemm_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200NERF_TRAIN_GEMM");
+    v = (e && strcmp(e, "fp32") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+// ---- grouped / K-segmented problems for tgemm_kernel ----------------------------------------------------------
+struct GemmSeg {
+  const float* A; long sAm, sAk;
+  const float* B; long sBk, sBn;
+  int K;
+};
+struct GemmProb {
+  int M = 0, N = 0, nseg = 0;
+  GemmSeg seg[b200::tg::MAX_SEG];
+  float* C = nullptr;
+  int ldc = 0, beta = 0;
+  const float* bias = nullptr;
+  int act = 0;
+  float slope = 0.f;
+  float* colsum = nullptr;       // += column sums of A^T, i.e. sum_k A(m,k) (bias gradient); target pre-zeroed
+  const float* dact = nullptr;   // epilogue *= LeakyReLU'(dact)
+  int ld_dact = 0;
+  bool c_zeroed = false;         // C is known to be zero: a split-K launch needs no memset
+  void add(const float* A, long sAm, long sAk, const float* B, long sBk, long sBn, int K) {
+    seg[nseg++] = GemmSeg{A, sAm, sAk, B, sBk, sBn, K};
+  }
+};
+// Y[n, M] = sum of X_s[n, K_s] * W[:, off_s : off_s+K_s]^T segments (+ bias) (+ LeakyReLU)
+static GemmProb prob_fwd(int n, int M, float* Y, int ldy, const float* bias, int act, float slope) {
+  GemmProb q;
+  q.M = n; q.N = M; q.C = Y; q.ldc = ldy; q.bias = bias; q.act = act; q.slope = slope;
+  return q;
+}
+static void seg_fwd(GemmProb& q, const float* X, int ldx, const float* W, int ldw, int off, int K) { q.add(X, ldx, 1, W + off, 1, ldw, K); }
+// dX[n, K] = dY[n, M] * W[:, off:off+K]   (optionally * LeakyReLU'(post))
+static GemmProb prob_dgrad(int n, int M, int K, const float* dY, int ldy, const float* W, int ldw, int off, float* dX, int ldx,
+                           const float* post = nullptr, int ld_post = 0, float slope = 0.f) {
+  GemmProb q;
+  q.M = n; q.N = K; q.C = dX; q.ldc = ldx; q.dact = post; q.ld_dact = ld_post; q.slope = slope;
+  q.add(dY, ldy, 1, W + off, ldw, 1, M);
+  return q;
+}
+// dW[:, off:off+K] = dY[n, M]^T * X[n, K]   (+ db[m] = sum_n dY[n, m] when db != nullptr)
+static GemmProb prob_wgrad(int n, int M, int K, const float* dY, int ldy, const float* X, int ldx, float* dW, int ldw, int off,
+                           float* db, bool zeroed) {
+  GemmProb q;
+  q.M = M; q.N = K; q.C = dW + off; q.ldc = ldw; q.colsum = db; q.c_zeroed = zeroed;
+  q.add(dY, 1, ldy, X, ldx, 1, n);
+  return q;
+}
+
+static int g_sm_count = 0;
+static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
+  namespace tg = b200::tg;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_TRY(cudaFuncSetAttribute(tg::tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_BYTES));
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  if (nprob < 1 || nprob > tg::MAX_PROB) return b200_fail("tgemm_group: %d problems", nprob);
+  tg::Group g;
+  memset(&g, 0, sizeof(g));
+  g.nprob = nprob;
+  int total_tiles = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const GemmProb& q = probs[i];
+    if (q.nseg < 1 || q.nseg > tg::MAX_SEG || q.M < 1 || q.N < 1) return b200_fail("tgemm_group: bad problem %d", i);
+    total_tiles += ((q.N + tg::BN - 1) / tg::BN) * ((q.M + tg::BM - 1) / tg::BM);
+  }
+  int cta = 0;
+  for (int i = 0; i < nprob; ++i) {
+    const GemmProb& q = probs[i];
+    tg::Prob& P = g.prob[i];
+    for (int s = 0; s < q.nseg; ++s) {
+      const GemmSeg& a = q.seg[s];
+      tg::Seg& S = P.seg[s];
+      S.A = a.A; S.B = a.B; S.sAm = a.sAm; S.sAk = a.sAk; S.sBk = a.sBk; S.sBn = a.sBn; S.K = a.K;
+      S.vecA = a.sAk == 1 && (a.sAm & 3) == 0 && (reinterpret_cast<uintptr_t>(a.A) & 15) == 0;
+      S.vecB = a.sBk == 1 && (a.sBn & 3) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0;
+    }
+    if (q.colsum && q.seg[0].sAk == 1) return b200_fail("tgemm_group: colsum needs a k-strided A");
+    P.C = q.C; P.bias = q.bias; P.colsum = q.colsum; P.dact = q.dact;
+    P.M = q.M; P.N = q.N; P.nseg = q.nseg; P.ldc = q.ldc; P.beta = q.beta; P.act = q.act; P.ld_dact = q.ld_dact; P.slope = q.slope;
+    P.tiles_x = (q.N + tg::BN - 1) / tg::BN;
+    P.tiles_y = (q.M + tg::BM - 1) / tg::BM;
+    // long reductions into a small output (weight gradients): split K until the launch fills the GPU about twice
+    int splits = 1;
+    const int K0 = q.seg[0].K;
+    if (q.nseg == 1 && !q.act && !q.dact && K0 >= 512) {
+      // ~8 chunks per CTA, like the CTAs of the other problems in the group; fewer splits once the launch is several waves deep
+      splits = K0 / 256;
+      while (splits > 1 && total_tiles * splits > 8 * g_sm_count) splits >>= 1;
+    }
+    int k_per = (K0 + splits - 1) / splits;
+    k_per = (k_per + tg::KC - 1) / tg::KC * tg::KC;
+    splits = (K0 + k_per - 1) / k_per;
+    P.splits = splits;
+    P.k_per = k_per;
+    P.cta_begin = cta;
+    cta += P.tiles_x * P.tiles_y * splits;
+    if (splits > 1 && !q.beta && !q.c_zeroed)
+      CUDA_TRY(cudaMemset2DAsync(q.C, static_cast<size_t>(q.ldc) * sizeof(float), 0, static_cast<size_t>(q.N) * sizeof(float), q.M, st));
+  }
+  tg::tgemm_kernel<<<cta, tg::CTA_THREADS, tg::SMEM_BYTES, st>>>(g);
+  LAUNCH_CHECK();
+  return 0;
+}
+static int tgemm(cudaStream_t st, int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBk, long sBn,
+                 float* C, int ldc, int beta, const float* bias, int act, float slope) {
+  GemmProb q;
+  q.M = M; q.N = N; q.C = C; q.ldc = ldc; q.beta = beta; q.bias = bias; q.act = act; q.slope = slope;
+  q.add(A, sAm, sAk, B, sBk, sBn, K);
+  return tgemm_group(st, &q, 1);
+}
+
 static int sgemm(cudaStream_t st, int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBk, long sBn,
                  float* C, int ldc, int beta, const float* bias = nullptr, int act = 0, float slope = 0.f) {
   if (M <= 0 || N <= 0) return 0;
+  if (tgemm_enabled() && M >= 32 && N >= 8 && K >= 8) return tgemm(st, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, bias, act, slope);
   dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
   const int blocks = static_cast<int>(grid.x * grid.y);
   if (!act && blocks < 120 && K >= 512) {
@@ -234,6 +360,7 @@ struct DnWs {             // float offsets into the workspace
   std::vector<size_t> xb[3];   // branch outputs
   std::vector<size_t> a;       // cat layer outputs (post activation)
   size_t g0, g1, g2;           // gradient scratch, [n, maxw] each
+  size_t gx[6];                // per-branch ping/pong scratch of the grouped backward
 };
 static DnWs dn_layout(const DnArch& ar, size_t n) {
   DnWs w;
@@ -251,6 +378,7 @@ static DnWs dn_layout(const DnArch& ar, size_t n) {
   w.g0 = take(n * maxw);
   w.g1 = take(n * maxw);
   w.g2 = take(n * maxw);
+  for (int i = 0; i < 6; ++i) w.gx[i] = take(n * maxw);
   w.total = o;
   return w;
 }
@@ -289,6 +417,45 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
   depthnet_encode_kernel<<<(n + 127) / 128, 128, 0, st>>>(rays_o, rays_d, n, radius, E);
   LAUNCH_CHECK();
   const int ed[3] = {63, 63, 126}, eo[3] = {0, 63, 126};
+  if (tgemm_enabled() && n >= 32) {
+    // tensor-core path: the three branches advance together (one grouped launch per layer index), Linear(cat([x, e])) is two
+    // K segments of one product, cat_layers.0 is four
+    for (int i = 0; i < ar.nb; ++i) {
+      GemmProb q[3];
+      for (int b = 0; b < 3; ++b) {
+        const float* e = E + eo[b];
+        const float* W = params[pidx_branch(ar, b, i)];
+        const int prev_w = i == 0 ? ed[b] : ar.h[i - 1];
+        const float* prev = i == 0 ? e : ws + w.xb[b][i - 1];
+        const int prev_ld = i == 0 ? 252 : ar.h[i - 1];
+        const int ldw = prev_w + ed[b];
+        q[b] = prob_fwd(n, ar.h[i], ws + w.xb[b][i], ar.h[i], params[pidx_branch(ar, b, i) + 1], 0, 0.f);
+        seg_fwd(q[b], prev, prev_ld, W, ldw, 0, prev_w);
+        seg_fwd(q[b], e, 252, W, ldw, prev_w, ed[b]);
+      }
+      if (tgemm_group(st, q, 3)) return 1;
+    }
+    const int hl = ar.h[ar.nb - 1];
+    {
+      const float* W = params[pidx_cat(ar, 0)];
+      const int ldw = 3 * hl + 252;
+      GemmProb q = prob_fwd(n, ar.c[0], ws + w.a[0], ar.c[0], params[pidx_cat(ar, 0) + 1], 1, 0.01f);
+      for (int b = 0; b < 3; ++b) seg_fwd(q, ws + w.xb[b][ar.nb - 1], hl, W, ldw, b * hl, hl);
+      seg_fwd(q, E, 252, W, ldw, 3 * hl, 252);
+      if (tgemm_group(st, &q, 1)) return 1;
+    }
+    for (int j = 1; j < ar.nc; ++j) {
+      GemmProb q = prob_fwd(n, ar.c[j], ws + w.a[j], ar.c[j], params[pidx_cat(ar, j) + 1], 1, 0.01f);
+      seg_fwd(q, ws + w.a[j - 1], ar.c[j - 1], params[pidx_cat(ar, j)], ar.c[j - 1], 0, ar.c[j - 1]);
+      if (tgemm_group(st, &q, 1)) return 1;
+    }
+    const int cl = ar.c[ar.nc - 1];
+    if (lin_fwd(st, n, 1, cl, ws + w.a[ar.nc - 1], cl, params[pidx_head(ar)], cl, 0, ws + w.t, 1, 0, params[pidx_head(ar) + 1], 0, 0.f))
+      return 1;
+    depth_head_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws + w.t, n, near_, far_, ws + w.s, out_z);
+    LAUNCH_CHECK();
+    return 0;
+  }
   for (int b = 0; b < 3; ++b) {
     const float* e = E + eo[b];
     for (int i = 0; i < ar.nb; ++i) {
@@ -350,6 +517,91 @@ extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_bra
   if (lin_wgrad(st, n, 1, cl, dt, 1, ws + w.a[ar.nc - 1], cl, grads[ph], cl, 0)) return 1;
   if (colsum(st, dt, n, 1, 1, grads[ph + 1])) return 1;
   if (lin_dgrad(st, n, 1, cl, dt, 1, params[ph], cl, 0, g, cl, 0)) return 1;
+  if (tgemm_enabled() && n >= 32) {
+    // tensor-core path.  Weight gradients are split-K sums and bias gradients column sums added atomically: zero the
+    // gradient tensors first -- one memset when the caller laid them out back to back (training.py does), else one each.
+    {
+      std::vector<size_t> numel;
+      const int ed[3] = {63, 63, 126};
+      for (int b = 0; b < 3; ++b)
+        for (int i = 0; i < ar.nb; ++i) {
+          numel.push_back(static_cast<size_t>(ar.h[i]) * ((i == 0 ? ed[b] : ar.h[i - 1]) + ed[b]));
+          numel.push_back(ar.h[i]);
+        }
+      for (int j = 0; j < ar.nc; ++j) {
+        numel.push_back(static_cast<size_t>(ar.c[j]) * (j == 0 ? 3 * hl + 252 : ar.c[j - 1]));
+        numel.push_back(ar.c[j]);
+      }
+      const size_t n_body = numel.size();   // the head's two tensors were written above
+      bool flat = true;
+      size_t total = 0;
+      for (size_t k = 0; k < n_body; ++k) {
+        if (k + 1 < n_body && grads[k + 1] != grads[k] + numel[k]) flat = false;
+        total += numel[k];
+      }
+      if (flat) {
+        CUDA_TRY(cudaMemsetAsync(grads[0], 0, total * sizeof(float), st));
+      } else {
+        for (size_t k = 0; k < n_body; ++k) CUDA_TRY(cudaMemsetAsync(grads[k], 0, numel[k] * sizeof(float), st));
+      }
+    }
+    {
+      const size_t tot = static_cast<size_t>(n) * cl;
+      leaky_bwd_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(g, ws + w.a[ar.nc - 1], tot, 0.01f);
+      LAUNCH_CHECK();
+    }
+    // cat layers: g = d(pre-activation of layer j).  One launch per layer: weight gradient (+ bias gradient from the same
+    // loads) and the input gradient, whose epilogue applies LeakyReLU' of the layer below.
+    for (int j = ar.nc - 1; j >= 1; --j) {
+      const int pc = pidx_cat(ar, j);
+      GemmProb q[2];
+      q[0] = prob_wgrad(n, ar.c[j], ar.c[j - 1], g, ar.c[j], ws + w.a[j - 1], ar.c[j - 1], grads[pc], ar.c[j - 1], 0, grads[pc + 1], true);
+      q[1] = prob_dgrad(n, ar.c[j], ar.c[j - 1], g, ar.c[j], params[pc], ar.c[j - 1], 0, g2, ar.c[j - 1], ws + w.a[j - 1], ar.c[j - 1], 0.01f);
+      if (tgemm_group(st, q, 2)) return 1;
+      float* tmp = g;
+      g = g2;
+      g2 = tmp;
+    }
+    const int ed[3] = {63, 63, 126}, eo[3] = {0, 63, 126};
+    const int pc0 = pidx_cat(ar, 0);
+    const int ldw0 = 3 * hl + 252;
+    float* cur[3];
+    float* alt[3];
+    for (int b = 0; b < 3; ++b) {
+      cur[b] = ws + w.gx[2 * b];
+      alt[b] = ws + w.gx[2 * b + 1];
+    }
+    {
+      GemmProb q[7];
+      for (int b = 0; b < 3; ++b)
+        q[b] = prob_wgrad(n, ar.c[0], hl, g, ar.c[0], ws + w.xb[b][ar.nb - 1], hl, grads[pc0], ldw0, b * hl, b == 0 ? grads[pc0 + 1] : nullptr, true);
+      q[3] = prob_wgrad(n, ar.c[0], 252, g, ar.c[0], E, 252, grads[pc0], ldw0, 3 * hl, nullptr, true);
+      for (int b = 0; b < 3; ++b) q[4 + b] = prob_dgrad(n, ar.c[0], hl, g, ar.c[0], params[pc0], ldw0, b * hl, cur[b], hl);
+      if (tgemm_group(st, q, 7)) return 1;
+    }
+    for (int i = ar.nb - 1; i >= 0; --i) {
+      GemmProb q[9];
+      int nq = 0;
+      for (int b = 0; b < 3; ++b) {
+        const float* e = E + eo[b];
+        const int pb = pidx_branch(ar, b, i);
+        const int prev_w = i == 0 ? ed[b] : ar.h[i - 1];
+        const float* prev = i == 0 ? e : ws + w.xb[b][i - 1];
+        const int prev_ld = i == 0 ? 252 : ar.h[i - 1];
+        const int ldw = prev_w + ed[b];
+        q[nq++] = prob_wgrad(n, ar.h[i], prev_w, cur[b], ar.h[i], prev, prev_ld, grads[pb], ldw, 0, grads[pb + 1], true);
+        q[nq++] = prob_wgrad(n, ar.h[i], ed[b], cur[b], ar.h[i], e, 252, grads[pb], ldw, prev_w, nullptr, true);
+        if (i > 0) q[nq++] = prob_dgrad(n, ar.h[i], ar.h[i - 1], cur[b], ar.h[i], params[pb], ldw, 0, alt[b], ar.h[i - 1]);
+      }
+      if (tgemm_group(st, q, nq)) return 1;
+      for (int b = 0; b < 3; ++b) {
+        float* t = cur[b];
+        cur[b] = alt[b];
+        alt[b] = t;
+      }
+    }
+    return 0;
+  }
   // cat layers, last to first: g holds d(post-activation output of layer j)
   for (int j = ar.nc - 1; j >= 0; --j) {
     const size_t tot = static_cast<size_t>(n) * ar.c[j];
@@ -601,6 +853,21 @@ extern "C" int b200nerf_adam_step(float* param, const float* grad, float* exp_av
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
   adam_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- diagnostics
+/* The strided GEMM of the training slice (tensor-core 3xTF32 path unless B200NERF_TRAIN_GEMM=fp32, or force_fp32 != 0),
+   exposed so that a GPU test can pin it against torch on every operand layout the training passes use. */
+extern "C" int b200nerf_debug_sgemm(int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBk, long sBn, float* C,
+                                    int ldc, int beta, const float* bias, int act, float slope, int force_fp32, void* stream) {
+  if (!A || !B || !C || M < 0 || N < 0 || K < 0) return b200_fail("b200nerf_debug_sgemm: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!force_fp32) return sgemm(st, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, bias, act, slope);
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
+  sgemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, bias, act, slope);
   LAUNCH_CHECK();
   return 0;
 }

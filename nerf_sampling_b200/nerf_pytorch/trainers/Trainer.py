@@ -101,8 +101,10 @@ class Trainer:
         loss = img_loss
         psnr = nerf_utils.run_nerf_helpers.mse2psnr(img_loss)
         depth_net_loss = F.mse_loss(extras["depth_net_z_vals"], extras["max_z_vals"])
-        depth_net_loss.backward(retain_graph=True)
-        loss.backward()
+        # The reference calls depth_net_loss.backward(retain_graph=True) and then loss.backward() (Trainer.py:537-538): the
+        # parameter gradients are the sum of the two.  One backward over both roots gives the same sum with ONE pass through
+        # DepthNet's backward (autograd adds the two d/dz contributions before it reaches DepthNetTrainFn).
+        torch.autograd.backward([depth_net_loss, loss])
         return loss, depth_net_loss, psnr, None
 
     def reduce_and_step(self, sampling_optimizer):

@@ -55,6 +55,17 @@ def allreduce_gradients(params, group=None) -> float:
     if world == 1:
         return 1.0
     grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 1.0 / world
+    # training.DepthNetTrainFn lays the gradients out back to back in one buffer: reduce it in place
+    sp = grads[0].untyped_storage().data_ptr()
+    back_to_back = all(g.is_contiguous() and g.dtype == grads[0].dtype and g.untyped_storage().data_ptr() == sp for g in grads) and all(
+        b.data_ptr() == a.data_ptr() + a.numel() * a.element_size() for a, b in zip(grads, grads[1:]))
+    if back_to_back:
+        total = sum(g.numel() for g in grads)
+        flat = torch.as_strided(grads[0], (total,), (1,), grads[0].storage_offset())
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / world
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     off = 0

@@ -73,7 +73,13 @@ class DepthNetTrainFn(torch.autograd.Function):
         hidden, cat = ctx.arch
         L = _lib.lib()
         dz = dz.contiguous().float()
-        grads = [torch.empty_like(p) for p in params]
+        # one flat buffer, parameter order: the C side zeroes it with a single memset (its split-K weight gradients and bias
+        # gradients are atomic sums) and parallel.allreduce_gradients reduces it in place without a cat / copy-back
+        flat = torch.empty(sum(p.numel() for p in params), device=dz.device)
+        grads, off = [], 0
+        for p in params:
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
         with torch.cuda.device(dz.device):
             _lib.check(L.b200nerf_depthnet_train_bwd(_ptrs(list(params)), len(hidden), _ints(hidden), len(cat), _ints(cat), ctx.n,
                                                      ctx.nf[0], ctx.nf[1], ctx.ws.data_ptr(), dz.data_ptr(), _ptrs(grads), _stream()))

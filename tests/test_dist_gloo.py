@@ -73,6 +73,11 @@ def _grad_worker(rank, world, port, q):
     scale = allreduce_gradients(params)
     ok = (scale == 0.5 and torch.equal(params[0].grad, torch.full((3, 5), 3.0)) and torch.equal(params[1].grad, torch.full((7,), 6.0))
           and params[2].grad is None)
+    # gradients laid out back to back in one buffer (what training.DepthNetTrainFn.backward produces): reduced in place
+    flat = torch.arange(22, dtype=torch.float32) * (rank + 1)
+    params[0].grad, params[1].grad = flat[:15].view(3, 5), flat[15:22]
+    scale = allreduce_gradients(params)
+    ok = ok and scale == 0.5 and torch.equal(flat, torch.arange(22, dtype=torch.float32) * 3) and params[0].grad.data_ptr() == flat.data_ptr()
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()

@@ -41,6 +41,52 @@ def test_umma_selftest(lib, K, N):
     assert float((d.double() - want).abs().max()) < 1e-3 * max(1.0, float(want.abs().max()))
 
 
+def _debug_sgemm(lib, M, N, K, A, sAm, sAk, B, sBk, sBn, C, ldc, beta, bias, act, slope, force_fp32):
+    from nerf_sampling_b200 import _lib
+
+    _lib.check(lib.b200nerf_debug_sgemm(M, N, K, A.data_ptr(), sAm, sAk, B.data_ptr(), sBk, sBn, C.data_ptr(), ldc, beta,
+                                        None if bias is None else bias.data_ptr(), act, slope, force_fp32,
+                                        torch.cuda.current_stream().cuda_stream))
+
+
+@pytest.mark.parametrize("n", [4096, 200, 37])
+def test_training_gemm_3xtf32_all_layouts(lib, n):
+    """csrc/tgemm.cuh (tcgen05 kind::tf32, hi/lo split) on the three operand layouts of the training passes (Linear forward
+    with a column offset into W and beta / bias / LeakyReLU, input gradient, split-K weight gradient) against fp64 torch;
+    the error must be fp32-grade: within 6x of the CUDA-core fp32 kernel's own rounding error (or 4e-6 of the output scale)."""
+    g = torch.Generator().manual_seed(n)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(DEV)  # noqa: E731
+    for (M_out, K_in, off, ldw) in ((256, 252, 63, 400), (256, 63, 0, 126), (128, 256, 0, 256), (70, 126, 126, 252 + 7)):
+        X, W, bias, Y0 = rnd(n, 300)[:, :K_in], rnd(M_out, ldw), rnd(M_out), rnd(n, M_out)
+        # forward: Y = Y0 + X W[:, off:off+K]^T + b, LeakyReLU
+        want = torch.nn.functional.leaky_relu((Y0.double() + X.double() @ W[:, off:off + K_in].double().T + bias.double()), 0.01)
+        errs = []
+        for force in (0, 1):
+            Y = Y0.clone()
+            _debug_sgemm(lib, n, M_out, K_in, X, X.stride(0), 1, W[:, off:], 1, ldw, Y, M_out, 1, bias, 1, 0.01, force)
+            errs.append(float((Y.double() - want).abs().max()))
+        scale = float(want.abs().max())
+        assert errs[0] <= max(6 * errs[1], 4e-6 * scale), ("fwd", M_out, K_in, errs)
+        # input gradient: dX = dY W[:, off:off+K]
+        dY = rnd(n, M_out)
+        want = dY.double() @ W[:, off:off + K_in].double()
+        errs = []
+        for force in (0, 1):
+            dX = torch.full((n, K_in), 7.0, device=DEV)
+            _debug_sgemm(lib, n, K_in, M_out, dY, M_out, 1, W[:, off:], ldw, 1, dX, K_in, 0, None, 0, 0.0, force)
+            errs.append(float((dX.double() - want).abs().max()))
+        assert errs[0] <= max(6 * errs[1], 4e-6 * float(want.abs().max())), ("dgrad", M_out, K_in, errs)
+        # weight gradient into a column block of dW: dW[:, off:off+K] = dY^T X (long reduction over the rays: split K)
+        want = dY.double().T @ X.double()
+        errs = []
+        for force in (0, 1):
+            dW = torch.full((M_out, ldw), 3.0, device=DEV)
+            _debug_sgemm(lib, M_out, K_in, n, dY, 1, M_out, X, X.stride(0), 1, dW[:, off:], ldw, 0, None, 0, 0.0, force)
+            errs.append(float((dW[:, off:off + K_in].double() - want).abs().max()))
+            assert bool((dW[:, :off] == 3.0).all()) and bool((dW[:, off + K_in:] == 3.0).all())  # neighbours untouched
+        assert errs[0] <= max(6 * errs[1], 4e-6 * float(want.abs().max())), ("wgrad", M_out, K_in, errs)
+
+
 # --------------------------------------------------------------------------------------------- small operators
 def test_get_rays_matches_oracle(lib):
     from nerf_sampling_b200 import ops
