@@ -252,6 +252,10 @@ int b200nerf_umma_selftest(const uint16_t* A, const uint16_t* B, float* D, int K
 int b200nerf_debug_sgemm(int M, int N, int K, const float* A, long sAm, long sAk, const float* B, long sBk, long sBn, float* C,
                          int ldc, int beta, const float* bias, int act, float slope, int force_fp32, void* stream);
 
+/* Diagnostics: CTA 0 of every grouped-GEMM launch writes %globaltimer stamps (ns) of its phases into dev_buf (16 int64):
+ * [0] entry, [1] barriers + TMEM ready, [2] last MMA retired, [3] epilogue stored, [4+c] chunk c handed to the MMA warp. */
+void b200nerf_debug_set_tgemm_timeline(long long* dev_buf);
+
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 unsigned long long b200nerf_launch_count(void);
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "b200nerf_sample_pdf_merge": (I, [P, P, P, I, I, I, I, P, P, P, P]),
     "b200nerf_argmax_gather": (I, [P, P, P, I, I, P, P, P, P, P]),
     "b200nerf_umma_selftest": (I, [P, P, P, I, I, P]),
+    "b200nerf_debug_set_tgemm_timeline": (None, [P]),
     "b200nerf_debug_sgemm": (I, [I, I, I, P, C.c_long, C.c_long, P, C.c_long, C.c_long, P, I, I, P, I, F, I, P]),
     "b200nerf_depthnet_train_ws_floats": (SZ, [I, I, P, I, P]),
     "b200nerf_depthnet_n_params": (I, [I, I]),

@@ -64,6 +64,7 @@ struct Prob {
 };
 struct Group {
   int nprob;
+  long long* dbg;   // diagnostics: CTA 0 writes %globaltimer stamps of its phases here (null in normal use)
   Prob prob[MAX_PROB];
 };
 static_assert(sizeof(Group) <= 4000, "kernel parameter space");
@@ -71,6 +72,11 @@ static_assert(sizeof(Group) <= 4000, "kernel parameter space");
 // kind::tf32 instruction descriptor: D = f32, A = B = TF32 (format 2), both K-major
 __host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -132,6 +138,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
   uint8_t* smem = tg_smem_ + ((128u - (smem_u32(tg_smem_) & 127u)) & 127u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  const bool stamp = g.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamp) g.dbg[0] = gtimer();
   int pi = 0;
   while (pi + 1 < g.nprob && static_cast<int>(blockIdx.x) >= g.prob[pi + 1].cta_begin) ++pi;
   const Prob& P = g.prob[pi];
@@ -200,6 +208,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
   }
 
   // ---- loader warps
+  if (stamp) g.dbg[1] = gtimer();
   float va[QA][4], vb[QB][4];
   bool a_kfast, b_kfast;
   auto prefetch = [&]() {   // loads chunk (cs, ck) into registers and advances the walk
@@ -235,6 +244,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(&full[s]);
+    if (stamp && c < 12) g.dbg[4 + c] = gtimer();
   }
 
   if (P.colsum) {   // k-strided A: a thread's quads all belong to row (tid & 127)
@@ -246,37 +256,87 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
   const int last = nchunks - 1;
   mbar_wait(&mma_done[last & 1], static_cast<uint32_t>(last >> 1) & 1u);
   tc_fence_after();
+  if (stamp) g.dbg[2] = gtimer();
 
-  // epilogue: warp w reads TMEM lanes 32*(w&3).. (its sub-partition) and columns 32*(w>>2)..
+  // epilogue: warp w reads TMEM lanes 32*(w&3).. (its sub-partition) and columns 32*(w>>2).. and parks them in shared memory
+  // (both operand stages are free: every MMA has retired) as a [128][64 + 4] fp32 tile, so that the global pass below
+  // runs along rows: 16 lanes x float4 = one 256-byte row segment.  Thread-per-row stores straight from TMEM cost 6.8 us of a
+  // 15 us CTA (4-byte writes to 32 different rows per instruction: 8x the L2 sector operations).
   {
-    const int lq = warp & 3, ch = warp >> 2;
-    const int gm = m0 + lq * 32 + lane;
-    const int gn0 = n0 + ch * 32;
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + static_cast<uint32_t>(ch * 32), v);
-    tmem_ld_wait();
-    if (gm < P.M) {
-      float* crow = P.C + static_cast<size_t>(gm) * P.ldc;
-      const float* drow = P.dact ? P.dact + static_cast<size_t>(gm) * P.ld_dact : nullptr;
+    constexpr int TLD = BN + 4;   // floats per tile row: 272 B keeps the float4 stores of 32 rows conflict-free
+    float* tile = reinterpret_cast<float*>(smem);
+    {
+      const int lq = warp & 3, ch = warp >> 2;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lq * 32) << 16) + static_cast<uint32_t>(ch * 32), v);
+      tmem_ld_wait();
+      float* trow = tile + (lq * 32 + lane) * TLD + ch * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int gn = gn0 + j;
-        if (gn < P.N) {
-          float x = __uint_as_float(v[j]);
-          if (split) {
-            if (P.bias && sz == 0) x += __ldg(P.bias + gn);
-            atomicAdd(crow + gn, x);
-          } else {
-            if (P.beta) x += crow[gn];
-            if (P.bias) x += __ldg(P.bias + gn);
-            if (P.act) x = x > 0.f ? x : x * P.slope;
-            if (drow) x = __ldg(drow + gn) > 0.f ? x : x * P.slope;
-            crow[gn] = x;
-          }
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(trow + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+    named_bar_sync(1, THREADS);
+    const bool vec_c = (P.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(P.C) & 15) == 0 && !split;
+    const bool vec_d = P.dact && (P.ld_dact & 3) == 0 && (reinterpret_cast<uintptr_t>(P.dact) & 15) == 0;
+#pragma unroll 2
+    for (int it = 0; it < BM * (BN / 4) / THREADS; ++it) {
+      const int idx = tid + it * THREADS;
+      const int row = idx >> 4, c4 = (idx & 15) * 4;
+      const int gm = m0 + row, gn = n0 + c4;
+      if (gm >= P.M || gn >= P.N) continue;
+      const float4 t4 = *reinterpret_cast<const float4*>(tile + row * TLD + c4);
+      float x[4] = {t4.x, t4.y, t4.z, t4.w};
+      float* crow = P.C + static_cast<size_t>(gm) * P.ldc + gn;
+      const bool full4 = gn + 3 < P.N;
+      if (split) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gn + j < P.N) atomicAdd(crow + j, (P.bias && sz == 0) ? x[j] + __ldg(P.bias + gn + j) : x[j]);
+        continue;
+      }
+      if (P.beta) {
+        if (full4 && vec_c) {
+          const float4 c4v = *reinterpret_cast<const float4*>(crow);
+          x[0] += c4v.x; x[1] += c4v.y; x[2] += c4v.z; x[3] += c4v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (gn + j < P.N) x[j] += crow[j];
         }
+      }
+      if (P.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gn + j < P.N) x[j] += __ldg(P.bias + gn + j);
+      }
+      if (P.act) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = x[j] > 0.f ? x[j] : x[j] * P.slope;
+      }
+      if (P.dact) {
+        const float* drow = P.dact + static_cast<size_t>(gm) * P.ld_dact + gn;
+        float d[4] = {1.f, 1.f, 1.f, 1.f};
+        if (full4 && vec_d) {
+          const float4 d4 = __ldg(reinterpret_cast<const float4*>(drow));
+          d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (gn + j < P.N) d[j] = __ldg(drow + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = d[j] > 0.f ? x[j] : x[j] * P.slope;
+      }
+      if (full4 && vec_c) {
+        *reinterpret_cast<float4*>(crow) = make_float4(x[0], x[1], x[2], x[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gn + j < P.N) crow[j] = x[j];
       }
     }
   }
+  if (stamp) g.dbg[3] = gtimer();
   tc_fence_before();
   __syncthreads();   // pairs with the MMA warp's: it frees the accumulator after every epilogue warp has read it
 }

@@ -153,6 +153,9 @@ static GemmProb prob_wgrad(int n, int M, int K, const float* dY, int ldy, const 
 }
 
 static int g_sm_count = 0;
+static long long* g_tgemm_dbg = nullptr;
+/* diagnostics: device buffer of 16 int64; CTA 0 of every grouped-GEMM launch writes its phase time stamps (ns) there */
+extern "C" void b200nerf_debug_set_tgemm_timeline(long long* dev_buf) { g_tgemm_dbg = dev_buf; }
 static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
   namespace tg = b200::tg;
   static bool configured = false;
@@ -167,11 +170,10 @@ static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
   tg::Group g;
   memset(&g, 0, sizeof(g));
   g.nprob = nprob;
-  int total_tiles = 0;
+  g.dbg = g_tgemm_dbg;
   for (int i = 0; i < nprob; ++i) {
     const GemmProb& q = probs[i];
     if (q.nseg < 1 || q.nseg > tg::MAX_SEG || q.M < 1 || q.N < 1) return b200_fail("tgemm_group: bad problem %d", i);
-    total_tiles += ((q.N + tg::BN - 1) / tg::BN) * ((q.M + tg::BM - 1) / tg::BM);
   }
   int cta = 0;
   for (int i = 0; i < nprob; ++i) {
@@ -193,9 +195,11 @@ static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
     int splits = 1;
     const int K0 = q.seg[0].K;
     if (q.nseg == 1 && !q.act && !q.dact && K0 >= 512) {
-      // ~8 chunks per CTA, like the CTAs of the other problems in the group; fewer splits once the launch is several waves deep
+      // ~8 chunks per CTA, like the CTAs of the other problems in the group: a CTA that walks the whole reduction would be
+      // the launch's tail (ncu: SMs idle 55 % of a backward group when the weight-gradient CTAs had 64 chunks each)
       splits = K0 / 256;
-      while (splits > 1 && total_tiles * splits > 8 * g_sm_count) splits >>= 1;
+      const int own_tiles = P.tiles_x * P.tiles_y;
+      while (splits > 1 && own_tiles * splits > 4 * g_sm_count) splits >>= 1;
     }
     int k_per = (K0 + splits - 1) / splits;
     k_per = (k_per + tg::KC - 1) / tg::KC * tg::KC;
