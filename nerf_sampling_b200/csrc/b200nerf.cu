@@ -605,6 +605,28 @@ __global__ void place_uniform_kernel(const float* __restrict__ mean, const float
   z[idx] = v;
 }
 
+// The same for S % 4 == 0: one thread writes four consecutive samples as a float4 (32-bit index arithmetic, a quarter of
+// the threads); the one-element kernel above ran at ~1 TB/s of the 4*S + 4 B per ray it moves.
+__global__ void __launch_bounds__(256) place_uniform_vec4_kernel(const float* __restrict__ mean, const float* __restrict__ grid,
+                                                                 int n_rays, int S, float lo, float hi, float* __restrict__ z) {
+  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
+  const unsigned qpr = static_cast<unsigned>(S) >> 2;         // float4s per ray
+  const unsigned ray = q / qpr;
+  if (ray >= static_cast<unsigned>(n_rays)) return;
+  const int s0 = static_cast<int>(q - ray * qpr) * 4;
+  const float m = __ldg(mean + ray);
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int s = s0 + i;
+    float x = m;
+    if (s <= S - 2 && __ldg(grid + s) < 0.f) x = __fadd_rn(m, __ldg(grid + s));
+    else if (s >= 1 && !(__ldg(grid + s - 1) < 0.f)) x = __fadd_rn(m, __ldg(grid + s - 1));
+    v[i] = x < lo ? lo : (x > hi ? hi : x);
+  }
+  reinterpret_cast<float4*>(z)[q] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // Gaussian mode: one warp sorts one ray's S values (bitonic network over a power-of-two padded row in smem).
 __global__ void place_sorted_kernel(const float* __restrict__ mean, const float* __restrict__ offs, int n_rays, int S,
                                     int P /*pow2 >= S*/, float* __restrict__ z) {
@@ -653,7 +675,10 @@ extern "C" int b200nerf_place_samples(const float* mean, const float* offsets, i
   }
   if (S > 1 && !offsets) return fail("b200nerf_place_samples: offsets is null");
   if (mode == B200NERF_PLACE_UNIFORM) {
-    place_uniform_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(mean, offsets, n_rays, S, clip_lo, clip_hi, out_z);
+    if ((S & 3) == 0 && (reinterpret_cast<uintptr_t>(out_z) & 15) == 0 && total / 4 < 0x7fffff00ull)
+      place_uniform_vec4_kernel<<<static_cast<unsigned>((total / 4 + 255) / 256), 256, 0, st>>>(mean, offsets, n_rays, S, clip_lo, clip_hi, out_z);
+    else
+      place_uniform_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(mean, offsets, n_rays, S, clip_lo, clip_hi, out_z);
     LAUNCH_CHECK();
     return 0;
   }

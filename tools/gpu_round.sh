@@ -15,7 +15,7 @@ python tools/profile_step.py > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"nerf_fast|composite|mlp_exact" -c 8 -f -o gpurun_out/prof_step python tools/profile_step.py > gpurun_out/ncu_step.log 2>&1
 echo "ncu step rc=$?" | tee -a gpurun_out/summary.txt
 timeout 300 python tools/bench_hierarchical.py 5 > gpurun_out/bench_hier.json 2> gpurun_out/bench_hier.err; echo "bench hierarchical rc=$?" | tee -a gpurun_out/summary.txt
-timeout 300 python tools/bench_train.py 20 > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err; echo "bench train rc=$?" | tee -a gpurun_out/summary.txt
+(timeout 300 python tools/bench_train.py 30; timeout 300 python tools/bench_train.py 30 --graph; B200NERF_TRAIN_GEMM=fp32 timeout 300 python tools/bench_train.py 30) > gpurun_out/bench_train.json 2> gpurun_out/bench_train.err; echo "bench train rc=$?" | tee -a gpurun_out/summary.txt
 (timeout 300 python tools/profile_composite.py 64; B200NERF_COMPOSITE_LDG=1 timeout 300 python tools/profile_composite.py 64; timeout 300 python tools/profile_composite.py 32; timeout 300 python tools/profile_composite.py 128) > gpurun_out/bench_composite.txt 2>&1; echo "composite rc=$?" | tee -a gpurun_out/summary.txt
 timeout 300 python tools/train_breakdown.py 4096 > gpurun_out/train_breakdown.txt 2>&1; echo "train breakdown rc=$?" | tee -a gpurun_out/summary.txt
 tail -n 4 gpurun_out/t_gpu.log gpurun_out/smoke.log
