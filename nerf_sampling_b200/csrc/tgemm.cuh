@@ -33,11 +33,13 @@ namespace tg {
 
 constexpr int BM = 128, BN = 64, KC = 32, THREADS = 256;   // THREADS = the loader / epilogue warps
 constexpr int CTA_THREADS = THREADS + 32;                   // + one warp that owns TMEM and issues the MMAs
-constexpr int LBO_A = BM * 16 + 16;            // bytes between consecutive k-quads (4 TF32 = 16 B) of the A plane
-constexpr int LBO_B = BN * 16 + 16;
-constexpr int PLANE_A = (KC / 4) * LBO_A;      // 16,512 B
-constexpr int PLANE_B = (KC / 4) * LBO_B;      //  8,320 B
-constexpr int STAGE_BYTES = 2 * PLANE_A + 2 * PLANE_B;   // hi + lo of both operands: 49,664 B
+constexpr int SBO = 144;                       // bytes between 8-row groups: 128 + 16, so that stores of rows 4l..4l+3 (the
+                                               // 4 x 4 micro-tile mapping) and of consecutive rows both spread over all bank groups
+constexpr int LBO_A = (BM / 8) * SBO + 16;     // bytes between consecutive k-quads (4 TF32 = 16 B) of the A plane: 2,320
+constexpr int LBO_B = (BN / 8) * SBO + 16;     // 1,168
+constexpr int PLANE_A = (KC / 4) * LBO_A;      // 18,560 B
+constexpr int PLANE_B = (KC / 4) * LBO_B;      //  9,344 B
+constexpr int STAGE_BYTES = 2 * PLANE_A + 2 * PLANE_B;   // hi + lo of both operands: 55,808 B
 constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 128;
 constexpr uint32_t TMEM_COLS = 64;
 constexpr int MAX_SEG = 4, MAX_PROB = 9;
@@ -89,52 +91,128 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
-// R rows x KC k of one operand into registers: element (row, k) = src[row*srow + k*sk]; rows >= row_lim, k >= k_end -> 0.
-template <int R, int Q>
-__device__ __forceinline__ void load_quads(const float* __restrict__ src, long srow, long sk, int row0, int row_lim, int k0, int k_end,
-                                           int vec, int tid, float (&v)[Q][4]) {
-#pragma unroll
-  for (int i = 0; i < Q; ++i) {
-    const int qi = tid + i * THREADS;
-    int r, kq;
-    if (sk == 1) { r = qi >> 3; kq = qi & 7; } else { r = qi & (R - 1); kq = qi / R; }   // lanes along the contiguous dimension
-    const int gr = row0 + r, gk = k0 + kq * 4;
-    const float* s = src + gr * srow + gk * sk;
-    if (gr < row_lim && vec && gk + 3 < k_end) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(s));
-      v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+__device__ __forceinline__ int row_off(int r) { return (r & 7) * 16 + (r >> 3) * SBO; }
+
+// Per-thread loader of one operand (R rows x KC k per chunk, Q k-quads per thread).  Four mappings, chosen per segment
+// (CTA-uniform) from the operand's strides and alignment:
+//   KVEC    k contiguous, rows 16-byte aligned: quad (row, kq) = one LDG.128; 8 lanes cover one row's 128 bytes
+//   KSCALAR k contiguous, unaligned: the same quads, four LDG.32 each
+//   RVEC    rows contiguous (k strided), aligned, full tile (A only): a 4 rows x 4 k micro-tile per thread -- four LDG.128, each
+//           a fully coalesced 512-byte warp access -- transposed in registers into the quads of rows 4*lane .. 4*lane+3
+//   RSCALAR rows contiguous otherwise: lanes along rows, four LDG.32 per quad
+// Interior tiles (all rows valid, whole chunk inside the K range) take a path without any bounds arithmetic: the pointer of
+// quad 0 and the constant stride to the thread's next quads are set up once per segment and advanced by one add per chunk.
+// (The first version recomputed rows, bounds and 64-bit addresses per element and chunk: ~450 instructions per thread
+// and chunk, which made the kernel issue-bound -- ncu: 48 % issue-active with the tensor pipe at 9 %.)
+enum : int { KVEC = 0, KSCALAR = 1, RVEC = 2, RSCALAR = 3 };
+
+template <int R, int Q, int LBO>
+struct OpLoader {
+  const float* p0;   // quad 0 at the current chunk
+  const float* src;  // segment base (generic path)
+  long qstride;      // elements between this thread's consecutive quads
+  long sk, srow;
+  int off0, offstride;   // shared-memory byte offset of quad 0, stride to the next quads
+  int mode, row0, row_lim, rows_full;
+
+  __device__ __forceinline__ void setup(const float* base, long srow_, long sk_, int vec, int row0_, int row_lim_, int k0, int tid,
+                                        bool allow_rvec) {
+    src = base; srow = srow_; sk = sk_; row0 = row0_; row_lim = row_lim_;
+    rows_full = row0_ + R <= row_lim_;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (sk_ == 1) {
+      mode = vec ? KVEC : KSCALAR;
+      const int r = tid >> 3, kq = tid & 7;                   // quad i: row r + 32 i
+      p0 = base + (row0_ + r) * srow_ + (k0 + kq * 4);
+      qstride = 32 * srow_;
+      off0 = row_off(r) + kq * LBO;
+      offstride = 4 * SBO;
+    } else if (allow_rvec && Q == 4 && R == 128 && srow_ == 1 && (sk_ & 3) == 0 && rows_full &&
+               ((reinterpret_cast<uintptr_t>(base + row0_) & 15) == 0)) {
+      mode = RVEC;                                             // quad i: row 4 lane + i, kq = warp
+      p0 = base + (row0_ + 4 * lane) + (k0 + warp * 4) * sk_;
+      qstride = 0;
+      off0 = row_off(4 * lane) + warp * LBO;
+      offstride = 16;
     } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[i][j] = (gr < row_lim && gk + j < k_end) ? __ldg(s + j * sk) : 0.f;
+      mode = RSCALAR;
+      const int r = tid & (R - 1), kq = tid / R;               // quad i: kq + (THREADS / R) i
+      p0 = base + (row0_ + r) * srow_ + (k0 + kq * 4) * sk_;
+      qstride = (THREADS / R) * 4 * sk_;
+      off0 = row_off(r) + kq * LBO;
+      offstride = (THREADS / R) * LBO;
     }
   }
-}
-// hi / lo split and 16-byte stores into the UMMA planes; `kfast` = the mapping load_quads used (sk == 1)
-template <int R, int Q>
-__device__ __forceinline__ void split_store(const float (&v)[Q][4], bool kfast, uint8_t* hi_plane, uint8_t* lo_plane, int lbo, int tid) {
+
+  // chunk [k0, k0 + KC) of the segment, valid k < k_end
+  __device__ __forceinline__ void load(float (&v)[Q][4], int k0, int k_end, int tid) {
+    if (mode == RVEC) {
+      const int kb = k0 + (tid >> 5) * 4;
+      float4 t[4];
 #pragma unroll
-  for (int i = 0; i < Q; ++i) {
-    const int qi = tid + i * THREADS;
-    int r, kq;
-    if (kfast) { r = qi >> 3; kq = qi & 7; } else { r = qi & (R - 1); kq = qi / R; }
-    const int off = r * 16 + kq * lbo;
-    uint32_t h[4], l[4];
+      for (int kk = 0; kk < 4; ++kk)
+        t[kk] = kb + kk < k_end ? __ldg(reinterpret_cast<const float4*>(p0 + kk * sk)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      h[j] = __float_as_uint(v[i][j]) & 0xffffe000u;
-      l[j] = __float_as_uint(v[i][j] - __uint_as_float(h[j]));
+      for (int kk = 0; kk < 4; ++kk) {
+        v[0 % Q][kk] = t[kk].x; v[1 % Q][kk] = t[kk].y; v[2 % Q][kk] = t[kk].z; v[3 % Q][kk] = t[kk].w;
+      }
+    } else if (rows_full && k0 + KC <= k_end) {
+      if (mode == KVEC) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(p0 + i * qstride));
+          v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+        }
+      } else if (mode == KSCALAR) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[i][j] = __ldg(p0 + i * qstride + j);
+      } else {
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[i][j] = __ldg(p0 + i * qstride + j * sk);
+      }
+    } else {
+      // edge tile / tail chunk: bounds-checked, same quad mapping
+#pragma unroll
+      for (int i = 0; i < Q; ++i) {
+        const int qi = tid + i * THREADS;
+        int r, kq;
+        if (sk == 1) { r = qi >> 3; kq = qi & 7; } else { r = qi & (R - 1); kq = qi / R; }
+        const int gr = row0 + r, gk = k0 + kq * 4;
+        const float* s = src + gr * srow + gk * sk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] = (gr < row_lim && gk + j < k_end) ? __ldg(s + j * sk) : 0.f;
+      }
     }
-    *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    p0 += KC * sk;
   }
-}
+
+  // hi / lo split and 16-byte stores into the UMMA planes
+  __device__ __forceinline__ void store(const float (&v)[Q][4], uint8_t* hi_plane, uint8_t* lo_plane) const {
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const int off = off0 + i * offstride;
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        h[j] = __float_as_uint(v[i][j]) & 0xffffe000u;
+        l[j] = __float_as_uint(v[i][j] - __uint_as_float(h[j]));
+      }
+      *reinterpret_cast<uint4*>(hi_plane + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(lo_plane + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+};
 
 __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_constant__ Group g) {
   extern __shared__ __align__(128) uint8_t tg_smem_[];
   __shared__ uint64_t mma_done[2];   // stage s: its MMAs have retired (tcgen05.commit)
   __shared__ uint64_t full[2];       // stage s: all eight loader warps have stored (and proxy-fenced) their quads
   __shared__ uint32_t tmem_slot;
-  __shared__ float colsum_red[THREADS];
+  __shared__ float colsum_red[BM];
   uint8_t* smem = tg_smem_ + ((128u - (smem_u32(tg_smem_) & 127u)) & 127u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -189,10 +267,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < KC / 8; ++j) {
           // one K8 step = two k-quads of each plane
-          const uint64_t dah = umma_desc_kmajor(a_hi + j * 2 * LBO_A, LBO_A, 128);
-          const uint64_t dal = umma_desc_kmajor(a_lo + j * 2 * LBO_A, LBO_A, 128);
-          const uint64_t dbh = umma_desc_kmajor(b_hi + j * 2 * LBO_B, LBO_B, 128);
-          const uint64_t dbl = umma_desc_kmajor(b_lo + j * 2 * LBO_B, LBO_B, 128);
+          const uint64_t dah = umma_desc_kmajor(a_hi + j * 2 * LBO_A, LBO_A, SBO);
+          const uint64_t dal = umma_desc_kmajor(a_lo + j * 2 * LBO_A, LBO_A, SBO);
+          const uint64_t dbh = umma_desc_kmajor(b_hi + j * 2 * LBO_B, LBO_B, SBO);
+          const uint64_t dbl = umma_desc_kmajor(b_lo + j * 2 * LBO_B, LBO_B, SBO);
           mma_tf32(tmem_base, dal, dbh, idesc, (c > 0 || j > 0) ? 1u : 0u);
           mma_tf32(tmem_base, dah, dbl, idesc, 1u);
           mma_tf32(tmem_base, dah, dbh, idesc, 1u);
@@ -210,22 +288,35 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
   // ---- loader warps
   if (stamp) g.dbg[1] = gtimer();
   float va[QA][4], vb[QB][4];
-  bool a_kfast, b_kfast;
-  auto prefetch = [&]() {   // loads chunk (cs, ck) into registers and advances the walk
+  OpLoader<BM, QA, LBO_A> la;
+  OpLoader<BN, QB, LBO_B> lb;
+  auto open_segment = [&]() {
     const Seg& S = P.seg[cs];
-    a_kfast = S.sAk == 1;
-    b_kfast = S.sBk == 1;
-    load_quads<BM, QA>(S.A, S.sAm, S.sAk, m0, P.M, ck, ce, S.vecA, tid, va);
-    load_quads<BN, QB>(S.B, S.sBn, S.sBk, n0, P.N, ck, ce, S.vecB, tid, vb);
+    la.setup(S.A, S.sAm, S.sAk, S.vecA, m0, P.M, ck, tid, true);
+    lb.setup(S.B, S.sBn, S.sBk, S.vecB, n0, P.N, ck, tid, false);
+  };
+  int a_mode;   // the mapping of the chunk held in va (the segment may change under it)
+  int a_off0, a_offstride, b_off0, b_offstride;
+  auto prefetch = [&]() {   // loads chunk (cs, ck) into registers and advances the walk
+    a_mode = la.mode;
+    a_off0 = la.off0; a_offstride = la.offstride; b_off0 = lb.off0; b_offstride = lb.offstride;
+    la.load(va, ck, ce, tid);
+    lb.load(vb, ck, ce, tid);
     ck += KC;
     if (ck >= ce && !split && cs + 1 < P.nseg) {
       ++cs;
       ck = 0;
       ce = P.seg[cs].K;
+      open_segment();
     }
   };
+  if (P.colsum) {
+    for (int i = tid; i < BM; i += THREADS) colsum_red[i] = 0.f;
+    named_bar_sync(1, THREADS);
+  }
+  open_segment();
   prefetch();
-  float csum = 0.f;
+  float csum[4] = {0.f, 0.f, 0.f, 0.f};
 
   for (int c = 0; c < nchunks; ++c) {
     const int s = c & 1;
@@ -234,11 +325,20 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
     uint8_t* b_hi = a_lo + PLANE_A;
     uint8_t* b_lo = b_hi + PLANE_B;
     if (c >= 2) mbar_wait(&mma_done[s], static_cast<uint32_t>((c >> 1) - 1) & 1u);   // the MMAs that read this stage have retired
-    split_store<BM, QA>(va, a_kfast, a_hi, a_lo, LBO_A, tid);
-    split_store<BN, QB>(vb, b_kfast, b_hi, b_lo, LBO_B, tid);
-    if (P.colsum) {
+    {
+      OpLoader<BM, QA, LBO_A> sa = la;
+      sa.off0 = a_off0; sa.offstride = a_offstride;
+      sa.store(va, a_hi, a_lo);
+      OpLoader<BN, QB, LBO_B> sb = lb;
+      sb.off0 = b_off0; sb.offstride = b_offstride;
+      sb.store(vb, b_hi, b_lo);
+    }
+    if (P.colsum) {   // k-strided A: RVEC -> quad i is row 4 lane + i; RSCALAR -> every quad is row tid & 127
 #pragma unroll
-      for (int i = 0; i < QA; ++i) csum += (va[i][0] + va[i][1]) + (va[i][2] + va[i][3]);
+      for (int i = 0; i < QA; ++i) {
+        const float t = (va[i][0] + va[i][1]) + (va[i][2] + va[i][3]);
+        if (a_mode == RVEC) csum[i] += t; else csum[0] += t;
+      }
     }
     if (c + 1 < nchunks) prefetch();   // in flight while the MMA warp works and the next stage is waited for
     fence_proxy_async_smem();
@@ -247,10 +347,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
     if (stamp && c < 12) g.dbg[4 + c] = gtimer();
   }
 
-  if (P.colsum) {   // k-strided A: a thread's quads all belong to row (tid & 127)
-    colsum_red[tid] = csum;
+  if (P.colsum) {
+    if (a_mode == RVEC) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(&colsum_red[4 * lane + i], csum[i]);
+    } else {
+      atomicAdd(&colsum_red[tid & (BM - 1)], csum[0]);
+    }
     named_bar_sync(1, THREADS);
-    if (tid < BM && tx == 0 && m0 + tid < P.M) atomicAdd(P.colsum + m0 + tid, colsum_red[tid] + colsum_red[tid + BM]);
+    if (tid < BM && tx == 0 && m0 + tid < P.M) atomicAdd(P.colsum + m0 + tid, colsum_red[tid]);
   }
 
   const int last = nchunks - 1;
