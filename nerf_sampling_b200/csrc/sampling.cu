@@ -66,8 +66,8 @@ __global__ void sample_pdf_kernel(const float* __restrict__ bins_or_z, const flo
   const int wpb = blockDim.x >> 5, wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x * wpb + wib;
   if (ray >= n_rays) return;  // whole warp leaves together
-  // per-warp carve-up: bins[B], cdf[B], row[P]
-  float* bins = sm + static_cast<size_t>(wib) * (2 * B + P);
+  // per-warp carve-up: bins[B], cdf[B], row[P], merged[B + 1 + Sf]
+  float* bins = sm + static_cast<size_t>(wib) * (2 * B + P + B + 1 + Sf);
   float* cdf = bins + B;
   float* row = cdf + B;
   const int Sc = B + 1;  // coarse samples when FROM_COARSE
@@ -121,6 +121,43 @@ __global__ void sample_pdf_kernel(const float* __restrict__ bins_or_z, const flo
   }
   if (o_all == nullptr) return;
   for (int i = lane; i < Sc; i += 32) row[i] = zsrc[i];
+  __syncwarp();
+  // Deterministic sampling (u = linspace, Trainer.py:651-672 with perturb == 0) gives non-decreasing samples, and the coarse
+  // depths are monotone: sort(cat(z_coarse, z_samples)) is then a MERGE of two sorted runs -- every element finds its rank
+  // with one binary search over the other run (coarse before equal samples).  ~500 instructions per ray instead of the
+  // ~3,500 of the bitonic network below, which remains for random u, unsorted inputs and NaNs (any failed <= sends us there).
+  {
+    bool sorted = true;
+    for (int i = lane; i + 1 < Sc; i += 32) sorted = sorted && (row[i] <= row[i + 1]);
+    for (int k = lane; k + 1 < Sf; k += 32) sorted = sorted && (row[Sc + k] <= row[Sc + k + 1]);
+    if (__all_sync(0xffffffffu, sorted)) {
+      float* out = row + P;
+      const float* smp = row + Sc;
+      for (int i = lane; i < Sc; i += 32) {
+        const float v = row[i];
+        int lo = 0, hi = Sf;   // number of samples < v
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (smp[mid] < v) lo = mid + 1;
+          else hi = mid;
+        }
+        out[i + lo] = v;
+      }
+      for (int k = lane; k < Sf; k += 32) {
+        const float v = smp[k];
+        int lo = 0, hi = Sc;   // number of coarse depths <= v
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (row[mid] <= v) lo = mid + 1;
+          else hi = mid;
+        }
+        out[k + lo] = v;
+      }
+      __syncwarp();
+      for (int i = lane; i < Sc + Sf; i += 32) o_all[static_cast<size_t>(ray) * (Sc + Sf) + i] = out[i];
+      return;
+    }
+  }
   for (int i = Sc + Sf + lane; i < P; i += 32) row[i] = __int_as_float(0x7f800000);
   __syncwarp();
   for (int k = 2; k <= P; k <<= 1)
@@ -147,7 +184,7 @@ static int launch_sample_pdf(bool from_coarse, const float* a, const float* w, c
   int P = 1;
   while (P < B + 1 + Sf) P <<= 1;
   const int wpb = 4;
-  const size_t smem = static_cast<size_t>(wpb) * (2 * B + P) * sizeof(float);
+  const size_t smem = static_cast<size_t>(wpb) * (2 * B + P + B + 1 + Sf) * sizeof(float);
   if (smem > 48 * 1024) return fail("sample_pdf: row too long (B=%d, Sf=%d)", B, Sf);
   const unsigned grid = (n_rays + wpb - 1) / wpb;
   if (from_coarse)

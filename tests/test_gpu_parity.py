@@ -390,6 +390,12 @@ def test_sample_pdf_indices_bit_exact_on_reference_inputs(lib):
     assert float((zs.cpu() - torch.from_numpy(g["z_samples"])).abs().max()) <= 2e-6
     assert float((z_all.cpu() - torch.from_numpy(g["z_fine"])).abs().max()) <= 2e-6
     assert bool((z_all[:, 1:] >= z_all[:, :-1]).all())
+    # the merge of the two sorted runs is exactly the sort of their concatenation (same multiset, bit for bit)
+    assert torch.equal(z_all, torch.sort(torch.cat([zc, zs], -1), -1).values)
+    # ties: every sample identical (u constant), and samples that coincide with coarse depths
+    u_const = torch.full((zc.shape[0], 24), 0.5)
+    zs2, za2, _ = ops.sample_pdf_merge(zc, wc, 24, u=u_const.to(DEV))
+    assert torch.equal(za2, torch.sort(torch.cat([zc, zs2], -1), -1).values)
     # generic entry point (bins, weights) + random u (unsorted samples)
     mid = 0.5 * (zc[:, 1:] + zc[:, :-1])
     u = torch.rand(zc.shape[0], 40, generator=torch.Generator().manual_seed(9))
