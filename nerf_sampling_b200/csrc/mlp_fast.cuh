@@ -175,7 +175,7 @@ __device__ __forceinline__ void encode_store(const float (&x)[3], uint8_t* dst /
 // epilogues (one thread = one accumulator row x one column half)
 // ---------------------------------------------------------------------------------------------
 // 32 accumulator columns: + bias, activation, pack, 4 x 16-byte operand stores (K chunks kc .. kc+3).
-// MODE 0: ReLU   1: ReLU + alpha-head partial sums   2: no activation (feature_linear)
+// MODE 0: ReLU   1: ReLU + alpha-head partial sums (+ sum of magnitudes)   3: the same without the magnitudes   2: no activation
 template <int MODE, bool FP16>
 __device__ __forceinline__ void epi_store32(const uint32_t (&v)[32], const float* bias, const float* hw, uint8_t* dst,
                                             float& hsum, float& habs) {
@@ -187,7 +187,7 @@ __device__ __forceinline__ void epi_store32(const uint32_t (&v)[32], const float
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] += __uint_as_float(v[j + i]);
     uint32_t h[4];
-    if (MODE == 1) {
+    if (MODE == 1 || MODE == 3) {
       const float4 w0 = *reinterpret_cast<const float4*>(hw + j);
       const float4 w1 = *reinterpret_cast<const float4*>(hw + j + 4);
       const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -195,7 +195,7 @@ __device__ __forceinline__ void epi_store32(const uint32_t (&v)[32], const float
       for (int i = 0; i < 8; ++i) {
         x[i] = fmaxf(x[i], 0.f);
         hsum = fmaf(x[i], w[i], hsum);
-        habs = fmaf(x[i], fabsf(w[i]), habs);
+        if (MODE == 1) habs = fmaf(x[i], fabsf(w[i]), habs);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) h[i] = pack_half2<FP16, false>(x[2 * i], x[2 * i + 1]);
@@ -595,7 +595,12 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
             uint8_t* dst = a_tile + hf * 16 * KC_STRIDE + row_off;
             if (s == 7) {
               float hs = 0.f, ha = 0.f;
-              epilogue_store<1, FP16>(tacc + hf * 128, sf32 + SF_B7 + hf * 128, sf32 + SF_WA + hf * 128, dst, hs, ha);
+              // sum |h7 * w_alpha| feeds the guard-band test, which only looks at the LAST sample of a ray: the 32 rows of this
+              // warp need it only when one of them is such a row and a guard list was asked for (warp-uniform)
+              const int grow0 = ((u * NCTA + static_cast<int>(rank)) * 2 + slot) * TILE_M + (row & ~31);
+              const bool need_abs = p.guard_count != nullptr && (p.S - 1 - grow0 % p.S) < 32;
+              if (need_abs) epilogue_store<1, FP16>(tacc + hf * 128, sf32 + SF_B7 + hf * 128, sf32 + SF_WA + hf * 128, dst, hs, ha);
+              else epilogue_store<3, FP16>(tacc + hf * 128, sf32 + SF_B7 + hf * 128, sf32 + SF_WA + hf * 128, dst, hs, ha);
               if (hf == 1) {
                 tail->alpha_part[slot][row] = hs;
                 tail->eabs_part[slot][row] = ha;
