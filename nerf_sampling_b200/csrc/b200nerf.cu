@@ -437,13 +437,28 @@ extern "C" int b200nerf_nerf_pack_fast(const float* const* t, int prec, void* h_
     o = pack_step_fast(256, sg, 1, fp16, o);
   }
   {
-    const FastSeg sg[1] = {{Wf, 256, 256, 0, 256}};                              // step 8: feature_linear
-    o = pack_step_fast(256, sg, 1, fp16, o);
-  }
-  {
-    // step 9: feature columns, gamma(viewdir), and two all-zero K16 blocks that fill the last ring stage
-    const FastSeg sg[3] = {{Wv, 256, 283, 0, 256}, {Wv, 27, 283, 256, 32}, {Wv, 0, 283, 0, 32}};
+    // step 8: views_linears.0 with feature_linear folded in (no activation between them, run_nerf_helpers.py:116-121):
+    //   W' = W_view[:, :256] * W_feature,  b' = W_view[:, :256] * b_feature + b_view   (fp64 sums)
+    // K = [h7 (256) | gamma(viewdir) (27 -> 32) | two all-zero K16 blocks that fill the last ring stage]
+    const float *bv = t[17], *bf = t[19];
+    std::vector<float> wfold(static_cast<size_t>(128) * 283);
+    std::vector<float> bfold(128);
+    for (int r = 0; r < 128; ++r) {
+      const float* wr = Wv + static_cast<size_t>(r) * 283;
+      for (int k = 0; k < 256; ++k) {
+        double a = 0.0;
+        for (int j = 0; j < 256; ++j) a += static_cast<double>(wr[j]) * static_cast<double>(Wf[static_cast<size_t>(j) * 256 + k]);
+        wfold[static_cast<size_t>(r) * 283 + k] = static_cast<float>(a);
+      }
+      for (int k = 256; k < 283; ++k) wfold[static_cast<size_t>(r) * 283 + k] = wr[k];
+      double b = static_cast<double>(bv[r]);
+      for (int j = 0; j < 256; ++j) b += static_cast<double>(wr[j]) * static_cast<double>(bf[j]);
+      bfold[r] = static_cast<float>(b);
+    }
+    const FastSeg sg[3] = {{wfold.data(), 256, 283, 0, 256}, {wfold.data(), 27, 283, 256, 32}, {wfold.data(), 0, 283, 0, 32}};
     o = pack_step_fast(128, sg, 3, fp16, o);
+    memcpy(o, bfold.data(), 128 * sizeof(float));   // fast::FOLD_BIAS_OFF
+    o += 128 * sizeof(float);
   }
   if (static_cast<size_t>(o - static_cast<uint8_t*>(h_wpack)) != fast::WPACK_BYTES)
     return fail("b200nerf_nerf_pack_fast: internal size mismatch");

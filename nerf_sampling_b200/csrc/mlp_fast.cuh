@@ -40,11 +40,12 @@ constexpr int TILE_ACT_BYTES = TILE_KC * KC_STRIDE;   // 90,112 B per slot
 constexpr int RING_BYTES = 32768;
 constexpr int AUX_FLOATS = 3080;                      // the fp32 aux block in global memory (shared with the exact kernel)
 constexpr int SF32_FLOATS = 1032;                     // its part kept in shared memory as fp32: alpha layer, view layer, heads
-constexpr int SBIAS16 = 8 * 256;                      // 16-bit bias table of the eight plain layers (steps 0-6 and 8)
+constexpr int SBIAS16 = 7 * 256;                      // 16-bit bias table of the seven plain layers (steps 0-6)
 constexpr int THREADS = 512;
-constexpr int NSTEPS = 10;
+constexpr int NSTEPS = 9;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, PRO_WARP0 = 12, PRO_WARPS = 4;
-constexpr size_t WPACK_BYTES = 1196032;               // 136 slabs x 8 KB + 20 slabs x 4 KB (view layer padded to K = 320)
+constexpr size_t FOLD_BIAS_OFF = 65 * 16384;              // after the 65 ring stages: the folded view-layer bias, 128 fp32
+constexpr size_t WPACK_BYTES = FOLD_BIAS_OFF + 512;       // 1,065,472 B
 
 // aux block (float offsets) -- same layout as the split-precision kernel's NeRF aux
 enum : uint32_t { AUX_B0 = 0, AUX_BF = 2048, AUX_BV = 2304, AUX_WA = 2432, AUX_BA = 2688, AUX_WR = 2692, AUX_BR = 3076 };
@@ -53,17 +54,21 @@ enum : uint32_t { SF_B7 = 0, SF_BV = 256, SF_WA = 384, SF_BA = 640, SF_WR = 644,
 
 // The layer program.  Step s reads K16 blocks [kb1, kb1+nk1) then [kb2, kb2+nk2) of the slot's operand buffer.
 //   s: 0 = pts_linears.0 (gamma(pts) only), 1-4, 5 = skip layer [h | gamma(pts)], 6, 7 (+ alpha head),
-//      8 = feature_linear (no activation), 9 = views_linears.0 [feature | gamma(viewdir)] (N = 128, + rgb head)
+//      8 = views_linears.0 on [h7 | gamma(viewdir)] (N = 128, + rgb head).
+// feature_linear has NO activation (run_nerf_helpers.py:116-121: `feature = self.feature_linear(h)` goes straight into
+// `views_linears[0](cat([feature, input_views]))`), so it is folded into the view layer when the weights are packed:
+//   W' = W_view[:, :256] * W_feature (fp64),  b' = W_view[:, :256] * b_feature + b_view.
+// One 256x256 layer (11 % of the network's MACs), its epilogue and one 16-bit rounding of the activations disappear; the
+// result is the same function of the same parameters (roofline numbers still count the reference's 1,186,816 FLOP/point).
 __host__ __device__ constexpr int step_nk1(int s) { return s == 0 ? 4 : 16; }
 __host__ __device__ constexpr int step_kb1(int s) { return s == 0 ? ENC_KB : 0; }
-__host__ __device__ constexpr int step_nk2(int s) { return s == 5 ? 4 : (s == 9 ? 2 : 0); }
+__host__ __device__ constexpr int step_nk2(int s) { return s == 5 ? 4 : (s == NSTEPS - 1 ? 2 : 0); }
 __host__ __device__ constexpr int step_kb2(int s) { return s == 5 ? ENC_KB : VIEW_KB; }
-__host__ __device__ constexpr int step_n(int s) { return s == 9 ? 128 : 256; }
+__host__ __device__ constexpr int step_n(int s) { return s == NSTEPS - 1 ? 128 : 256; }
 __host__ __device__ constexpr int step_nk(int s) { return step_nk1(s) + step_nk2(s); }
-__host__ __device__ constexpr uint32_t step_bias(int s) { return s < 8 ? AUX_B0 + 256u * s : (s == 8 ? AUX_BF : AUX_BV); }
 // ring stages of a step: one stage = 8 KB per CTA = two K16 blocks at N = 256, four at N = 128 (the view layer,
 // whose 18 blocks are padded to 20 with zero weights)
-__host__ __device__ constexpr int step_stages(int s) { return s == 9 ? 5 : step_nk(s) / 2; }
+__host__ __device__ constexpr int step_stages(int s) { return s == NSTEPS - 1 ? 5 : step_nk(s) / 2; }
 __host__ __device__ constexpr uint32_t step_woff(int s) {  // byte offset of the step's first stage in the pack
   uint32_t o = 0;
   for (int i = 0; i < s; ++i) o += static_cast<uint32_t>(step_stages(i)) * 16384u;
@@ -106,7 +111,10 @@ struct FastParams {
 constexpr int NSTAGE = 4;                             // ring stages; one stage = this CTA's half of two K16 slabs
 constexpr int STAGE_BYTES = RING_BYTES / NSTAGE;      // 8 KB
 constexpr int NCTA = 2;                               // CTAs per cluster (tcgen05 cta_group::2 pair)
-constexpr int STAGGER = 5;                            // slot 1 runs this many steps behind slot 0, so that one slot's
+#ifndef B200NERF_FAST_STAGGER
+#define B200NERF_FAST_STAGGER 5
+#endif
+constexpr int STAGGER = B200NERF_FAST_STAGGER;                            // slot 1 runs this many steps behind slot 0, so that one slot's
                                                       // epilogue-heavy tile boundary (steps 9, 0) meets the other's MMA-heavy steps
 
 struct __align__(16) Tail {
@@ -352,16 +360,19 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
     tmem_relinquish_cg2();
   }
   for (int i = threadIdx.x; i < SF32_FLOATS; i += THREADS) {
-    // B7 | BV | WA | BA.. | WR | BR.. gathered from the global aux block
-    const uint32_t src = i < 256 ? AUX_B0 + 7 * 256 + i : i < 384 ? AUX_BV + (i - 256) : i < 640 ? AUX_WA + (i - 384)
-                       : i < 644 ? AUX_BA + (i - 640) : i < 1028 ? AUX_WR + (i - 644) : AUX_BR + (i - 1028);
-    sf32[i] = p.aux[src];
+    // B7 | folded view bias | WA | BA.. | WR | BR..: from the global aux block, the folded bias from the tail of the pack
+    if (i >= 256 && i < 384) {
+      sf32[i] = reinterpret_cast<const float*>(p.wpack + FOLD_BIAS_OFF)[i - 256];
+    } else {
+      const uint32_t src = i < 256 ? AUX_B0 + 7 * 256 + i : i < 640 ? AUX_WA + (i - 384)
+                         : i < 644 ? AUX_BA + (i - 640) : i < 1028 ? AUX_WR + (i - 644) : AUX_BR + (i - 1028);
+      sf32[i] = p.aux[src];
+    }
   }
   for (int i = threadIdx.x; i < SBIAS16; i += THREADS) {
-    // biases of steps 0..6 and of feature_linear (step 8) in the operand's 16-bit format: the plain-layer epilogue adds
-    // them with one packed fma.relu per two columns
-    const float b = p.aux[i < 7 * 256 ? AUX_B0 + i : AUX_BF + (i - 7 * 256)];
-    sb16[i] = static_cast<uint16_t>(pack_half2<FP16, false>(b, 0.f) & 0xffffu);
+    // biases of steps 0..6 in the operand's 16-bit format: the plain-layer epilogue adds them with one packed fma.relu
+    // per two columns
+    sb16[i] = static_cast<uint16_t>(pack_half2<FP16, false>(p.aux[AUX_B0 + i], 0.f) & 0xffffu);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -591,7 +602,7 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
           if (lane == 0 && q == 0) TL_STAMP(1 + hf, tl_idx, 1);
           const uint32_t tacc = t_lane + slot * 256u;
           uint8_t* a_tile = act + slot * TILE_ACT_BYTES;
-          if (s < 8) {
+          if (s < NSTEPS - 1) {
             uint8_t* dst = a_tile + hf * 16 * KC_STRIDE + row_off;
             if (s == 7) {
               float hs = 0.f, ha = 0.f;
@@ -611,9 +622,6 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
             } else {
               epilogue_store_packed<true, FP16>(tacc + hf * 128, sb16 + s * 256 + hf * 128, dst);
             }
-          } else if (s == 8) {
-            uint8_t* dst = a_tile + hf * 16 * KC_STRIDE + row_off;
-            epilogue_store_packed<false, FP16>(tacc + hf * 128, sb16 + 7 * 256 + hf * 128, dst);
           } else {
             // view layer (128 columns, 64 per column half) + rgb head; sigma = alpha head of layer 7
             float r = 0.f, g = 0.f, b = 0.f;
@@ -658,7 +666,8 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
               }
             }
           }
-          if (s == 8) named_bar_sync(1, EPI_WARPS * 32);   // layer 7's alpha partials are visible to half 0
+          // (layer 7's alpha partials, written by the column-half-1 warp of a lane quarter, are read by its half-0 partner after
+          // the pair barrier of the last step)
           if (s < NSTEPS - 1) fence_proxy_async_smem();    // operand stores -> visible to the tensor core
           tc_fence_before();
           __syncwarp();
