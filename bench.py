@@ -359,19 +359,19 @@ def main():
                                      else "mlp_chain_kernel<BF16,NERF> via b200nerf_nerf_query")),
                          "achieved": mlp_tflops,
                          "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tf_sustained"],
-                         "frac_executed": mlp_tflops * (1_056_768 if prec in (PREC_FAST, PREC_FP16) else 1_187_840) / 1_186_816 / pk["tf_sustained"],
+                         "frac_executed": mlp_tflops * (1_187_840 if prec == PREC_BF16 else 1_056_768) / 1_186_816 / pk["tf_sustained"],
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.prec),
                          "peak_source": pk["src"] + ", sustained bf16", "ms_per_launch": k_ms[2],
                          "algorithmic_flop_per_point": NERF_FLOP_PER_POINT,
                          # executed tensor-core work: padded K (1,187,840 FLOP/point); the fast kernel folds feature_linear into the view
-                         # layer (-131,072 FLOP/point), the split kernel issues 3 MMAs per MAC
-                         "executed_mma_tflops": mlp_tflops * ((3 * 1_187_840) if prec == PREC_SPLIT else
+                         # layer (-131,072 FLOP/point) and so does the pipelined split kernel, which issues 3 MMAs per MAC
+                         "executed_mma_tflops": mlp_tflops * ((3 * 1_056_768) if prec == PREC_SPLIT else
                                                               (1_187_840 if prec == PREC_BF16 else 1_056_768)) / 1_186_816,
                          "guard_band_points_last_step": int(guard[0]) if prec == PREC_FAST else None,
                          "note": ("achieved counts the reference network's 1,186,816 FLOP/point; the fast kernel folds the activation-free "
                                   "feature_linear into views_linears.0 when packing (1,056,768 FLOP/point executed), so frac can "
                                   "exceed 1 -- frac_executed = executed_mma_tflops / peak is the tensor-pipe load")
-                         if prec in (PREC_FAST, PREC_FP16) else None},
+                         if prec != PREC_BF16 else None},
             "roofline_composite": {"bound": "hbm", "kernel": "comp::composite_tma_kernel<16> (TMA-staged, persistent)", "achieved": comp_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                    "frac": comp_gbs / pk["hbm"], "ms_per_launch": k_ms[3], "bytes_per_ray": COMPOSITE_BYTES_PER_RAY},
             "kernel_ms": {"depthnet": k_ms[0], "place": k_ms[1], "nerf_mlp": k_ms[2], "composite": k_ms[3]},

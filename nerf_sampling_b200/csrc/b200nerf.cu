@@ -132,6 +132,29 @@ static exact::XStep xstep(int n1a, int kb1a, int n1b, int kb1b, int n2, int kb2,
   return s;
 }
 
+// views_linears.0 with the activation-free feature_linear folded in: returns W'' [128, 283] = [W_view[:, :256] * W_feature |
+// W_view[:, 256:]] (valid until the next call on this thread) and, if asked, b' = W_view[:, :256] * b_feature + b_view.
+static const float* nerf_fold_view(const float* const* t, float* bias128) {
+  static thread_local std::vector<float> wfold;
+  const float *Wv = t[16], *bv = t[17], *Wf = t[18], *bf = t[19];
+  wfold.resize(static_cast<size_t>(128) * 283);
+  for (int r = 0; r < 128; ++r) {
+    const float* wr = Wv + static_cast<size_t>(r) * 283;
+    for (int k = 0; k < 256; ++k) {
+      double a = 0.0;
+      for (int j = 0; j < 256; ++j) a += static_cast<double>(wr[j]) * static_cast<double>(Wf[static_cast<size_t>(j) * 256 + k]);
+      wfold[static_cast<size_t>(r) * 283 + k] = static_cast<float>(a);
+    }
+    for (int k = 256; k < 283; ++k) wfold[static_cast<size_t>(r) * 283 + k] = wr[k];
+    if (bias128) {
+      double b = static_cast<double>(bv[r]);
+      for (int j = 0; j < 256; ++j) b += static_cast<double>(wr[j]) * static_cast<double>(bf[j]);
+      bias128[r] = static_cast<float>(b);
+    }
+  }
+  return wfold.data();
+}
+
 // NeRF (run_nerf_helpers.py:109-134); t = the 24 tensors in state_dict order (may be null when only the steps are needed)
 static XProgram nerf_xprogram(const float* const* t) {
   auto T = [&](int i) { return t ? t[i] : nullptr; };
@@ -157,12 +180,14 @@ static XProgram nerf_xprogram(const float* const* t) {
           XSeg{0, 16, T(2 * i), 256, 0, 256}, none, 1);
     }
   }
-  add(xstep(8, 0, 0, 0, 8, 8, 2, exact::EPI_STORE, exact::ACT_NONE, NERF_BF), 256, XSeg{0, 16, T(18), 256, 0, 256}, none, 1);
   {
-    exact::XStep s9 = xstep(8, 0, 2, exact::VIEW_KB, 8, 8, 1, exact::EPI_NERF_OUT, exact::ACT_RELU, NERF_BV);
-    s9.wait_v = 1;
-    s9.sig_v = 1;
-    add(s9, 128, XSeg{0, 16, T(16), 283, 0, 256}, XSeg{exact::VIEW_KB, 2, T(16), 283, 256, 27}, 2);
+    // feature_linear has no activation (run_nerf_helpers.py:116-121), so it is folded into views_linears.0 here exactly as in
+    // the throughput kernel's pack: W' = W_view[:, :256] * W_feature (fp64 sums; nerf_fold_view), aux[NERF_BV] = folded bias
+    exact::XStep s8 = xstep(8, 0, 2, exact::VIEW_KB, 8, 8, 1, exact::EPI_NERF_OUT, exact::ACT_RELU, NERF_BV);
+    s8.wait_v = 1;
+    s8.sig_v = 1;
+    const float* wfold = t ? nerf_fold_view(t, nullptr) : nullptr;
+    add(s8, 128, XSeg{0, 16, wfold, 283, 0, 256}, XSeg{exact::VIEW_KB, 2, wfold, 283, 256, 27}, 2);
   }
   return pg;
 }
@@ -351,7 +376,8 @@ extern "C" int b200nerf_nerf_pack(const float* const* t, int prec, void* h_wpack
   memset(h_aux, 0, NERF_AUX_FLOATS * sizeof(float));
   for (int i = 0; i < 8; ++i) memcpy(h_aux + NERF_B0 + 256 * i, B[i], 256 * sizeof(float));
   memcpy(h_aux + NERF_BF, Bf, 256 * sizeof(float));
-  memcpy(h_aux + NERF_BV, Bv, 128 * sizeof(float));
+  if (pipelined) nerf_fold_view(t, h_aux + NERF_BV);   // the pipelined program runs the folded view layer
+  else memcpy(h_aux + NERF_BV, Bv, 128 * sizeof(float));
   memcpy(h_aux + NERF_WA, Wa, 256 * sizeof(float));
   h_aux[NERF_BA] = Ba[0];
   memcpy(h_aux + NERF_WR, Wr, 384 * sizeof(float));
@@ -440,24 +466,11 @@ extern "C" int b200nerf_nerf_pack_fast(const float* const* t, int prec, void* h_
     // step 8: views_linears.0 with feature_linear folded in (no activation between them, run_nerf_helpers.py:116-121):
     //   W' = W_view[:, :256] * W_feature,  b' = W_view[:, :256] * b_feature + b_view   (fp64 sums)
     // K = [h7 (256) | gamma(viewdir) (27 -> 32) | two all-zero K16 blocks that fill the last ring stage]
-    const float *bv = t[17], *bf = t[19];
-    std::vector<float> wfold(static_cast<size_t>(128) * 283);
-    std::vector<float> bfold(128);
-    for (int r = 0; r < 128; ++r) {
-      const float* wr = Wv + static_cast<size_t>(r) * 283;
-      for (int k = 0; k < 256; ++k) {
-        double a = 0.0;
-        for (int j = 0; j < 256; ++j) a += static_cast<double>(wr[j]) * static_cast<double>(Wf[static_cast<size_t>(j) * 256 + k]);
-        wfold[static_cast<size_t>(r) * 283 + k] = static_cast<float>(a);
-      }
-      for (int k = 256; k < 283; ++k) wfold[static_cast<size_t>(r) * 283 + k] = wr[k];
-      double b = static_cast<double>(bv[r]);
-      for (int j = 0; j < 256; ++j) b += static_cast<double>(wr[j]) * static_cast<double>(bf[j]);
-      bfold[r] = static_cast<float>(b);
-    }
-    const FastSeg sg[3] = {{wfold.data(), 256, 283, 0, 256}, {wfold.data(), 27, 283, 256, 32}, {wfold.data(), 0, 283, 0, 32}};
+    float bfold[128];
+    const float* wfold = nerf_fold_view(t, bfold);
+    const FastSeg sg[3] = {{wfold, 256, 283, 0, 256}, {wfold, 27, 283, 256, 32}, {wfold, 0, 283, 0, 32}};
     o = pack_step_fast(128, sg, 3, fp16, o);
-    memcpy(o, bfold.data(), 128 * sizeof(float));   // fast::FOLD_BIAS_OFF
+    memcpy(o, bfold, 128 * sizeof(float));   // fast::FOLD_BIAS_OFF
     o += 128 * sizeof(float);
   }
   if (static_cast<size_t>(o - static_cast<uint8_t*>(h_wpack)) != fast::WPACK_BYTES)
