@@ -443,7 +443,7 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
       };
 
       // view layer (N = 128): one stage = four K16 blocks; a_lo2 is the operand block of MMAs 2 and 3
-      auto issue_stage4 = [&](auto acc_first, uint32_t d_tmem, uint32_t a_lo, uint32_t a_lo2, uint32_t idesc) {
+      auto issue_stage4 = [&](auto acc_first, auto two_only, uint32_t d_tmem, uint32_t a_lo, uint32_t a_lo2, uint32_t idesc) {
         constexpr uint32_t B_LBO = ((128u * 8u) >> 4) << 16, PIECE16 = 128;
         mbar_wait_lean(full_addr + stage * 8u, phase);
         tc_fence_after();
@@ -454,8 +454,10 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
           const uint64_t b0 = (static_cast<uint64_t>(DESC_HI) << 32) | b_lo;
           tc_mma_f16_cg2_imm<decltype(acc_first)::value>(d_tmem, a0, b0, idesc);
           tc_mma_f16_cg2_imm<true>(d_tmem, a0 + A_STEP, b0 + PIECE16, idesc);
-          tc_mma_f16_cg2_imm<true>(d_tmem, a2, b0 + 2 * PIECE16, idesc);
-          tc_mma_f16_cg2_imm<true>(d_tmem, a2 + A_STEP, b0 + 3 * PIECE16, idesc);
+          if (!decltype(two_only)::value) {   // the last stage of the view layer holds two real blocks and two all-zero ones
+            tc_mma_f16_cg2_imm<true>(d_tmem, a2, b0 + 2 * PIECE16, idesc);
+            tc_mma_f16_cg2_imm<true>(d_tmem, a2 + A_STEP, b0 + 3 * PIECE16, idesc);
+          }
           tc_commit_cg2_addr(empty_addr + stage * 8u, 3);
         }
         stage = (stage + 1) & (NSTAGE - 1);
@@ -491,14 +493,14 @@ nerf_fast_kernel(const __grid_constant__ FastParams p, const __grid_constant__ T
           uint32_t a_lo = a_base + kb1 * A_STEP;
           if (s == NSTEPS - 1) {
             // [feature 0..15 | gamma(viewdir) 20,21 | the same two blocks again under zero weights]
-            issue_stage4(std::false_type{}, d_tmem, a_lo, a_lo + 2 * A_STEP, idesc);
+            issue_stage4(std::false_type{}, std::false_type{}, d_tmem, a_lo, a_lo + 2 * A_STEP, idesc);
 #pragma unroll 1
             for (int k4 = 1; k4 < 4; ++k4) {
               a_lo += 4 * A_STEP;
-              issue_stage4(std::true_type{}, d_tmem, a_lo, a_lo + 2 * A_STEP, idesc);
+              issue_stage4(std::true_type{}, std::false_type{}, d_tmem, a_lo, a_lo + 2 * A_STEP, idesc);
             }
             a_lo = a_base + VIEW_KB * A_STEP;
-            issue_stage4(std::true_type{}, d_tmem, a_lo, a_lo, idesc);
+            issue_stage4(std::true_type{}, std::true_type{}, d_tmem, a_lo, a_lo, idesc);   // gamma(viewdir): blocks 20, 21 only
           } else {
             issue_stage(std::false_type{}, d_tmem, a_lo, b_lbo, piece16, idesc);
             for (int k2 = 1; k2 < n1; ++k2) {
