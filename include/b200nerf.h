@@ -152,6 +152,12 @@ int b200nerf_composite_fwd(const float* raw, const float* z, const float* rays_d
                            int S, int white_bkgd, float* out_rgb, float* out_disp, float* out_acc, float* out_depth,
                            float* out_weights, float* out_alphas, void* stream);
 
+/* Same arithmetic, image-tile output: out_rgbd [n_rays,4] = (r, g, b, disp) per ray -- the layout the multi-GPU render
+ * all-gathers (one 16-byte pixel per ray), written by the kernel itself instead of two copy launches. */
+int b200nerf_composite_tile_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays,
+                                int S, int white_bkgd, float* out_rgbd, float* out_acc, float* out_depth,
+                                float* out_weights, float* out_alphas, void* stream);
+
 /* render_rays_test, DepthNet mode (nerf_utils.py:736-876): depthnet -> place -> encode+MLP -> composite for
  * n_rays rays already on the device.  ws_z [n_rays,S] and ws_raw [n_rays,S,4] are caller-provided workspaces
  * that double as the `depth_net_z_vals` / `raw` extras; ws_guard = n_rays + 4 ints (PREC_FAST only, else may be
@@ -162,6 +168,13 @@ int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_aux, int dn_h
                              float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, int* ws_guard,
                              float* out_rgb, float* out_disp, float* out_acc, float* out_depth, float* out_weights,
                              void* stream);
+
+/* b200nerf_render_depthnet with the image-tile output of b200nerf_composite_tile_fwd (out_rgbd [n_rays,4]). */
+int b200nerf_render_depthnet_tile(const void* dn_wpack, const float* dn_aux, int dn_hidden, int dn_prec,
+                                  const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d,
+                                  const float* viewdirs, int n_rays, int S, int mode, const float* offsets, float radius,
+                                  float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, int* ws_guard,
+                                  float* out_rgbd, float* out_acc, float* out_depth, float* out_weights, void* stream);
 
 /* Same, through host memory: copies h_rays_o / h_rays_d ([n_rays,3] each, ideally pinned) to the device
  * workspace, renders, copies rgb [n_rays,3] and disp [n_rays] back and synchronises `stream`.

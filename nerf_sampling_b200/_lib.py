@@ -42,6 +42,8 @@ SIGNATURES = {
     "b200nerf_nerf_mlp_fast_fwd": (I, [P, P, I, P, P, P, P, P, I, I, P, P, P, I, F, P]),
     "b200nerf_nerf_mlp_guarded_fwd": (I, [P, P, P, I, P, P, P, P, P, I, I, F, P, P, P]),
     "b200nerf_composite_fwd": (I, [P, P, P, P, I, I, I, P, P, P, P, P, P, P]),
+    "b200nerf_composite_tile_fwd": (I, [P, P, P, P, I, I, I, P, P, P, P, P, P]),
+    "b200nerf_render_depthnet_tile": (I, [P, P, I, I, P, P, P, P, I, I, I, P, F, F, F, P, P, P, P, P, P, P, P, P]),
     "b200nerf_nerf_query": (I, [P, P, P, P, P, P, I, I, P, P, P]),
     "b200nerf_render_depthnet": (I, [P, P, I, I, P, P, P, P, I, I, I, P, F, F, F, P, P, P, P, P, P, P, P, P, P]),
     "b200nerf_render_host_ws_bytes": (SZ, [I, I]),

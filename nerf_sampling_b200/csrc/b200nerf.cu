@@ -3,6 +3,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200nerf.h"
@@ -33,12 +36,11 @@ extern "C" const char* b200nerf_last_error(void) { return g_err; }
 extern "C" unsigned long long b200nerf_launch_count(void) { return g_b200_launches.load(); }
 
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
-  }
-  return n;
+  static int n[B200_MAX_DEVICES] = {0};
+  const int dev = b200_device();
+  if (dev < 0) return 0;
+  if (n[dev] == 0 && cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 0;
+  return n[dev];
 }
 
 // ------------------------------------------------------------------------------------------- host packing
@@ -273,7 +275,10 @@ static int make_exact_tmap(const void* wpack, size_t bytes, exact::TMap* out) {
 
 template <int INPUT>
 static int launch_exact(exact::ExactParams& p, const XProgram& pg, const void* wpack, cudaStream_t st) {
-  static int grid_cap = 0;
+  static int grid_caps[B200_MAX_DEVICES] = {0};
+  const int dev = b200_device();
+  if (dev < 0) return fail("mlp_exact_kernel: no usable CUDA device");
+  int& grid_cap = grid_caps[dev];
   constexpr int smem = exact::smem_bytes();
   auto kern = exact::mlp_exact_kernel<INPUT>;
   cudaLaunchConfig_t cfg;
@@ -302,13 +307,16 @@ static int launch_exact(exact::ExactParams& p, const XProgram& pg, const void* w
   }
   if (static_cast<int>(pg.layers.size()) > exact::MAX_STEPS) return fail("mlp_exact_kernel: too many layers");
   if (INPUT == exact::IN_DEPTHNET) {
-    // per-CTA staging image of the next tile's encoded rays (128 KB per CTA, ~19 MB): library-owned, allocated once per device
-    static uint8_t* scratch[64] = {nullptr};
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return fail("mlp_exact_kernel: device index %d out of range", dev);
-    if (!scratch[dev]) CUDA_TRY(cudaMalloc(&scratch[dev], static_cast<size_t>(grid_cap) * 2 * 32 * exact::KC_STRIDE));
-    p.scratch = scratch[dev];
+    // per-CTA staging image of the next tile's encoded rays (128 KB per CTA, ~19 MB): library-owned, one per (device, stream) --
+    // launches on different streams of a device may overlap and must not share it
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, uint8_t*> scratch;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      uint8_t*& buf = scratch[std::make_pair(dev, st)];
+      if (!buf) CUDA_TRY(cudaMalloc(&buf, static_cast<size_t>(grid_cap) * 2 * 32 * exact::KC_STRIDE));
+      p.scratch = buf;
+    }
   }
   p.n_steps = static_cast<int>(pg.layers.size());
   for (int i = 0; i < p.n_steps; ++i) p.steps[i] = pg.layers[i].st;
@@ -754,7 +762,7 @@ __global__ void __launch_bounds__(256, 4) composite_kernel(const float* __restri
                                                         int n_rays, int S, int white, float* __restrict__ o_rgb,
                                                         float* __restrict__ o_disp, float* __restrict__ o_acc,
                                                         float* __restrict__ o_depth, float* __restrict__ o_w,
-                                                        float* __restrict__ o_alpha) {
+                                                        float* __restrict__ o_alpha, int rgb_stride, int disp_stride) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lig = threadIdx.x & (LPR - 1);
   int ray = gtid / LPR;
@@ -864,11 +872,11 @@ __global__ void __launch_bounds__(256, 4) composite_kernel(const float* __restri
       s_b += bg;
     }
     if (o_rgb) {
-      o_rgb[ray * 3] = s_r;
-      o_rgb[ray * 3 + 1] = s_g;
-      o_rgb[ray * 3 + 2] = s_b;
+      o_rgb[ray * rgb_stride] = s_r;
+      o_rgb[ray * rgb_stride + 1] = s_g;
+      o_rgb[ray * rgb_stride + 2] = s_b;
     }
-    if (o_disp) o_disp[ray] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(s_d, __fadd_rn(s_a, 1e-10f))));
+    if (o_disp) o_disp[ray * disp_stride] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(s_d, __fadd_rn(s_a, 1e-10f))));
     if (o_acc) o_acc[ray] = s_a;
     if (o_depth) o_depth[ray] = s_d;
   }
@@ -877,16 +885,17 @@ __global__ void __launch_bounds__(256, 4) composite_kernel(const float* __restri
 // S == 1: the reference pads the interval list from an EMPTY slice, so every per-sample tensor is [N,0]
 // and the colour is sigmoid(raw rgb) (sampling_trainer.py:178-180, :220-221).
 __global__ void composite_single_kernel(const float* __restrict__ raw, int n_rays, float* __restrict__ o_rgb,
-                                        float* __restrict__ o_disp, float* __restrict__ o_acc, float* __restrict__ o_depth) {
+                                        float* __restrict__ o_disp, float* __restrict__ o_acc, float* __restrict__ o_depth,
+                                        int rgb_stride, int disp_stride) {
   const int ray = blockIdx.x * blockDim.x + threadIdx.x;
   if (ray >= n_rays) return;
   const float4 rw = __ldg(reinterpret_cast<const float4*>(raw) + ray);
   if (o_rgb) {
-    o_rgb[ray * 3] = 1.0f / (1.0f + expf(-rw.x));
-    o_rgb[ray * 3 + 1] = 1.0f / (1.0f + expf(-rw.y));
-    o_rgb[ray * 3 + 2] = 1.0f / (1.0f + expf(-rw.z));
+    o_rgb[ray * rgb_stride] = 1.0f / (1.0f + expf(-rw.x));
+    o_rgb[ray * rgb_stride + 1] = 1.0f / (1.0f + expf(-rw.y));
+    o_rgb[ray * rgb_stride + 2] = 1.0f / (1.0f + expf(-rw.z));
   }
-  if (o_disp) o_disp[ray] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(0.f, 1e-10f)));
+  if (o_disp) o_disp[ray * disp_stride] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(0.f, 1e-10f)));
   if (o_acc) o_acc[ray] = 0.f;
   if (o_depth) o_depth[ray] = 0.f;
 }
@@ -894,23 +903,26 @@ __global__ void composite_single_kernel(const float* __restrict__ raw, int n_ray
 template <int LPR>
 static void launch_composite(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays, int S,
                              int white, float* o_rgb, float* o_disp, float* o_acc, float* o_depth, float* o_w,
-                             float* o_alpha, cudaStream_t st) {
+                             float* o_alpha, int rs, int ds, cudaStream_t st) {
   const long long threads = static_cast<long long>(n_rays) * LPR;
   const unsigned grid = static_cast<unsigned>((threads + 255) / 256);
-  if (S == 4 * LPR) composite_kernel<LPR, true><<<grid, 256, 0, st>>>(raw, z, rays_d, noise, n_rays, S, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha);
-  else composite_kernel<LPR, false><<<grid, 256, 0, st>>>(raw, z, rays_d, noise, n_rays, S, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha);
+  if (S == 4 * LPR) composite_kernel<LPR, true><<<grid, 256, 0, st>>>(raw, z, rays_d, noise, n_rays, S, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha, rs, ds);
+  else composite_kernel<LPR, false><<<grid, 256, 0, st>>>(raw, z, rays_d, noise, n_rays, S, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha, rs, ds);
 }
 
 // S = 32 / 64 / 128 without a noise input: the TMA-staged persistent kernel (composite_tma.cuh).  raw viewed as
 // [n_rays*S/8 rows, 128 B]; one box = 256 rows = one 2048-sample tile, 128-byte swizzle.
 template <int LPR>
 static int launch_composite_tma(const float* raw, const float* z, const float* rays_d, int n_rays, int white, float* o_rgb,
-                                float* o_disp, float* o_acc, float* o_depth, float* o_w, float* o_alpha, cudaStream_t st) {
-  static bool configured = false;
+                                float* o_disp, float* o_acc, float* o_depth, float* o_w, float* o_alpha, int rs, int ds,
+                                cudaStream_t st) {
+  static bool configured[B200_MAX_DEVICES] = {false};
   auto kern = comp::composite_tma_kernel<LPR>;
-  if (!configured) {
+  const int dev = b200_device();
+  if (dev < 0) return fail("composite_tma_kernel: no usable CUDA device");
+  if (!configured[dev]) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, comp::SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail("cuTensorMapEncodeTiled is not available from the driver");
@@ -929,7 +941,7 @@ static int launch_composite_tma(const float* raw, const float* z, const float* r
   const int sms = sm_count();
   if (sms <= 0) return fail("no CUDA device");
   const int grid = static_cast<int>(tiles < 2LL * sms ? tiles : 2LL * sms);
-  kern<<<grid, comp::THREADS, comp::SMEM_BYTES, st>>>(tm, z, rays_d, n_rays, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha);
+  kern<<<grid, comp::THREADS, comp::SMEM_BYTES, st>>>(tm, z, rays_d, n_rays, white, o_rgb, o_disp, o_acc, o_depth, o_w, o_alpha, rs, ds);
   LAUNCH_CHECK();
   return 0;
 }
@@ -944,43 +956,61 @@ static bool composite_force_ldg() {
 }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-extern "C" int b200nerf_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays,
-                                      int S, int white_bkgd, float* out_rgb, float* out_disp, float* out_acc,
-                                      float* out_depth, float* out_weights, float* out_alphas, void* stream) {
+// rs / ds: element strides of the rgb and disp outputs (3 / 1 for separate maps, 4 / 4 for one [n,4] rgb|disp image tile)
+static int composite_impl(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays, int S,
+                          int white_bkgd, float* out_rgb, float* out_disp, float* out_acc, float* out_depth, float* out_weights,
+                          float* out_alphas, int rs, int ds, void* stream) {
   if (n_rays < 0 || S < 1) return fail("b200nerf_composite_fwd: bad sizes n_rays=%d S=%d", n_rays, S);
   if (n_rays == 0) return 0;
   if (!raw || !z || !rays_d) return fail("b200nerf_composite_fwd: null input");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (S == 1) {
-    composite_single_kernel<<<(n_rays + 255) / 256, 256, 0, st>>>(raw, n_rays, out_rgb, out_disp, out_acc, out_depth);
+    composite_single_kernel<<<(n_rays + 255) / 256, 256, 0, st>>>(raw, n_rays, out_rgb, out_disp, out_acc, out_depth, rs, ds);
     LAUNCH_CHECK();
     return 0;
   }
   if ((S == 32 || S == 64 || S == 128) && !noise && static_cast<long long>(n_rays) * S >= comp::TILE_SAMPLES && aligned16(raw) &&
       aligned16(z) && aligned16(out_weights) && aligned16(out_alphas) && !composite_force_ldg()) {
-    if (S == 32) return launch_composite_tma<8>(raw, z, rays_d, n_rays, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-    if (S == 64) return launch_composite_tma<16>(raw, z, rays_d, n_rays, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-    return launch_composite_tma<32>(raw, z, rays_d, n_rays, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+    if (S == 32) return launch_composite_tma<8>(raw, z, rays_d, n_rays, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, rs, ds, st);
+    if (S == 64) return launch_composite_tma<16>(raw, z, rays_d, n_rays, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, rs, ds, st);
+    return launch_composite_tma<32>(raw, z, rays_d, n_rays, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, rs, ds, st);
   }
   // lanes per ray: four samples per lane and pass
-  if (S <= 4) launch_composite<1>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-  else if (S <= 8) launch_composite<2>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-  else if (S <= 16) launch_composite<4>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-  else if (S <= 32) launch_composite<8>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-  else if (S <= 64) launch_composite<16>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
-  else launch_composite<32>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, st);
+  if (S <= 4) launch_composite<1>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, rs, ds, st);
+  else if (S <= 8) launch_composite<2>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, rs, ds, st);
+  else if (S <= 16) launch_composite<4>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, rs, ds, st);
+  else if (S <= 32) launch_composite<8>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, rs, ds, st);
+  else if (S <= 64) launch_composite<16>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, rs, ds, st);
+  else launch_composite<32>(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights, out_alphas, rs, ds, st);
   LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int b200nerf_composite_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays,
+                                      int S, int white_bkgd, float* out_rgb, float* out_disp, float* out_acc,
+                                      float* out_depth, float* out_weights, float* out_alphas, void* stream) {
+  return composite_impl(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgb, out_disp, out_acc, out_depth, out_weights,
+                        out_alphas, 3, 1, stream);
+}
+
+extern "C" int b200nerf_composite_tile_fwd(const float* raw, const float* z, const float* rays_d, const float* noise, int n_rays,
+                                           int S, int white_bkgd, float* out_rgbd, float* out_acc, float* out_depth,
+                                           float* out_weights, float* out_alphas, void* stream) {
+  if (!out_rgbd) return fail("b200nerf_composite_tile_fwd: null tile");
+  return composite_impl(raw, z, rays_d, noise, n_rays, S, white_bkgd, out_rgbd, out_rgbd + 3, out_acc, out_depth, out_weights,
+                        out_alphas, 4, 4, stream);
 }
 
 // ------------------------------------------------------------------------------------------- MLP launches
 template <bool SPLIT, int INPUT>
 static int launch_chain(const ChainParams& p, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured[B200_MAX_DEVICES] = {false};
   constexpr int smem = chain_smem_bytes<SPLIT>();
-  if (!configured) {
+  const int dev = b200_device();
+  if (dev < 0) return fail("mlp_chain_kernel: no usable CUDA device");
+  if (!configured[dev]) {
     CUDA_TRY(cudaFuncSetAttribute(mlp_chain_kernel<SPLIT, INPUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+    configured[dev] = true;
   }
   const int sms = sm_count();
   if (sms <= 0) return fail("no CUDA device");
@@ -1138,7 +1168,10 @@ static int make_piece_tmap(const void* wpack, int rows, fast::TMap* out) {
 
 template <bool FP16>
 static int launch_fast(const fast::FastParams& p, cudaStream_t st) {
-  static int grid_cap = 0;
+  static int grid_caps[B200_MAX_DEVICES] = {0};
+  const int dev = b200_device();
+  if (dev < 0) return fail("nerf_fast_kernel: no usable CUDA device");
+  int& grid_cap = grid_caps[dev];
   constexpr int smem = fast::smem_bytes();
   constexpr int NCTA = fast::NCTA;
   auto kern = fast::nerf_fast_kernel<FP16>;
@@ -1253,12 +1286,11 @@ extern "C" int b200nerf_nerf_query(const b200nerf_nerf_model* nerf, const float*
   }
 }
 
-extern "C" int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_aux, int dn_hidden, int dn_prec,
-                                        const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d,
-                                        const float* viewdirs, int n_rays, int S, int mode, const float* offsets, float radius,
-                                        float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, int* ws_guard,
-                                        float* out_rgb, float* out_disp, float* out_acc, float* out_depth, float* out_weights,
-                                        void* stream) {
+static int render_depthnet_impl(const void* dn_wpack, const float* dn_aux, int dn_hidden, int dn_prec,
+                                const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d, const float* viewdirs,
+                                int n_rays, int S, int mode, const float* offsets, float radius, float near_, float far_,
+                                float* ws_mean, float* ws_z, float* ws_raw, int* ws_guard, float* out_rgb, float* out_disp,
+                                float* out_acc, float* out_depth, float* out_weights, int rs, int ds, void* stream) {
   if (n_rays == 0) return 0;
   if (!ws_mean || !ws_z || !ws_raw || !nerf) return fail("b200nerf_render_depthnet: null workspace or model");
   int rc = b200nerf_depthnet_fwd(dn_wpack, dn_aux, dn_hidden, dn_prec, rays_o, rays_d, n_rays, radius, near_, far_, ws_mean, stream);
@@ -1270,8 +1302,31 @@ extern "C" int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_au
   if (rc) return rc;
   // DepthNet path: noise 0 and white background regardless of the caller's flags (misspelled kwargs,
   // nerf_utils.py:858-865)
-  return b200nerf_composite_fwd(ws_raw, ws_z, rays_d, nullptr, n_rays, S, 1, out_rgb, out_disp, out_acc, out_depth, out_weights,
-                                nullptr, stream);
+  return composite_impl(ws_raw, ws_z, rays_d, nullptr, n_rays, S, 1, out_rgb, out_disp, out_acc, out_depth, out_weights, nullptr,
+                        rs, ds, stream);
+}
+
+extern "C" int b200nerf_render_depthnet(const void* dn_wpack, const float* dn_aux, int dn_hidden, int dn_prec,
+                                        const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d,
+                                        const float* viewdirs, int n_rays, int S, int mode, const float* offsets, float radius,
+                                        float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw, int* ws_guard,
+                                        float* out_rgb, float* out_disp, float* out_acc, float* out_depth, float* out_weights,
+                                        void* stream) {
+  return render_depthnet_impl(dn_wpack, dn_aux, dn_hidden, dn_prec, nerf, rays_o, rays_d, viewdirs, n_rays, S, mode, offsets, radius,
+                              near_, far_, ws_mean, ws_z, ws_raw, ws_guard, out_rgb, out_disp, out_acc, out_depth, out_weights, 3, 1,
+                              stream);
+}
+
+extern "C" int b200nerf_render_depthnet_tile(const void* dn_wpack, const float* dn_aux, int dn_hidden, int dn_prec,
+                                             const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d,
+                                             const float* viewdirs, int n_rays, int S, int mode, const float* offsets,
+                                             float radius, float near_, float far_, float* ws_mean, float* ws_z, float* ws_raw,
+                                             int* ws_guard, float* out_rgbd, float* out_acc, float* out_depth, float* out_weights,
+                                             void* stream) {
+  if (!out_rgbd) return fail("b200nerf_render_depthnet_tile: null tile");
+  return render_depthnet_impl(dn_wpack, dn_aux, dn_hidden, dn_prec, nerf, rays_o, rays_d, viewdirs, n_rays, S, mode, offsets, radius,
+                              near_, far_, ws_mean, ws_z, ws_raw, ws_guard, out_rgbd, out_rgbd + 3, out_acc, out_depth, out_weights, 4,
+                              4, stream);
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }

@@ -44,7 +44,8 @@ template <int LPR>
 __global__ void __launch_bounds__(THREADS, 2)
 composite_tma_kernel(const __grid_constant__ TMap tm_raw, const float* __restrict__ z, const float* __restrict__ rays_d,
                      int n_rays, int white, float* __restrict__ o_rgb, float* __restrict__ o_disp, float* __restrict__ o_acc,
-                     float* __restrict__ o_depth, float* __restrict__ o_w, float* __restrict__ o_alpha) {
+                     float* __restrict__ o_depth, float* __restrict__ o_w, float* __restrict__ o_alpha, int rgb_stride,
+                     int disp_stride) {
   constexpr int S = 4 * LPR;
   static_assert(LPR == 8 || LPR == 16 || LPR == 32, "S must be 32, 64 or 128");
   extern __shared__ uint8_t smem_raw_[];
@@ -177,10 +178,10 @@ composite_tma_kernel(const __grid_constant__ TMap tm_raw, const float* __restric
     if (live && (lig & (O2 - 1)) == 0) {
       if (h1 && h2) {
         if (o_depth) o_depth[ray] = v;
-        if (o_disp) o_disp[ray] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(v, __fadd_rn(s_a, 1e-10f))));
+        if (o_disp) o_disp[ray * disp_stride] = __fdiv_rn(1.0f, fmaxf(1e-10f, __fdiv_rn(v, __fadd_rn(s_a, 1e-10f))));
       } else {
         const int ch = (h1 ? 1 : 0) + (h2 ? 2 : 0);
-        if (o_rgb) o_rgb[ray * 3 + ch] = white ? v + __fadd_rn(1.0f, -s_a) : v;
+        if (o_rgb) o_rgb[ray * rgb_stride + ch] = white ? v + __fadd_rn(1.0f, -s_a) : v;
         if (ch == 0 && o_acc) o_acc[ray] = s_a;
       }
     }

@@ -6,6 +6,16 @@
 int b200_fail(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_b200_launches;
 
+// One-time kernel setup (cudaFuncSetAttribute, occupancy-derived grid caps, SM counts) is cached PER DEVICE ORDINAL: function
+// attributes and occupancy are per-device state, and the host API accepts tensors on any device of the process.  The caches are
+// plain arrays written with idempotent values, so concurrent first calls from two threads are benign.
+constexpr int B200_MAX_DEVICES = 64;
+static inline int b200_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= B200_MAX_DEVICES) return -1;
+  return d;
+}
+
 #define CUDA_TRY(expr)                                                                                   \
   do {                                                                                                   \
     cudaError_t e__ = (expr);                                                                            \

@@ -152,20 +152,19 @@ static GemmProb prob_wgrad(int n, int M, int K, const float* dY, int ldy, const 
   return q;
 }
 
-static int g_sm_count = 0;
 static long long* g_tgemm_dbg = nullptr;
 /* diagnostics: device buffer of 16 int64; CTA 0 of every grouped-GEMM launch writes its phase time stamps (ns) there */
 extern "C" void b200nerf_debug_set_tgemm_timeline(long long* dev_buf) { g_tgemm_dbg = dev_buf; }
 static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
   namespace tg = b200::tg;
-  static bool configured = false;
-  if (!configured) {
+  static int sm_counts[B200_MAX_DEVICES] = {0};
+  const int dev = b200_device();
+  if (dev < 0) return b200_fail("tgemm_group: no usable CUDA device");
+  if (sm_counts[dev] == 0) {
     CUDA_TRY(cudaFuncSetAttribute(tg::tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_BYTES));
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
+    CUDA_TRY(cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev));
   }
+  const int g_sm_count = sm_counts[dev];
   if (nprob < 1 || nprob > tg::MAX_PROB) return b200_fail("tgemm_group: %d problems", nprob);
   tg::Group g;
   memset(&g, 0, sizeof(g));

@@ -5,7 +5,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .. import ops
+from .. import ops, packing
 from ..packing import PREC_SPLIT, PackedDepthNet
 
 
@@ -50,7 +50,7 @@ class DepthNet(nn.Module):
 
     def packed(self) -> PackedDepthNet:
         params = list(self.parameters())
-        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (self.precision, packing.generation()) + tuple((p.data_ptr(), p._version) for p in params)
         if self._packed is None or key != self._packed_key:
             self._packed = PackedDepthNet(self.state_dict(), params[0].device, self.precision)
             self._packed_key = key

@@ -116,75 +116,211 @@ def _write_png(path: str, rgb8) -> None:
                 + chunk(b"IDAT", zlib.compress(rows.tobytes(), 3)) + chunk(b"IEND", b""))
 
 
-def _pinned_views(n, H, W):
-    """Page-locked host slabs for n rendered views from torch's caching host allocator: the first call pays cudaHostAlloc
-    (~10 MB per view), later calls of the same size reuse the block once the previous results have been dropped."""
-    return torch.empty(n, H, W, 3, dtype=torch.float32, pin_memory=True), torch.empty(n, H, W, dtype=torch.float32, pin_memory=True)
+def write_video(path: str, rgbs) -> None:
+    """``imageio.mimwrite(video.mp4)`` of Trainer.py:224-229 when imageio (+ffmpeg) exists; the PNG frames are always written."""
+    try:
+        import imageio
+
+        imageio.mimwrite(path, run_nerf_helpers.to8b(rgbs), fps=30, quality=8)
+    except Exception as e:  # no encoder in this environment
+        print(f"[b200nerf] video not written ({type(e).__name__}); frames are in {os.path.dirname(path)}")
+
+
+class _HostRing:
+    """Page-locked staging slots for finished views (cudaHostAlloc is slow, so the ring is cached per shape and reused by
+    later calls); a slot is recycled once the worker that unloads it into the result arrays has finished."""
+
+    _cache = {}
+
+    def __init__(self, shape, slots):
+        self.bufs = [torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(slots)]
+        self.busy = [None] * slots   # the future that still reads the slot
+
+    @classmethod
+    def get(cls, shape, slots=4):
+        key = (tuple(shape), slots)
+        ring = cls._cache.get(key)
+        if ring is None:
+            ring = cls._cache[key] = cls(shape, slots)
+        return ring
+
+    def acquire(self, i):
+        k = i % len(self.bufs)
+        if self.busy[k] is not None:
+            self.busy[k].result()
+            self.busy[k] = None
+        return k, self.bufs[k]
+
+
+def _plain_depthnet_mode(trainer, render_kwargs):
+    return not (trainer.compare_nerf or trainer.use_nerf_max_pts or trainer.use_full_nerf
+                or getattr(trainer, "save_scene_data", False)) and render_kwargs.get("use_viewdirs", False)
+
+
+def _render_tile(H, W, K, c2w, lo, hi, chunk, render_kwargs, want_extras, out=None):
+    """rgb|disp tile [hi-lo, 4] of rays [lo, hi) of one view (+ extras dict of the slice when asked).
+
+    Plain DepthNet mode is ONE C call whose composite kernel writes the 16-byte pixels itself
+    (``b200nerf_render_depthnet_tile``); the NeRF-comparison modes go through ``render_test`` on the ray slice."""
+    trainer = render_kwargs["trainer"]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rays_o, rays_d, viewdirs = ops.get_rays(H, W, K, c2w, dev)
+    if (lo, hi) != (0, H * W):
+        rays_o, rays_d, viewdirs = rays_o[lo:hi], rays_d[lo:hi], viewdirs[lo:hi]
+    if _plain_depthnet_mode(trainer, render_kwargs) and not want_extras:
+        dn = render_kwargs["depth_network"]
+        net = render_kwargs["network_fine"] if render_kwargs.get("network_fine") is not None else render_kwargs["network_fn"]
+        res = ops.render_depthnet(dn.packed(), net.packed(), rays_o, rays_d, viewdirs, trainer.n_depth_samples,
+                                  trainer.sampling_mode, trainer.distance, radius=float(dn.sphere_radius), near=float(dn.near),
+                                  far=float(dn.far), want_weights=False, tile=True, tile_out=out)
+        return res["rgbd"], {}
+    kw = dict(render_kwargs)
+    near, far = kw.pop("near"), kw.pop("far")
+    ndc, use_viewdirs = kw.pop("ndc", False), kw.pop("use_viewdirs", False)
+    n = hi - lo
+    packed = torch.cat([rays_o, rays_d, torch.full((n, 1), float(near), device=dev), torch.full((n, 1), float(far), device=dev)]
+                       + ([viewdirs] if use_viewdirs else []), -1)
+    if ndc:
+        raise NotImplementedError("NDC rays (LLFF forward-facing scenes) are outside the Blender/DepthNet path")
+    ret = batchify_rays_test(packed, chunk, **kw)
+    tile = out if out is not None else torch.empty(n, 4, device=dev)
+    tile[:, :3] = ret["depth_net_rgb_map"]
+    tile[:, 3] = ret["depth_net_disp_map"]
+    return tile, ret
 
 
 def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=False, save_scene_data=False, gt_imgs=None,
-                savedir=None, render_factor=0):
+                savedir=None, render_factor=0, group=None, shard=None):
     """Render a list of camera poses (nerf_utils.py:258-360) -> (rgbs [n,H,W,3], disps [n,H,W], mean PSNR) as numpy.
 
-    Same results as the reference's loop, different schedule: view k+1 is rendered while view k's rgb / disp travel to
-    pinned host memory on a side stream, and PNG encoding (``savedir``) runs in worker threads, so the GPU never waits
-    for ``.cpu().numpy()``, PSNR arithmetic or file I/O.  ``wandb_log`` is accepted and ignored (logging is caller
-    context); ``save_scene_data`` collects ``depth_net_pts`` / ``depth_net_weights`` like the reference."""
+    Same results as the reference's loop, different schedule: view k+1 is rendered while view k's pixels travel to pinned
+    host memory on a side stream, and unloading / PNG encoding (``savedir``) runs in worker threads, so the GPU never waits
+    for ``.cpu().numpy()``, PSNR arithmetic or file I/O.
+
+    Multi-GPU (one process per GPU, ``torch.distributed`` initialised): ``shard="views"`` gives view i to rank
+    ``i % world`` (throughput: BASELINE config #3), ``shard="rays"`` gives every rank the contiguous ray slice
+    ``parallel.shard_bounds(H*W, world, rank)`` of EVERY view (latency / strong scaling).  Either way a rank writes its
+    finished pixels as one [n_local, 4] rgb|disp tile, the tiles are all-gathered with NCCL on a side stream while the next
+    view renders (double-buffered), and every rank returns the full image stack.  Rays are independent, so the sharded images
+    are bit-identical to the single-GPU ones.  ``shard=None`` (default) renders every pose on the calling rank.
+
+    ``wandb_log`` switches ``trainer.compare_nerf`` on like the reference (:294-295; the ray plots themselves are the host
+    application's); ``save_scene_data`` collects ``depth_net_pts`` / ``depth_net_weights`` for this call only."""
     import concurrent.futures
 
     import numpy as np
+    import torch.distributed as dist
+
+    from .. import parallel
 
     H, W, focal = hwf
     H, W = int(H), int(W)
     if render_factor != 0:
         H, W, focal = H // render_factor, W // render_factor, focal / render_factor
-    n = len(render_poses)
+    poses = torch.as_tensor(np.asarray(render_poses.detach().cpu()) if isinstance(render_poses, torch.Tensor) else np.asarray(render_poses),
+                            dtype=torch.float32)   # one D2H for all poses: the ray kernel takes the matrix by value
+    n = poses.shape[0]
+    n_rays = H * W
     trainer = render_kwargs["trainer"]
+    if wandb_log:
+        trainer.compare_nerf = True
+    prev_ssd = getattr(trainer, "save_scene_data", False)
     if save_scene_data:
         trainer.save_scene_data = True
+    world, rank = 1, 0
+    if shard is not None:
+        if shard not in ("views", "rays"):
+            raise ValueError("shard must be None, 'views' or 'rays'")
+        if dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world = max(world, 1)
+    sharded = world > 1
+    if sharded and (save_scene_data or trainer.compare_nerf):
+        raise NotImplementedError("per-sample extras (save_scene_data / compare_nerf) are not gathered across ranks")
+
     dev = torch.device("cuda", torch.cuda.current_device())
-    h_rgb, h_disp = _pinned_views(n, H, W)
-    copy_stream = torch.cuda.Stream(device=dev)
-    done = []
+    main = torch.cuda.current_stream()
+    side = _side_stream(dev)
+    rgbs = np.empty((n, H, W, 3), np.float32)
+    disps = np.empty((n, H, W), np.float32)
+    pool = concurrent.futures.ThreadPoolExecutor(max_workers=4)
     all_pts, all_weights, mses = [], [], []
-    pool = concurrent.futures.ThreadPoolExecutor(max_workers=4) if savedir is not None else None
-    jobs = []
     if savedir is not None:
         os.makedirs(savedir, exist_ok=True)
 
-    def save_png(i, ev):
+    def unload(views, host, ev):
+        """worker: wait for the D2H, de-interleave the rgb|disp pixels into the result arrays, encode PNGs."""
         ev.synchronize()
-        rgb8 = run_nerf_helpers.to8b(h_rgb[i].numpy())
-        _write_png(os.path.join(savedir, "{:03d}.png".format(i)), rgb8)
+        px = host.numpy()
+        for j, i in enumerate(views):
+            if i >= n:
+                continue
+            t = px[j].reshape(H, W, 4)
+            rgbs[i] = t[..., :3]
+            disps[i] = t[..., 3]
+            if savedir is not None:
+                _write_png(os.path.join(savedir, "{:03d}.png".format(i)), run_nerf_helpers.to8b(rgbs[i]))
 
-    for i, c2w in enumerate(render_poses):
-        c2w = torch.as_tensor(c2w)
-        rgb, disp, extras = render_test(H, W, K, chunk=chunk, c2w=c2w[:3, :4], **render_kwargs)
-        ready = torch.cuda.Event()
-        ready.record()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ready)
-            h_rgb[i].copy_(rgb, non_blocking=True)
-            h_disp[i].copy_(disp, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        rgb.record_stream(copy_stream)
-        disp.record_stream(copy_stream)
-        done.append(ev)
-        if trainer.compare_nerf and extras.get("max_z_vals") is not None:
-            # F.mse_loss(max_z [H,W,1], z_vals [H,W,S]) broadcasts over the samples in the reference (:311-316)
-            mses.append(torch.mean((extras["max_z_vals"] - extras["depth_net_z_vals"]) ** 2))
-        if save_scene_data and savedir is not None:
-            all_pts.append(torch.flatten(extras["depth_net_pts"], end_dim=2))
-            all_weights.append(torch.flatten(extras["depth_net_weights"], end_dim=2))
-        if pool is not None:
-            jobs.append(pool.submit(save_png, i, ev))
-    copy_stream.synchronize()
-    for j in jobs:
-        j.result()
-    if pool is not None:
-        pool.shutdown()
-    rgbs, disps = h_rgb.numpy(), h_disp.numpy()   # views of the pinned slabs (kept alive by the arrays)
+    try:
+        if not sharded:
+            ring = _HostRing.get((1, n_rays, 4))
+            for i in range(n):
+                want_extras = trainer.compare_nerf or save_scene_data
+                tile, extras = _render_tile(H, W, K, poses[i, :3, :4], 0, n_rays, chunk, render_kwargs, want_extras)
+                k, host = ring.acquire(i)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    host[0].copy_(tile, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                tile.record_stream(side)
+                ring.busy[k] = pool.submit(unload, [i], host, ev)
+                if trainer.compare_nerf and extras.get("max_z_vals") is not None:
+                    # F.mse_loss(max_z [H,W,1], z_vals [H,W,S]) broadcasts over the samples in the reference (:311-316)
+                    mses.append(torch.mean((extras["max_z_vals"] - extras["depth_net_z_vals"]) ** 2))
+                if save_scene_data and savedir is not None:
+                    all_pts.append(extras["depth_net_pts"].reshape(-1, 3))
+                    all_weights.append(extras["depth_net_weights"].reshape(-1))
+        else:
+            rounds = (n + world - 1) // world if shard == "views" else n
+            lo, hi = (0, n_rays) if shard == "views" else parallel.shard_bounds(n_rays, world, rank)
+            per = n_rays if shard == "views" else (n_rays + world - 1) // world   # padded tile rows (ragged ray shards)
+            ring = _HostRing.get((world, per, 4), slots=2)
+            tiles = [torch.zeros(per, 4, device=dev) for _ in range(2)]
+            gathered = [torch.empty(world, per, 4, device=dev) for _ in range(2)]
+            reusable = [None, None]   # event: the D2H that read gathered[b] (and the gather that read tiles[b]) has finished
+            for r in range(rounds):
+                b = r & 1
+                view = r * world + rank if shard == "views" else r
+                if reusable[b] is not None:
+                    main.wait_event(reusable[b])
+                if view < n:
+                    _render_tile(H, W, K, poses[view, :3, :4], lo, hi, chunk, render_kwargs, False, out=tiles[b][: hi - lo])
+                k, host = ring.acquire(r)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    dist.all_gather_into_tensor(gathered[b].view(world * per, 4), tiles[b], group=group)
+                    host.copy_(gathered[b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                reusable[b] = ev
+                if shard == "views":
+                    ring.busy[k] = pool.submit(unload, [r * world + q for q in range(world)], host, ev)
+                else:
+                    ring.busy[k] = pool.submit(_unload_ray_shards, host, ev, world, n_rays, H, W, r, rgbs, disps, savedir)
+        side.synchronize()
+        for fut in ring.busy:
+            if fut is not None:
+                fut.result()
+        ring.busy = [None] * len(ring.busy)
+    finally:
+        pool.shutdown(wait=True)
+        trainer.save_scene_data = prev_ssd
+
     total_psnr = 0.0
     if gt_imgs is not None and render_factor == 0:
         lines = []
@@ -200,6 +336,36 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
     if save_scene_data and savedir is not None:
         torch.save({"all_pts": torch.cat(all_pts), "all_weights": torch.cat(all_weights)}, os.path.join(savedir, "scene_data.pt"))
     return rgbs, disps, total_psnr / max(n, 1)
+
+
+def _unload_ray_shards(host, ev, world, n_rays, H, W, view, rgbs, disps, savedir):
+    """worker for shard="rays": stitch the ranks' ray slices (padded to equal length for the all-gather) into view ``view``."""
+    import numpy as np
+
+    from .. import parallel
+
+    ev.synchronize()
+    px = host.numpy()
+    full = np.empty((n_rays, 4), np.float32)
+    for q in range(world):
+        a, b = parallel.shard_bounds(n_rays, world, q)
+        full[a:b] = px[q, : b - a]
+    full = full.reshape(H, W, 4)
+    rgbs[view] = full[..., :3]
+    disps[view] = full[..., 3]
+    if savedir is not None:
+        _write_png(os.path.join(savedir, "{:03d}.png".format(view)), run_nerf_helpers.to8b(rgbs[view]))
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """One persistent copy / collective stream per device (stream creation per call churns the driver)."""
+    s = _SIDE_STREAMS.get(dev)
+    if s is None:
+        s = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return s
 
 
 def sample_as_in_NeRF(ray_batch, network_fn, network_fine, network_query_fn, N_samples, trainer, perturb, raw_noise_std,

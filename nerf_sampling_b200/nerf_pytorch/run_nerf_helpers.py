@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, packing
 from ..packing import PREC_FAST, PackedNeRF
 
 img2mse = lambda x, y: torch.mean((x - y) ** 2)  # noqa: E731  (run_nerf_helpers.py:9)
@@ -85,7 +85,7 @@ class NeRF(nn.Module):
         """Packed weight image for the current parameter values (rebuilt when a parameter changes)."""
         self._check_supported()
         params = list(self.parameters())
-        key = (self.precision,) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (self.precision, packing.generation()) + tuple((p.data_ptr(), p._version) for p in params)
         if self._packed is None or key != self._packed_key:
             self._packed = PackedNeRF(self.state_dict(), params[0].device, self.precision)
             self._packed_key = key

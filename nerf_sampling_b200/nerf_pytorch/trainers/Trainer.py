@@ -4,6 +4,7 @@ the constructor's config bag (:18-130), intrinsics (:136-146), ``core_optimizati
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -32,7 +33,91 @@ class Trainer:
         self.K = self.global_step = self.W = self.H = self.c2w = None
 
     def load_data(self):
-        raise NotImplementedError("dataset loading is outside the B200 hot path; feed poses/rays directly")
+        """-> (hwf, poses, i_test, i_val, i_train, images, render_poses).  Dataset readers are the host application's
+        (out of scope): ``nerf_sampling_b200.plugin.B200DepthNetTrainer`` inherits the reference's Blender
+        loader; a standalone user overrides this method."""
+        raise NotImplementedError("dataset loading is outside the B200 hot path: use nerf_sampling_b200.plugin."
+                                  "B200DepthNetTrainer (inherits the reference's loaders) or override load_data()")
+
+    def create_log_dir_and_copy_the_config_file(self):
+        """args.txt / config.txt next to the checkpoints (Trainer.py:148-160)."""
+        d = os.path.join(self.basedir, self.expname)
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "args.txt"), "w") as f:
+            for k, v in self.__dict__.items():
+                if not k.startswith("_b200"):
+                    f.write("{} = {}\n".format(k, v))
+        if self.config_path is not None:
+            with open(os.path.join(d, "config.txt"), "w") as f, open(self.config_path) as src:
+                f.write(src.read())
+
+    # ------------------------------------------------------------------ drivers (Trainer.py:181-230, 263-398, 712-787)
+    def render(self, render_test, save_scene_data, images, i_test, render_poses, hwf, render_kwargs_test):
+        """Render ``render_poses`` to ``<basedir>/<expname>/renderonly_*`` and return the mean PSNR against the test images
+        (Trainer.py:181-230); PNG frames always, ``video.mp4`` when an encoder is installed."""
+        with torch.no_grad():
+            gt = images[i_test] if render_test else None
+            savedir = os.path.join(self.basedir, self.expname,
+                                   "renderonly_{}_{:06d}".format("test" if render_test else "path", self.global_step))
+            os.makedirs(savedir, exist_ok=True)
+            rgbs, _, avg_test_psnr = nerf_utils.render_path(render_poses, hwf, self.K, self.chunk, render_kwargs_test,
+                                                            step=self.global_step, save_scene_data=save_scene_data, gt_imgs=gt,
+                                                            savedir=savedir, render_factor=self.render_factor)
+            nerf_utils.write_video(os.path.join(savedir, "video.mp4"), rgbs)
+        return avg_test_psnr
+
+    def log(self, i, render_poses, hwf, poses, i_test, i_train, images, loss, depth_net_loss, psnr, render_kwargs_train,
+            render_kwargs_test, optimizer, sampling_optimizer):
+        """Periodic test-set render, checkpoint and progress line (the wandb / optuna reporting of Trainer.py:263-398 belongs
+        to the host application and is not mirrored)."""
+        if i % self.i_testset == 0 and i > 0:
+            savedir = os.path.join(self.basedir, self.expname, "testset_{:06d}".format(i))
+            with torch.no_grad():
+                nerf_utils.render_path(self._host_poses(poses)[i_test], hwf, self.K, self.chunk, render_kwargs_test,
+                                       step=self.global_step, save_scene_data=self.save_scene_data, gt_imgs=images[i_test],
+                                       savedir=savedir)
+        if i % self.i_weights == 0:
+            from .. import utils
+
+            utils.save_state(global_step=self.global_step, network_fn=render_kwargs_train["network_fn"],
+                             network_fine=render_kwargs_train["network_fine"], optimizer=optimizer,
+                             depth_network=render_kwargs_train["depth_network"], sampling_optimizer=sampling_optimizer,
+                             path=os.path.join(self.basedir, self.expname, "{:06d}.tar".format(i)))
+        if i % self.i_print == 0:
+            info = f"Iter: {i} Loss: {loss.item()}, Depth Net Loss: {depth_net_loss.item()}, PSNR: {psnr.item():.5f}"
+            print(info)
+            with open(os.path.join(self.basedir, self.expname, "psnr.txt"), "a") as f:
+                f.write(info + "\n")
+
+    def train(self, N_iters=200000 + 1):
+        """load_data -> models -> (render only | optimisation loop), the control flow of Trainer.py:712-787."""
+        from .. import utils
+
+        hwf, poses, i_test, i_val, i_train, images, render_poses = self.load_data()
+        if self.render_test:
+            render_poses = torch.as_tensor(np.array(self._host_poses(poses)[i_test]))
+        hwf = self.cast_intrinsics_to_right_types(hwf=hwf)
+        self.create_log_dir_and_copy_the_config_file()
+        optimizer, sampling_optimizer, render_kwargs_train, render_kwargs_test = self.create_nerf_model()
+        if self.train_depth_net_only:
+            for key in ("network_fn", "network_fine"):
+                if render_kwargs_train[key] is not None:
+                    utils.freeze_model(render_kwargs_train[key])
+        if self.render_only:
+            return self.render(self.render_test, self.save_scene_data, images, i_test, render_poses, hwf, render_kwargs_test)
+        if self.use_batching:
+            raise NotImplementedError("pre-shuffled ray batching (no_batching=False) needs the host application's "
+                                      "prepare_raybatch_tensor_if_batching_random_rays; the lego configuration uses no_batching")
+        psnr = None
+        for i in range(self.start + 1, N_iters):
+            _, _, batch_rays, target_s = self.sample_random_ray_batch(None, None, i_train, images, poses, i)
+            loss, depth_net_loss, psnr, _ = self.core_optimization_loop(sampling_optimizer, render_kwargs_train, batch_rays, i, target_s)
+            self.update_learning_rate(optimizer)
+            self.log(i=i, render_poses=render_poses, hwf=hwf, poses=poses, i_test=i_test, i_train=i_train, images=images,
+                     loss=loss, depth_net_loss=depth_net_loss, psnr=psnr, render_kwargs_train=render_kwargs_train,
+                     render_kwargs_test=render_kwargs_test, optimizer=optimizer, sampling_optimizer=sampling_optimizer)
+            self.global_step += 1
+        return psnr
 
     def cast_intrinsics_to_right_types(self, hwf):
         H, W, focal = hwf
@@ -60,8 +145,8 @@ class Trainer:
             return rays_rgb, i_batch, batch_rays, target_s
         img_i = 42 if self.single_image else int(np.random.choice(i_train))
         dev = torch.device(self.device if str(self.device) != "cpu" else "cuda")
-        target = torch.as_tensor(images[img_i], dtype=torch.float32).to(dev)
-        self.c2w = torch.as_tensor(poses[img_i])[:3, :4].clone().detach()
+        target = self._device_image(images, img_i, dev)
+        self.c2w = self._host_poses(poses)[img_i, :3, :4].clone()
         if i < self.precrop_iters:
             dH, dW = int(self.H // 2 * self.precrop_frac), int(self.W // 2 * self.precrop_frac)
             h0, w0, hh, ww = self.H // 2 - dH, self.W // 2 - dW, 2 * dH, 2 * dW
@@ -78,6 +163,24 @@ class Trainer:
         rays_o, rays_d, _ = ops.get_rays_at(self.H, self.W, self.K, self.c2w, pix)
         target_s = ops.gather_pixels(target[..., :3].contiguous(), pix)
         return rays_rgb, i_batch, torch.stack([rays_o, rays_d], 0), target_s
+
+    def _device_image(self, images, img_i: int, dev) -> torch.Tensor:
+        """Training image ``img_i`` as a device tensor, uploaded once (the reference re-wraps the host array every step,
+        Trainer.py:421-422: 7.7 MB of pageable H2D per step at 800x800)."""
+        cache = self.__dict__.get("_b200_images")
+        if cache is None or cache["owner"] is not images:
+            cache = self.__dict__["_b200_images"] = {"owner": images, "dev": {}}
+        t = cache["dev"].get(img_i)
+        if t is None:
+            t = cache["dev"][img_i] = torch.as_tensor(images[img_i], dtype=torch.float32).to(dev).contiguous()
+        return t
+
+    def _host_poses(self, poses) -> torch.Tensor:
+        """Camera poses on the host (the kernels take the 3x4 matrix by value): one D2H for the whole run, not one per step."""
+        cache = self.__dict__.get("_b200_poses")
+        if cache is None or cache[0] is not poses:
+            cache = self.__dict__["_b200_poses"] = (poses, torch.as_tensor(poses).detach().to("cpu", torch.float32))
+        return cache[1]
 
     # ------------------------------------------------------------------ one optimisation step (config #5)
     def core_optimization_loop(self, sampling_optimizer, render_kwargs_train, batch_rays, i, target_s):

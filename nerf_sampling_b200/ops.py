@@ -180,8 +180,11 @@ def composite(raw, z, rays_d, white_bkgd=True, noise=None, want_alphas=True):
 
 
 def render_depthnet(dn: PackedDepthNet, nerf: PackedNeRF, rays_o, rays_d, viewdirs, n_samples: int, mode: str, std: float,
-                    radius=2.0, near=2.0, far=6.0, noise=None, want_weights=True):
-    """DepthNet branch of render_rays_test for rays on the device (nerf_utils.py:834-866), one C call."""
+                    radius=2.0, near=2.0, far=6.0, noise=None, want_weights=True, tile=False, tile_out=None):
+    """DepthNet branch of render_rays_test for rays on the device (nerf_utils.py:834-866), one C call.
+
+    ``tile=True`` (or a preallocated ``tile_out`` [N,4]) makes the composite kernel write one 16-byte (r, g, b, disp) pixel per
+    ray -- the layout the multi-GPU render all-gathers and render_path ships to the host -- instead of separate maps."""
     rays_o, rays_d, viewdirs = _dev(rays_o, "rays_o"), _dev(rays_d, "rays_d"), _dev(viewdirs, "viewdirs")
     n = rays_o.shape[0]
     dev = rays_o.device
@@ -197,20 +200,30 @@ def render_depthnet(dn: PackedDepthNet, nerf: PackedNeRF, rays_o, rays_d, viewdi
     mean = torch.empty(n, 1, device=dev)
     z = torch.empty(n, s, device=dev)
     raw = torch.empty(n, s, 4, device=dev)
-    rgb = torch.empty(n, 3, device=dev)
-    disp = torch.empty(n, device=dev)
     acc = torch.empty(n, device=dev)
     depth = torch.empty(n, device=dev)
     sw = s if s > 1 else 0
     weights = torch.empty(n, sw, device=dev) if want_weights else None
     ws = torch.empty(n + 4, device=dev, dtype=torch.int32) if nerf.prec == PREC_FAST else None
     model = nerf.c_model()
+    common = (_p(dn.wpack), _p(dn.aux), dn.n_hidden, dn.prec, C.byref(model), _p(rays_o), _p(rays_d), _p(viewdirs),
+              n, s, PLACE_MODES[mode], _p(offs), float(radius), float(near), float(far), _p(mean), _p(z), _p(raw), _p(ws))
+    tail = (_p(acc), _p(depth), _p(weights) if (want_weights and sw) else None, _stream())
+    out = dict(acc=acc, depth=depth, weights=weights, z=z, raw=raw, z_mean=mean, guard_ws=ws)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().b200nerf_render_depthnet(
-            _p(dn.wpack), _p(dn.aux), dn.n_hidden, dn.prec, C.byref(model), _p(rays_o), _p(rays_d), _p(viewdirs),
-            n, s, PLACE_MODES[mode], _p(offs), float(radius), float(near), float(far), _p(mean), _p(z), _p(raw), _p(ws), _p(rgb),
-            _p(disp), _p(acc), _p(depth), _p(weights) if (want_weights and sw) else None, _stream()))
-    return dict(rgb=rgb, disp=disp, acc=acc, depth=depth, weights=weights, z=z, raw=raw, z_mean=mean, guard_ws=ws)
+        if tile or tile_out is not None:
+            if tile_out is None:
+                tile_out = torch.empty(n, 4, device=dev)
+            elif tuple(tile_out.shape) != (n, 4) or not tile_out.is_contiguous() or tile_out.dtype != torch.float32 or tile_out.device != dev:
+                raise _lib.B200NerfError("tile_out must be a contiguous fp32 [n_rays, 4] tensor on the rays' device")
+            _lib.check(_lib.lib().b200nerf_render_depthnet_tile(*common, _p(tile_out), *tail))
+            out.update(rgbd=tile_out, rgb=tile_out[:, :3], disp=tile_out[:, 3])
+        else:
+            rgb = torch.empty(n, 3, device=dev)
+            disp = torch.empty(n, device=dev)
+            _lib.check(_lib.lib().b200nerf_render_depthnet(*common, _p(rgb), _p(disp), *tail))
+            out.update(rgb=rgb, disp=disp)
+    return out
 
 
 def coarse_z(near, far, n_rays: int, n_samples: int, lindisp: bool, t_rand: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -31,6 +31,28 @@ NERF_SHAPES = {
 }
 
 
+_GENERATION = 0
+
+
+def mark_updated(params) -> None:
+    """Tell the pack caches that ``params`` were rewritten through raw device pointers.
+
+    ``NeRF.packed()`` / ``DepthNet.packed()`` key their packed images on ``(data_ptr, _version)`` of every parameter.
+    torch bumps ``_version`` on its own in-place ops, but the library's fused Adam (``b200nerf_adam_step_multi_dev``) and
+    CUDA-graph replays write behind torch's back; every such writer calls this, which bumps the version counters (one
+    batched call) or, if this torch build lacks the hook, a global generation that is part of every cache key."""
+    global _GENERATION
+    params = [p for p in params if isinstance(p, torch.Tensor)]
+    try:
+        torch._C._autograd._unsafe_set_version_counter(params, [p._version + 1 for p in params])
+    except Exception:
+        _GENERATION += 1
+
+
+def generation() -> int:
+    return _GENERATION
+
+
 def _host_f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(device="cpu", dtype=torch.float32).contiguous()
 

@@ -13,7 +13,7 @@ from typing import List
 
 import torch
 
-from . import _lib
+from . import _lib, packing
 
 
 def _stream() -> int:
@@ -157,8 +157,13 @@ class Adam(torch.optim.Optimizer):
         buf = bufs.get(gi)
         if buf is None:
             n = len(group["params"])
-            buf = dict(step=torch.zeros((), dtype=torch.int32, device=dev), hyper_host=torch.zeros(5).pin_memory(),
-                       hyper=torch.zeros(5, device=dev), ptrs=None, table=None, table_host=None,
+            buf = dict(step=torch.zeros((), dtype=torch.int32, device=dev), hyper=torch.zeros(5, device=dev),
+                       # eager steps rotate through pinned blocks, each guarded by an event recorded after its upload: the
+                       # CPU never rewrites a block whose host->device copy may still be pending
+                       hyper_ring=[[torch.zeros(5).pin_memory(), None] for _ in range(4)], hyper_slot=0,
+                       # the block a captured graph's memcpy node re-reads on every replay (set_hyper rewrites it)
+                       hyper_host=torch.zeros(5).pin_memory(),
+                       ptrs=None, table=None, table_host=None,
                        # used only while a CUDA graph is being captured (no page-locked allocation may happen then, and the
                        # graph's memcpy node re-reads this buffer on every replay, so eager steps must never touch it)
                        graph_table_host=torch.zeros(n, 5, dtype=torch.int64).pin_memory(),
@@ -208,34 +213,79 @@ class Adam(torch.optim.Optimizer):
                         buf["table"] = host.to(dev, non_blocking=True)
                         buf["keep"] = [g for _, g, _ in rows]
                     table = buf["table"]
-                hh = buf["hyper_host"]
-                hh[0], hh[1], hh[2], hh[3], hh[4] = float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(grad_scale)
-                buf["hyper"].copy_(hh, non_blocking=True)   # in a captured graph: a memcpy node that re-reads the host values
+                vals = [float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(grad_scale)]
+                if capturing:
+                    hh = buf["hyper_host"]
+                    hh.numpy()[:] = vals
+                    buf["hyper"].copy_(hh, non_blocking=True)   # a memcpy node that re-reads the host values on every replay
+                else:
+                    slot = buf["hyper_ring"][buf["hyper_slot"]]
+                    buf["hyper_slot"] = (buf["hyper_slot"] + 1) % len(buf["hyper_ring"])
+                    if slot[1] is not None:
+                        slot[1].synchronize()
+                    slot[0].numpy()[:] = vals
+                    buf["hyper"].copy_(slot[0], non_blocking=True)
+                    slot[1] = torch.cuda.Event()
+                    slot[1].record()
                 _lib.check(L.b200nerf_adam_step_multi_dev(table.data_ptr(), len(rows), buf["hyper"].data_ptr(),
                                                           buf["step"].data_ptr(), _stream()))
+            # the kernel wrote the parameters through raw pointers: invalidate the packed inference images
+            packing.mark_updated([p for p, _, _ in rows])
         return None
 
-    def set_hyper(self, grad_scale: float = 1.0):
-        """Refresh the pinned hyper-parameter block before replaying a captured step (lr may have been changed on the group)."""
+    def params(self):
+        return [p for g in self.param_groups for p in g["params"]]
+
+    @torch.no_grad()
+    def init_state(self):
+        """Create the moment buffers and resolve a checkpoint-loaded step count now (both would otherwise happen lazily inside
+        ``step``, which must not allocate pinned memory or synchronise while a CUDA graph is being captured)."""
+        for gi, group in enumerate(self.param_groups):
+            ps = [p for p in group["params"] if p.requires_grad]
+            if not ps:
+                continue
+            buf = self._group_buffers(gi, group, ps[0].device)
+            for p in ps:
+                st = self.state[p]
+                if "exp_avg" not in st:
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                prev = st.get("step")
+                if prev is not buf["step"]:
+                    if prev is not None and int(prev) > int(buf["step"]):
+                        buf["step"].fill_(int(prev))
+                    st["step"] = buf["step"]
+
+    def set_hyper(self, grad_scale: float = None):
+        """Refresh the pinned hyper-parameter block before replaying a captured step (lr may have been changed on the group);
+        ``grad_scale=None`` keeps the value the capture recorded."""
         for gi, group in enumerate(self.param_groups):
             buf = self.__dict__.get("_b200_bufs", {}).get(gi)
             if buf is not None:
                 b1, b2 = group["betas"]
                 hh = buf["hyper_host"]
-                hh[0], hh[1], hh[2], hh[3], hh[4] = float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(grad_scale)
+                vals = [float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(hh[4]) if grad_scale is None else float(grad_scale)]
+                if hh.tolist() != [float(torch.tensor(v, dtype=torch.float32)) for v in vals]:
+                    # a replay still in flight may be about to read the block: drain it before the (rare) rewrite
+                    torch.cuda.current_stream().synchronize()
+                    hh.numpy()[:] = vals
 
 
 class GraphedTrainStep:
-    """``Trainer.core_optimization_loop`` with its device work captured in ONE CUDA graph (render, zero_grad, both backward
-    passes: ~440 small launches, launch-bound from Python at 512 rays per GPU); the gradient all-reduce and the two-launch
-    Adam step follow eagerly, so no collective is ever captured.
+    """``Trainer.core_optimization_loop`` as ONE CUDA graph: training render, zero_grad, both backward passes, the flat NCCL
+    gradient all-reduce and the fused Adam step (~90 launches, launch-bound from Python at 512 rays per GPU).
 
         step = GraphedTrainStep(trainer, sampling_optimizer, render_kwargs_train, n_rays)
-        loss, depth_net_loss, psnr = step(batch_rays, target_s)      # tensors (no host sync)
+        loss, depth_net_loss, psnr = step(batch_rays, target_s)      # fresh 0-dim tensors (no host sync)
 
+    Adam's step counter and hyper-parameters live in device memory and the graph re-reads ``lr`` / ``grad_scale`` from a pinned
+    block on every replay, so learning-rate schedules keep working.  NCCL collectives are capturable; set
+    ``capture_step=False`` (or ``B200NERF_GRAPH_COLLECTIVE=0``) to keep the all-reduce and Adam eager after the replay.
     Batch shape is fixed at construction; ``perturb`` must be 0 (random draws would be frozen into the graph)."""
 
-    def __init__(self, trainer, optimizer, render_kwargs_train, n_rays: int, warmup: int = 3):
+    def __init__(self, trainer, optimizer, render_kwargs_train, n_rays: int, warmup: int = 3, capture_step=None):
+        import os
+
         dev = next(p for g in optimizer.param_groups for p in g["params"]).device
         self.trainer, self.opt, self.kw = trainer, optimizer, render_kwargs_train
         self.rays = torch.zeros(2, n_rays, 3, device=dev)
@@ -245,19 +295,31 @@ class GraphedTrainStep:
         self.graph = None
         self.warmup = warmup
         self.out = None
+        if capture_step is None:
+            capture_step = os.environ.get("B200NERF_GRAPH_COLLECTIVE", "1") != "0"
+        self.capture_step = bool(capture_step) and isinstance(optimizer, Adam)
+        self.params = [p for g in optimizer.param_groups for p in g["params"]]
 
     def _capture(self):
+        import torch.distributed as dist
+
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for i in range(self.warmup):   # lazy initialisation (function attributes, cached grids) must not be captured
                 self.trainer.render_and_backward(self.opt, self.kw, (self.rays[0], self.rays[1]), i, self.target)
+            if self.capture_step:
+                self.opt.init_state()      # moment buffers and a possibly checkpoint-loaded step count, outside the capture
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    dist.all_reduce(torch.zeros(1, device=self.rays.device))   # the communicator must exist before capture
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             loss, dn_loss, psnr, _ = self.trainer.render_and_backward(self.opt, self.kw, (self.rays[0], self.rays[1]), 100, self.target)
-            self.out = (loss.detach(), dn_loss.detach(), psnr.detach())
+            if self.capture_step:
+                self.trainer.reduce_and_step(self.opt)
+            self.out = torch.stack([loss.detach(), dn_loss.detach(), psnr.detach()])
 
     def __call__(self, batch_rays, target_s):
         if self.graph is None:
@@ -265,6 +327,12 @@ class GraphedTrainStep:
         self.rays[0].copy_(batch_rays[0])
         self.rays[1].copy_(batch_rays[1])
         self.target.copy_(target_s)
+        if self.capture_step:
+            self.opt.set_hyper()                  # lr may have been changed on the param group since the last replay
         self.graph.replay()                       # gradients land in the tensors the capture allocated (static addresses)
-        self.trainer.reduce_and_step(self.opt)    # flat NCCL all-reduce + fused Adam, eager
-        return self.out
+        if self.capture_step:
+            packing.mark_updated(self.params)     # the replayed Adam wrote the weights behind torch's back
+        else:
+            self.trainer.reduce_and_step(self.opt)    # flat NCCL all-reduce + fused Adam, eager
+        out = self.out.clone()                    # the graph's output buffer is overwritten by the next replay
+        return out[0], out[1], out[2]

@@ -343,6 +343,63 @@ def test_plugin_hook_builds_trainer(tmp_path):
     assert tr.lindisp is True and tr.near == 2.0 and tr.far == 6.0 and tr.chunk == 32768 and tr.netchunk == 65536
 
 
+def test_plugin_subclasses_reference_trainer_and_routes_its_entry_points(tmp_path):
+    """nerf_sampling_b200.plugin.B200DepthNetTrainer derives from the REFERENCE's DepthNetTrainer (when baseline/_ref is
+    installed), keeps its train()/log()/load_data(), overrides the hot-path operators, and while train() runs the reference's
+    nerf_utils render entry points are this repo's (restored afterwards)."""
+    import importlib
+
+    from oracle import refpkg
+
+    if not refpkg.import_reference():
+        pytest.skip("baseline/_ref (the installed reference) is not present")
+    import nerf_sampling.nerf_pytorch.nerf_utils as ref_nu
+    from nerf_sampling.nerf_pytorch.trainers.Trainer import Trainer as RefTrainer
+    from nerf_sampling.nerf_pytorch.utils import load_obj_from_config
+    from nerf_sampling.trainers import DepthNetTrainer as RefDepthNetTrainer
+
+    import nerf_sampling_b200.plugin as plugin
+    from nerf_sampling_b200.nerf_pytorch import nerf_utils as nu
+
+    if not plugin.HAVE_REFERENCE:
+        plugin = importlib.reload(plugin)
+    os.makedirs(tmp_path / "e", exist_ok=True)
+    tr = load_obj_from_config({"module": "nerf_sampling_b200.plugin.B200DepthNetTrainer",
+                               "kwargs": dict(dataset_type="blender", basedir=str(tmp_path), expname="e", no_batching=True,
+                                              datadir="x", half_res=True, white_bkgd=True, n_layers=10, layer_width=256,
+                                              N_importance=128, input_dims_embed=3, device="cuda")})
+    cls = type(tr)
+    assert issubclass(cls, RefDepthNetTrainer) and cls.log is RefTrainer.log and cls.update_learning_rate is RefTrainer.update_learning_rate
+    for name in ("create_nerf_model", "render", "core_optimization_loop", "sample_random_ray_batch", "run_network", "raw2outputs",
+                 "sample_coarse_points", "sample_fine_points", "_sample_points"):
+        assert getattr(cls, name) is not getattr(RefDepthNetTrainer, name), name
+    original = ref_nu.render_path
+    seen = {}
+
+    def fake_load_data():
+        seen["render_path"] = ref_nu.render_path
+        seen["render"] = ref_nu.render
+        raise KeyboardInterrupt   # leave train() before anything needs a GPU
+
+    tr.load_data = fake_load_data
+    with pytest.raises(KeyboardInterrupt):
+        tr.train(N_iters=2)
+    assert seen["render_path"] is nu.render_path and seen["render"] is nu.render
+    assert ref_nu.render_path is original
+
+
+def test_mirror_trainer_has_the_drivers():
+    """The stand-alone mirror offers train / render / log with the reference's signatures (Trainer.py:181, 263, 712)."""
+    import inspect
+
+    from nerf_sampling_b200.trainers import DepthNetTrainer
+
+    assert list(inspect.signature(DepthNetTrainer.train).parameters) == ["self", "N_iters"]
+    assert list(inspect.signature(DepthNetTrainer.render).parameters) == ["self", "render_test", "save_scene_data", "images", "i_test",
+                                                                        "render_poses", "hwf", "render_kwargs_test"]
+    assert "sampling_optimizer" in inspect.signature(DepthNetTrainer.log).parameters
+
+
 # --------------------------------------------------------------------------------------------- reference KATs
 def nan_equal(a, b):
     return torch.allclose(a[~torch.isnan(a)], b[~torch.isnan(b)], equal_nan=True) and torch.equal(torch.isnan(a), torch.isnan(b))
