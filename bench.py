@@ -177,6 +177,8 @@ class CpuRenderer:
     them), else the oracle port (pinned bit-exactly to the reference by tests/golden/make_golden.py)."""
 
     def __init__(self):
+        import contextlib
+
         from oracle import refpkg
 
         torch.set_num_threads(os.cpu_count() or 1)
@@ -185,8 +187,9 @@ class CpuRenderer:
         if refpkg.import_reference():
             try:
                 self.tmp = tempfile.mkdtemp(prefix="b200ref_")
-                self.tr, _, self.rk_test = refpkg.build_reference_trainer(self.tmp, device="cpu", n_depth_samples=S, distance=DISTANCE,
-                                                                          sampling_mode="uniform")
+                with contextlib.redirect_stdout(sys.stderr):   # the reference prints its configuration; stdout carries ONE JSON line
+                    self.tr, _, self.rk_test = refpkg.build_reference_trainer(self.tmp, device="cpu", n_depth_samples=S,
+                                                                              distance=DISTANCE, sampling_mode="uniform")
                 from nerf_sampling.nerf_pytorch import nerf_utils, run_nerf_helpers
 
                 self.ref_nu, self.ref_h = nerf_utils, run_nerf_helpers
@@ -209,7 +212,9 @@ class CpuRenderer:
         return packed[base : base + n]
 
     def render(self, rays):
-        with torch.no_grad():
+        import contextlib
+
+        with torch.no_grad(), contextlib.redirect_stdout(sys.stderr):
             if self.kind == "reference":
                 return self.ref_nu.render_test(H, W, self.K, chunk=REF_CHUNK, rays=rays, **self.rk_test)[0]
             c, f, d = self.models
@@ -371,6 +376,7 @@ def bench_config5(models, dev, world, rank, steps=20):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         out[mode] = {"ms_per_step": float(ms), "rays_per_sec": n_total * 1e3 / float(ms), "host_enqueue_ms": host_ms,
                      "loss": float(res[0]), "depth_net_loss": float(res[1])}
+        del res, run, opt
         with torch.no_grad():   # both modes start from the same weights
             for p, s0 in zip(models[2].parameters(), saved):
                 p.copy_(s0)

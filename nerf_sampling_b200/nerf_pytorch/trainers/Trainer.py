@@ -208,7 +208,9 @@ class Trainer:
         # parameter gradients are the sum of the two.  One backward over both roots gives the same sum with ONE pass through
         # DepthNet's backward (autograd adds the two d/dz contributions before it reaches DepthNetTrainFn).
         torch.autograd.backward([depth_net_loss, loss])
-        return loss, depth_net_loss, psnr, None
+        # detached: a caller that keeps the losses (the reference's loop keeps `psnr`) must not keep the autograd graph -- and
+        # with it the parameters' AccumulateGrad nodes, which are bound to the stream they were created on -- alive
+        return loss.detach(), depth_net_loss.detach(), psnr.detach(), None
 
     def reduce_and_step(self, sampling_optimizer):
         """Second half: data-parallel gradient all-reduce (one flat buffer) and the optimizer step (Trainer.py:542)."""

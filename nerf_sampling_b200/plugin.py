@@ -77,11 +77,8 @@ class B200DepthNetTrainer(_Base):
     core_optimization_loop = _MirrorTrainer.core_optimization_loop
     render_and_backward = _MirrorTrainer.render_and_backward
     reduce_and_step = _MirrorTrainer.reduce_and_step
-
-    def __init__(self, *args, **kwargs):
-        super().__init__(*args, **kwargs)
-        if str(self.device) == "cpu":
-            raise RuntimeError("B200DepthNetTrainer needs device='cuda': the B200 path has no CPU fallback")
+    _device_image = _MirrorTrainer._device_image
+    _host_poses = _MirrorTrainer._host_poses
 
     render = _MirrorTrainer.render
 
