@@ -248,6 +248,13 @@ int b200nerf_adam_step(float* param, const float* grad, float* exp_avg, float* e
 int b200nerf_adam_step_multi(const void* d_table, int n_tensors, float lr, float beta1, float beta2, float eps, int step,
                              float grad_scale, void* stream);
 
+/* Losses of Trainer.core_optimization_loop on the DepthNet path (nerf_pytorch/trainers/Trainer.py:525-538) and the gradient they send
+ * into the predicted depth, in one pass: raw [n,1,4] and draw_dz [n,4] from b200nerf_nerf_point_jvp, z_dn / max_z [n], target [n,3].
+ * out_losses = {img_loss = mean((sigmoid(raw rgb) - target)^2), depth_net_loss = mean((z_dn - max_z)^2), psnr = -10 log10(img_loss)};
+ * out_dz [n] = d(depth_net_loss + img_loss)/d z_dn (what the reference's two backward() calls accumulate);  ws2: 2 floats of scratch. */
+int b200nerf_train_loss(const float* raw, const float* draw_dz, const float* z_dn, const float* max_z, const float* target,
+                        int n_rays, float* ws2, float* out_losses, float* out_dz, void* stream);
+
 /* CUDA-graph friendly form: the step counter (*d_step, incremented by the call) and {lr, beta1, beta2, eps, grad_scale}
  * (d_hyper, 5 floats) live in device memory, so a captured launch stays valid while they change. */
 int b200nerf_adam_step_multi_dev(const void* d_table, int n_tensors, const float* d_hyper, int* d_step, void* stream);

@@ -344,11 +344,384 @@ __global__ void depth_head_bwd_kernel(const float* __restrict__ dz, const float*
   if (i >= n) return;
   dt[i] = dz[i] * (far_ - near_) * s[i] * (1.0f - s[i]);
 }
+// Fused head (tensor-core path): t = a_last . w + b, s = sigmoid(t), z = near (1 - s) + far s; one warp per ray
+__global__ void depth_head_fused_kernel(const float* __restrict__ a, int n, int cl, const float* __restrict__ w, const float* __restrict__ b,
+                                        float near_, float far_, float* __restrict__ s_out, float* __restrict__ z) {
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (ray >= n) return;
+  const float* row = a + static_cast<size_t>(ray) * cl;
+  float acc = 0.f;
+  for (int c = lane; c < cl; c += 32) acc = fmaf(row[c], __ldg(w + c), acc);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    const float s = 1.0f / (1.0f + expf(-(acc + __ldg(b))));
+    s_out[ray] = s;
+    z[ray] = __fadd_rn(__fmul_rn(near_, __fadd_rn(1.0f, -s)), __fmul_rn(far_, s));
+  }
+}
+// Its backward in one pass over a_last: dt = dz (far - near) s (1 - s);  g[r, c] = dt w[c] LeakyReLU'(a_last[r, c]) (the gradient of
+// the last cat layer's pre-activation);  dw[c] += sum_r dt a_last[r, c];  db += sum_r dt  (dw / db pre-zeroed)
+constexpr int HEAD_ROWS = 32;
+__global__ void __launch_bounds__(256) depth_head_bwd_fused_kernel(const float* __restrict__ dz, const float* __restrict__ s,
+                                                                   const float* __restrict__ a, const float* __restrict__ w, int n, int cl,
+                                                                   float near_, float far_, float slope, float* __restrict__ g,
+                                                                   float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float dts[HEAD_ROWS];
+  const int r0 = blockIdx.x * HEAD_ROWS;
+  if (threadIdx.x < HEAD_ROWS) {
+    const int r = r0 + threadIdx.x;
+    dts[threadIdx.x] = r < n ? dz[r] * (far_ - near_) * s[r] * (1.0f - s[r]) : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cl; c += blockDim.x) {
+    const float wc = __ldg(w + c);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < HEAD_ROWS; ++q) {
+      const int r = r0 + q;
+      if (r >= n) break;
+      const float av = a[static_cast<size_t>(r) * cl + c];
+      g[static_cast<size_t>(r) * cl + c] = dts[q] * wc * (av > 0.f ? 1.0f : slope);
+      acc = fmaf(dts[q], av, acc);
+    }
+    atomicAdd(dw + c, acc);
+  }
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int q = 0; q < HEAD_ROWS; ++q) t += dts[q];
+    atomicAdd(db, t);
+  }
+}
+
 // dpre = dpost * (post > 0 ? 1 : slope), in place
 __global__ void leaky_bwd_kernel(float* __restrict__ d, const float* __restrict__ post, size_t total, float slope) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   if (!(post[i] > 0.f)) d[i] *= slope;
+}
+
+// ------------------------------------------------------------------------------------------- DepthNet branches, collapsed
+// The origin / direction / intersection branches have NO activation (depth_net.py:140,148,156 construct a LeakyReLU module
+// and drop it): x_i = W_i [x_{i-1}; e] + b_i = U_i x_{i-1} + V_i e + b_i is affine in the ray's encoding e, x_i = A_i e + c_i with
+//   A_0 = U_0 + V_0, c_0 = b_0,   A_i = U_i A_{i-1} + V_i,   c_i = U_i c_{i-1} + b_i                    (weights only, no ray dimension).
+// Forward per ray: ONE product x_last = e A_last^T + c_last instead of L.  Backward, with D = dLoss/dx_last [n, h] per ray:
+//   dLoss/dx_i = D Q_i, Q_i = U_{L-1} ... U_{i+1};   G = D^T e [h, d], g = D^T 1 [h]      (ONE reduction over the rays)
+//   R_i = Q_i^T [G | g] (R_{L-1} = [G | g], R_{i-1} = U_i^T R_i):   dV_i = R_i[:, :d],  db_i = R_i[:, d],
+//   dU_i = dx_i^T x_{i-1} = R_i[:, :d] A_{i-1}^T + R_i[:, d] c_{i-1}^T = R_i [A_{i-1} | c_{i-1}]^T        (dU_0 = R_0[:, :d]).
+// 30 per-ray layers of forward and 60 per-ray products of backward (72 % of DepthNet's training FLOPs) become two per-ray
+// products, two weight-only recurrences and 27 small [h, d+1] x [d+1, h] products.  The recurrences run in plain fp32 FMA
+// (they are tiny and 10 deep: fp32-grade gradients need fp32-grade chain products); their COLUMNS are independent, so a
+// CTA owns CH_CW columns of [A_i | c_i] (or R_i) through the whole chain and never talks to another CTA.
+constexpr int CH_CW = 4;        // columns per CTA
+constexpr int CH_MAXL = 12;     // layers per branch
+constexpr int CH_LD = 128;      // row stride of the [h, d+1] chain matrices (d + 1 <= 127)
+constexpr int CH_MAXH = 256;    // widths up to 256: one thread per row
+struct ChainBranch {
+  const float* W[CH_MAXL];
+  const float* b[CH_MAXL];
+  float* gW[CH_MAXL];
+  float* gb[CH_MAXL];
+  int h[CH_MAXL];
+  int d;              // encoding width (63 / 63 / 126)
+  int cta_begin;      // first CTA of this branch in the launch
+  float* Aaug;        // [L][CH_MAXH][CH_LD]: [A_i | c_i]
+  float* Raug;        // [L][CH_MAXH][CH_LD]: R_i
+  float* c_last;      // [h_last]
+  const float* G;     // [h_last][CH_LD]: D^T e (columns 0..d-1)
+  const float* g;     // [h_last]: D^T 1
+};
+struct ChainParams {
+  ChainBranch br[3];
+  int L;
+};
+
+__device__ __forceinline__ const ChainBranch& chain_branch(const ChainParams& p, int cta, int* local) {
+  const int b = cta >= p.br[2].cta_begin ? 2 : (cta >= p.br[1].cta_begin ? 1 : 0);
+  *local = cta - p.br[b].cta_begin;
+  return p.br[b];
+}
+
+// Both recurrences read the whole W_i = [U_i | V_i] (h x (pw + d) fp32, ~330-390 KB) per layer and CTA.  The rows are 319 / 382
+// floats apart, so no vector load is aligned -- but a block of 32 rows is one contiguous, 16-byte aligned span, i.e. one 1-D bulk
+// copy (cp.async.bulk, SASS UBLKCP).  A CTA streams the blocks of ALL its layers through a 4-stage ring (the weights do not
+// depend on the recurrence, so the ring never drains at a layer boundary) and computes from shared memory; what bounds a layer is
+// the bulk-copy bandwidth of one SM, not 4-byte load latency (the first version: 194 / 890 us for the two kernels).
+constexpr int CH_THREADS = 1024;
+constexpr int CH_STAGES = 4;
+constexpr int CH_ROWS = 32;                        // rows of W_i per ring stage
+constexpr int CH_STAGE_BYTES = 49152;              // >= 32 x (256 + 126) x 4
+constexpr int CH_PART_BYTES = 4 * CH_MAXH * CH_CW * 4;   // bwd: partial sums of the four row groups
+constexpr int CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + CH_PART_BYTES + 128;
+
+// the producer side of the ring, run by thread 0: blocks are numbered q = 0, 1, ... over the layers in visiting order
+struct ChainFeed {
+  int layer, block, issued;
+};
+template <bool FWD>
+__device__ __forceinline__ void chain_feed(const ChainBranch& B, int L, ChainFeed& f, uint8_t* ring, uint64_t* full, uint64_t* empty) {
+  if (FWD ? f.layer >= L : f.layer < 1) return;
+  const int h = B.h[f.layer], ldw = B.h[f.layer - 1] + B.d;
+  const int s = f.issued % CH_STAGES, use = f.issued / CH_STAGES;
+  if (use > 0) b200::mbar_wait(&empty[s], static_cast<uint32_t>(use - 1) & 1u);   // every warp has read the stage's previous block
+  const int r0 = f.block * CH_ROWS;
+  const int rows = h - r0 < CH_ROWS ? h - r0 : CH_ROWS;
+  const uint32_t bytes = static_cast<uint32_t>(rows) * ldw * 4u;
+  b200::mbar_arrive_expect_tx(&full[s], bytes);
+  // four 8-row copies per block: the latency of one bulk copy (~2 us for 40 KB) bounds the stream unless enough are in flight
+  for (int sub = 0; sub < rows; sub += CH_ROWS / 4) {
+    const int nr = rows - sub < CH_ROWS / 4 ? rows - sub : CH_ROWS / 4;
+    b200::tma_load_1d(ring + static_cast<size_t>(s) * CH_STAGE_BYTES + static_cast<size_t>(sub) * ldw * 4,
+                      B.W[f.layer] + static_cast<size_t>(r0 + sub) * ldw, static_cast<uint32_t>(nr) * ldw * 4u, &full[s]);
+  }
+  ++f.issued;
+  if (++f.block * CH_ROWS >= h) {
+    f.block = 0;
+    f.layer += FWD ? 1 : -1;
+  }
+}
+
+// [A_i | c_i][m, c] = sum_k U_i[m, k] [A_{i-1} | c_{i-1}][k, c] + [V_i | b_i][m, c].  Warp w owns row w of every 32-row block; its
+// lanes stride over k, the four column sums are reduced with a value-splitting butterfly (6 shuffles).
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ uint8_t ch_smem_[];
+  __shared__ __align__(16) float buf[2][CH_MAXH][CH_CW];
+  __shared__ uint64_t full[CH_STAGES], empty[CH_STAGES];
+  uint8_t* ring = ch_smem_ + ((128u - (b200::smem_u32(ch_smem_) & 127u)) & 127u);
+  int local;
+  const ChainBranch& B = chain_branch(p, blockIdx.x, &local);
+  const int d = B.d, c0 = local * CH_CW, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < CH_STAGES; ++s) {
+      b200::mbar_init(&full[s], 1);
+      b200::mbar_init(&empty[s], CH_THREADS / 32);
+    }
+    b200::fence_mbar_init();
+  }
+  if (tid < CH_MAXH) {
+    const int m = tid, h = B.h[0], ldw = 2 * d;
+    const float* W0 = B.W[0];
+#pragma unroll
+    for (int j = 0; j < CH_CW; ++j) {
+      const int c = c0 + j;
+      float v = 0.f;
+      if (m < h && c <= d) v = c < d ? W0[static_cast<size_t>(m) * ldw + c] + W0[static_cast<size_t>(m) * ldw + d + c] : B.b[0][m];
+      buf[0][m][j] = v;
+      if (m < h && c <= d) B.Aaug[static_cast<size_t>(m) * CH_LD + c] = v;
+    }
+  }
+  __syncthreads();
+  ChainFeed feed{1, 0, 0};
+  if (tid == 0)
+    for (int k = 0; k < CH_STAGES - 1; ++k) chain_feed<true>(B, p.L, feed, ring, full, empty);
+  static_assert(CH_CW == 4, "the forward recurrence keeps a 4-column slice of [A | c] in registers");
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+  const int my_col = c0 + (b4 ? 2 : 0) + (b3 ? 1 : 0);   // the column whose sum this lane ends up with
+  int q = 0;
+  for (int i = 1; i < p.L; ++i) {
+    const int h = B.h[i], pw = B.h[i - 1], ldw = pw + d;
+    float(*dst)[CH_CW] = buf[i & 1];
+    const float* bias = B.b[i];
+    // this lane's rows k = lane + 32 j of [A_{i-1} | c_{i-1}] stay in registers for the whole layer: every warp multiplies them
+    // with one row of U_i per block, and re-reading them from shared memory per row made the kernel shared-memory bound
+    float4 a[CH_MAXH / 32];
+#pragma unroll
+    for (int j = 0; j < CH_MAXH / 32; ++j) {
+      const int k = lane + 32 * j;
+      a[j] = k < pw ? *reinterpret_cast<const float4*>(buf[(i - 1) & 1][k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int r0 = 0; r0 < h; r0 += CH_ROWS, ++q) {
+      if (tid == 0) chain_feed<true>(B, p.L, feed, ring, full, empty);
+      const int s = q % CH_STAGES;
+      b200::mbar_wait(&full[s], static_cast<uint32_t>(q / CH_STAGES) & 1u);
+      const float* Us = reinterpret_cast<const float*>(ring + static_cast<size_t>(s) * CH_STAGE_BYTES) + warp * ldw;
+      const int m = r0 + warp;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (m < h) {
+#pragma unroll
+        for (int j = 0; j < CH_MAXH / 32; ++j) {
+          const int k = lane + 32 * j;
+          const float u = k < pw ? Us[k] : 0.f;
+          a0 = fmaf(u, a[j].x, a0);
+          a1 = fmaf(u, a[j].y, a1);
+          a2 = fmaf(u, a[j].z, a2);
+          a3 = fmaf(u, a[j].w, a3);
+        }
+      }
+      // value-splitting butterfly: every step keeps half of the sums and ships the other half (2 + 1 + 3 shuffles)
+      float x0 = b4 ? a2 : a0, x1 = b4 ? a3 : a1;
+      x0 += __shfl_xor_sync(0xffffffffu, b4 ? a0 : a2, 16);
+      x1 += __shfl_xor_sync(0xffffffffu, b4 ? a1 : a3, 16);
+      float y = b3 ? x1 : x0;
+      y += __shfl_xor_sync(0xffffffffu, b3 ? x0 : x1, 8);
+      y += __shfl_xor_sync(0xffffffffu, y, 4);
+      y += __shfl_xor_sync(0xffffffffu, y, 2);
+      y += __shfl_xor_sync(0xffffffffu, y, 1);
+      if ((lane & 7) == 0 && m < h) {
+        float v = 0.f;
+        if (my_col <= d) {
+          v = y + (my_col < d ? Us[pw + my_col] : bias[m]);
+          B.Aaug[(static_cast<size_t>(i) * CH_MAXH + m) * CH_LD + my_col] = v;
+        }
+        dst[m][my_col - c0] = v;
+      }
+      __syncwarp();
+      if (lane == 0) b200::mbar_arrive(&empty[s]);
+    }
+    __syncthreads();
+  }
+  const int hl = B.h[p.L - 1];
+  if (d >= c0 && d < c0 + CH_CW && tid < hl) B.c_last[tid] = buf[(p.L - 1) & 1][tid][d - c0];
+}
+
+// R_{i-1}[k, c] = sum_m U_i[m, k] R_i[m, c]: thread (g, k) sums rows 8 g .. 8 g + 7 of every 32-row block (consecutive threads read
+// consecutive shared-memory words), the four partial sums per element are added through shared memory at the end of the layer.
+__global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ uint8_t ch_smem_[];
+  __shared__ __align__(16) float buf[2][CH_MAXH][CH_CW];
+  __shared__ uint64_t full[CH_STAGES], empty[CH_STAGES];
+  uint8_t* ring = ch_smem_ + ((128u - (b200::smem_u32(ch_smem_) & 127u)) & 127u);
+  float(*part)[CH_MAXH][CH_CW] = reinterpret_cast<float(*)[CH_MAXH][CH_CW]>(ring + CH_STAGES * CH_STAGE_BYTES);
+  int local;
+  const ChainBranch& B = chain_branch(p, blockIdx.x, &local);
+  const int d = B.d, c0 = local * CH_CW, tid = threadIdx.x, lane = tid & 31, k = tid & (CH_MAXH - 1), g = tid >> 8;
+  if (tid == 0) {
+    for (int s = 0; s < CH_STAGES; ++s) {
+      b200::mbar_init(&full[s], 1);
+      b200::mbar_init(&empty[s], CH_THREADS / 32);
+    }
+    b200::fence_mbar_init();
+  }
+  if (tid < CH_MAXH) {
+    const int h = B.h[p.L - 1];
+#pragma unroll
+    for (int j = 0; j < CH_CW; ++j) {
+      const int c = c0 + j;
+      float v = 0.f;
+      if (tid < h && c <= d) v = c < d ? B.G[static_cast<size_t>(tid) * CH_LD + c] : B.g[tid];
+      buf[(p.L - 1) & 1][tid][j] = v;
+    }
+  }
+  __syncthreads();
+  ChainFeed feed{p.L - 1, 0, 0};
+  if (tid == 0)
+    for (int n = 0; n < CH_STAGES - 1; ++n) chain_feed<false>(B, p.L, feed, ring, full, empty);
+  int q = 0;
+  for (int i = p.L - 1; i >= 0; --i) {
+    const int h = B.h[i], pw = i ? B.h[i - 1] : d, ldw = pw + d;
+    const float(*src)[CH_CW] = buf[i & 1];
+    if (tid < h) {   // gradients of layer i that are columns of R_i
+      float* gw = B.gW[i] + static_cast<size_t>(tid) * ldw;
+#pragma unroll
+      for (int j = 0; j < CH_CW; ++j) {
+        const int c = c0 + j;
+        const float r = src[tid][j];
+        if (c < d) {
+          gw[pw + c] = r;
+          if (i == 0) gw[c] = r;
+        } else if (c == d) {
+          B.gb[i][tid] = r;
+        }
+        if (c <= d) B.Raug[(static_cast<size_t>(i) * CH_MAXH + tid) * CH_LD + c] = r;
+      }
+    }
+    if (i == 0) break;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int r0 = 0; r0 < h; r0 += CH_ROWS, ++q) {
+      if (tid == 0) chain_feed<false>(B, p.L, feed, ring, full, empty);
+      const int s = q % CH_STAGES;
+      b200::mbar_wait(&full[s], static_cast<uint32_t>(q / CH_STAGES) & 1u);
+      const float* Us = reinterpret_cast<const float*>(ring + static_cast<size_t>(s) * CH_STAGE_BYTES) + k;
+      if (k < pw) {
+#pragma unroll
+        for (int r = 0; r < CH_ROWS / 4; ++r) {
+          const int rr = g * (CH_ROWS / 4) + r, m = r0 + rr;
+          if (m < h) {
+            const float u = Us[rr * ldw];
+            const float4 a = *reinterpret_cast<const float4*>(src[m]);
+            a0 = fmaf(u, a.x, a0);
+            a1 = fmaf(u, a.y, a1);
+            a2 = fmaf(u, a.z, a2);
+            a3 = fmaf(u, a.w, a3);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) b200::mbar_arrive(&empty[s]);
+    }
+    *reinterpret_cast<float4*>(part[g][k]) = make_float4(a0, a1, a2, a3);
+    __syncthreads();
+    {
+      const int kk = tid >> 2, c = tid & 3;   // one (row, column) element per thread
+      buf[(i - 1) & 1][kk][c] = kk < pw ? (part[0][kk][c] + part[1][kk][c]) + (part[2][kk][c] + part[3][kk][c]) : 0.f;
+    }
+    __syncthreads();
+  }
+}
+
+// dU_i[m, k] = sum_c R_i[m, c] [A_{i-1} | c_{i-1}][k, c]: up to 3 x (CH_MAXL - 1) independent small products, one launch
+struct DuProb {
+  const float* R;   // [h, CH_LD]
+  const float* A;   // [pw, CH_LD]
+  float* C;         // grads of W_i, row stride ldw
+  int h, pw, K, ldw;
+};
+struct DuBatch {
+  DuProb p[3 * (CH_MAXL - 1)];
+};
+__global__ void __launch_bounds__(256) chain_du_kernel(const __grid_constant__ DuBatch batch) {
+  const DuProb q = batch.p[blockIdx.z];
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  if (m0 >= q.h || n0 >= q.pw) return;
+  __shared__ float Rs[GK][GM + 4];
+  __shared__ float As[GK][GN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < q.K; k0 += GK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      const int r = idx >> 4, k = idx & 15;   // both operands are k-contiguous
+      Rs[k][r] = (m0 + r < q.h && k0 + k < q.K) ? __ldg(q.R + static_cast<size_t>(m0 + r) * CH_LD + k0 + k) : 0.f;
+      As[k][r] = (n0 + r < q.pw && k0 + k < q.K) ? __ldg(q.A + static_cast<size_t>(n0 + r) * CH_LD + k0 + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&Rs[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&As[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= q.h) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn < q.pw) q.C[static_cast<size_t>(gm) * q.ldw + gn] = acc[i][j];
+    }
+  }
+}
+
+// B200NERF_TRAIN_BRANCHES=literal keeps the per-layer, per-ray form of the branches (A/B measurements, reference point in tests)
+static bool branches_collapsed() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200NERF_TRAIN_BRANCHES");
+    v = (e && strcmp(e, "literal") == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 // ------------------------------------------------------------------------------------------- DepthNet, literal form
@@ -364,6 +737,7 @@ struct DnWs {             // float offsets into the workspace
   std::vector<size_t> a;       // cat layer outputs (post activation)
   size_t g0, g1, g2;           // gradient scratch, [n, maxw] each
   size_t gx[6];                // per-branch ping/pong scratch of the grouped backward
+  size_t Aaug[3], Raug[3], G[3], gv[3], c_last[3];   // collapsed-branch chain matrices (weights only, no ray dimension)
 };
 static DnWs dn_layout(const DnArch& ar, size_t n) {
   DnWs w;
@@ -382,6 +756,13 @@ static DnWs dn_layout(const DnArch& ar, size_t n) {
   w.g1 = take(n * maxw);
   w.g2 = take(n * maxw);
   for (int i = 0; i < 6; ++i) w.gx[i] = take(n * maxw);
+  for (int b = 0; b < 3; ++b) {
+    w.Aaug[b] = take(static_cast<size_t>(ar.nb) * CH_MAXH * CH_LD);
+    w.Raug[b] = take(static_cast<size_t>(ar.nb) * CH_MAXH * CH_LD);
+    w.c_last[b] = take(CH_MAXH);
+  }
+  for (int b = 0; b < 3; ++b) w.G[b] = take(static_cast<size_t>(CH_MAXH) * CH_LD);   // G and gv back to back: one memset
+  for (int b = 0; b < 3; ++b) w.gv[b] = take(CH_MAXH);
   w.total = o;
   return w;
 }
@@ -398,6 +779,57 @@ static int dn_arch(int nb, const int* h, int nc, const int* c, DnArch* ar) {
 static inline int pidx_branch(const DnArch& ar, int b, int i) { return (b * ar.nb + i) * 2; }
 static inline int pidx_cat(const DnArch& ar, int j) { return (3 * ar.nb + j) * 2; }
 static inline int pidx_head(const DnArch& ar) { return (3 * ar.nb + ar.nc) * 2; }
+
+// widths up to 256 and multiples of 4 (every 32-row block of W_i is then a 16-byte multiple), 16-byte aligned weight tensors
+static bool can_collapse(const DnArch& ar, int n, const float* const* params) {
+  if (!tgemm_enabled() || n < 32 || !branches_collapsed() || ar.nb > CH_MAXL) return false;
+  for (int v : ar.h)
+    if (v > CH_MAXH || (v & 3)) return false;
+  for (int b = 0; b < 3; ++b)
+    for (int i = 0; i < ar.nb; ++i)
+      if (reinterpret_cast<uintptr_t>(params[pidx_branch(ar, b, i)]) & 15) return false;
+  return true;
+}
+static int chain_configure() {
+  static bool configured[B200_MAX_DEVICES] = {false};
+  const int dev = b200_device();
+  if (dev < 0) return b200_fail("chain kernels: no usable CUDA device");
+  if (!configured[dev]) {
+    CUDA_TRY(cudaFuncSetAttribute(chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(chain_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
+    configured[dev] = true;
+  }
+  return 0;
+}
+static ChainParams chain_params(const DnArch& ar, const DnWs& w, float* ws, const float* const* params, float* const* grads) {
+  ChainParams cp;
+  memset(&cp, 0, sizeof(cp));
+  const int ed[3] = {63, 63, 126};
+  cp.L = ar.nb;
+  int cta = 0;
+  for (int b = 0; b < 3; ++b) {
+    ChainBranch& B = cp.br[b];
+    for (int i = 0; i < ar.nb; ++i) {
+      B.W[i] = params[pidx_branch(ar, b, i)];
+      B.b[i] = params[pidx_branch(ar, b, i) + 1];
+      if (grads) {
+        B.gW[i] = grads[pidx_branch(ar, b, i)];
+        B.gb[i] = grads[pidx_branch(ar, b, i) + 1];
+      }
+      B.h[i] = ar.h[i];
+    }
+    B.d = ed[b];
+    B.cta_begin = cta;
+    cta += (ed[b] + 1 + CH_CW - 1) / CH_CW;
+    B.Aaug = ws + w.Aaug[b];
+    B.Raug = ws + w.Raug[b];
+    B.c_last = ws + w.c_last[b];
+    B.G = ws + w.G[b];
+    B.g = ws + w.gv[b];
+  }
+  return cp;
+}
+static int chain_ctas(const ChainParams& cp) { return cp.br[2].cta_begin + (cp.br[2].d + 1 + CH_CW - 1) / CH_CW; }
 
 extern "C" size_t b200nerf_depthnet_train_ws_floats(int n_rays, int n_branch, const int* hidden, int n_cat, const int* cat_hidden) {
   DnArch ar;
@@ -421,9 +853,24 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
   LAUNCH_CHECK();
   const int ed[3] = {63, 63, 126}, eo[3] = {0, 63, 126};
   if (tgemm_enabled() && n >= 32) {
-    // tensor-core path: the three branches advance together (one grouped launch per layer index), Linear(cat([x, e])) is two
+    const bool collapse = can_collapse(ar, n, params);
+    if (collapse) {
+      // collapsed branches: [A_i | c_i] recurrences over the weights (one launch), then x_last = e A_last^T + c_last per ray
+      const ChainParams cp = chain_params(ar, w, ws, params, nullptr);
+      if (chain_configure()) return 1;
+      chain_fwd_kernel<<<chain_ctas(cp), CH_THREADS, CH_SMEM_BYTES, st>>>(cp);
+      LAUNCH_CHECK();
+      GemmProb q[3];
+      const int hlast = ar.h[ar.nb - 1];
+      for (int b = 0; b < 3; ++b) {
+        q[b] = prob_fwd(n, hlast, ws + w.xb[b][ar.nb - 1], hlast, ws + w.c_last[b], 0, 0.f);
+        seg_fwd(q[b], E + eo[b], 252, ws + w.Aaug[b] + static_cast<size_t>(ar.nb - 1) * CH_MAXH * CH_LD, CH_LD, 0, ed[b]);
+      }
+      if (tgemm_group(st, q, 3)) return 1;
+    }
+    // literal branches: they advance together (one grouped launch per layer index), Linear(cat([x, e])) is two
     // K segments of one product, cat_layers.0 is four
-    for (int i = 0; i < ar.nb; ++i) {
+    for (int i = 0; i < (collapse ? 0 : ar.nb); ++i) {
       GemmProb q[3];
       for (int b = 0; b < 3; ++b) {
         const float* e = E + eo[b];
@@ -453,9 +900,8 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
       if (tgemm_group(st, &q, 1)) return 1;
     }
     const int cl = ar.c[ar.nc - 1];
-    if (lin_fwd(st, n, 1, cl, ws + w.a[ar.nc - 1], cl, params[pidx_head(ar)], cl, 0, ws + w.t, 1, 0, params[pidx_head(ar) + 1], 0, 0.f))
-      return 1;
-    depth_head_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws + w.t, n, near_, far_, ws + w.s, out_z);
+    depth_head_fused_kernel<<<(n + 7) / 8, 256, 0, st>>>(ws + w.a[ar.nc - 1], n, cl, params[pidx_head(ar)], params[pidx_head(ar) + 1], near_,
+                                                        far_, ws + w.s, out_z);
     LAUNCH_CHECK();
     return 0;
   }
@@ -514,13 +960,16 @@ extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_bra
   const int cl = ar.c[ar.nc - 1], hl = ar.h[ar.nb - 1];
   // head: t = a_last . w + b, s = sigmoid(t), z = near + (far - near) s
   float* dt = ws + w.t;  // t itself is no longer needed
-  depth_head_bwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(dz, ws + w.s, n, near_, far_, dt);
-  LAUNCH_CHECK();
   const int ph = pidx_head(ar);
-  if (lin_wgrad(st, n, 1, cl, dt, 1, ws + w.a[ar.nc - 1], cl, grads[ph], cl, 0)) return 1;
-  if (colsum(st, dt, n, 1, 1, grads[ph + 1])) return 1;
-  if (lin_dgrad(st, n, 1, cl, dt, 1, params[ph], cl, 0, g, cl, 0)) return 1;
-  if (tgemm_enabled() && n >= 32) {
+  const bool tensor_path = tgemm_enabled() && n >= 32;
+  if (!tensor_path) {
+    depth_head_bwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(dz, ws + w.s, n, near_, far_, dt);
+    LAUNCH_CHECK();
+    if (lin_wgrad(st, n, 1, cl, dt, 1, ws + w.a[ar.nc - 1], cl, grads[ph], cl, 0)) return 1;
+    if (colsum(st, dt, n, 1, 1, grads[ph + 1])) return 1;
+    if (lin_dgrad(st, n, 1, cl, dt, 1, params[ph], cl, 0, g, cl, 0)) return 1;
+  }
+  if (tensor_path) {
     // tensor-core path.  Weight gradients are split-K sums and bias gradients column sums added atomically: zero the
     // gradient tensors first -- one memset when the caller laid them out back to back (training.py does), else one each.
     {
@@ -535,7 +984,9 @@ extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_bra
         numel.push_back(static_cast<size_t>(ar.c[j]) * (j == 0 ? 3 * hl + 252 : ar.c[j - 1]));
         numel.push_back(ar.c[j]);
       }
-      const size_t n_body = numel.size();   // the head's two tensors were written above
+      numel.push_back(cl);   // the head: its gradients are atomic sums of the fused head kernel below
+      numel.push_back(1);
+      const size_t n_body = numel.size();
       bool flat = true;
       size_t total = 0;
       for (size_t k = 0; k < n_body; ++k) {
@@ -548,11 +999,10 @@ extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_bra
         for (size_t k = 0; k < n_body; ++k) CUDA_TRY(cudaMemsetAsync(grads[k], 0, numel[k] * sizeof(float), st));
       }
     }
-    {
-      const size_t tot = static_cast<size_t>(n) * cl;
-      leaky_bwd_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(g, ws + w.a[ar.nc - 1], tot, 0.01f);
-      LAUNCH_CHECK();
-    }
+    // head backward + LeakyReLU' of the last cat layer, one pass: g = d(pre-activation of the last cat layer)
+    depth_head_bwd_fused_kernel<<<(n + HEAD_ROWS - 1) / HEAD_ROWS, 256, 0, st>>>(dz, ws + w.s, ws + w.a[ar.nc - 1], params[ph], n, cl, near_,
+                                                                              far_, 0.01f, g, grads[ph], grads[ph + 1]);
+    LAUNCH_CHECK();
     // cat layers: g = d(pre-activation of layer j).  One launch per layer: weight gradient (+ bias gradient from the same
     // loads) and the input gradient, whose epilogue applies LeakyReLU' of the layer below.
     for (int j = ar.nc - 1; j >= 1; --j) {
@@ -581,6 +1031,40 @@ extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_bra
       q[3] = prob_wgrad(n, ar.c[0], 252, g, ar.c[0], E, 252, grads[pc0], ldw0, 3 * hl, nullptr, true);
       for (int b = 0; b < 3; ++b) q[4 + b] = prob_dgrad(n, ar.c[0], hl, g, ar.c[0], params[pc0], ldw0, b * hl, cur[b], hl);
       if (tgemm_group(st, q, 7)) return 1;
+    }
+    if (can_collapse(ar, n, params)) {
+      // cur[b] = D_b = dLoss/dx_{b,last}.  One reduction over the rays per branch (G = D^T e, g = D^T 1), the R recurrence over
+      // the weights (writes dV_i, db_i, dU_0), then the 3 (L-1) small dU_i products in one launch.
+      CUDA_TRY(cudaMemsetAsync(ws + w.G[0], 0, (w.gv[2] + CH_MAXH - w.G[0]) * sizeof(float), st));
+      GemmProb q[3];
+      for (int b = 0; b < 3; ++b)
+        q[b] = prob_wgrad(n, hl, ed[b], cur[b], hl, E + eo[b], 252, ws + w.G[b], CH_LD, 0, ws + w.gv[b], true);
+      if (tgemm_group(st, q, 3)) return 1;
+      const ChainParams cp = chain_params(ar, w, ws, params, grads);
+      if (chain_configure()) return 1;
+      chain_bwd_kernel<<<chain_ctas(cp), CH_THREADS, CH_SMEM_BYTES, st>>>(cp);
+      LAUNCH_CHECK();
+      if (ar.nb > 1) {
+        DuBatch batch;
+        memset(&batch, 0, sizeof(batch));
+        int np = 0, maxh = 0, maxpw = 0;
+        for (int b = 0; b < 3; ++b)
+          for (int i = 1; i < ar.nb; ++i) {
+            DuProb& d = batch.p[np++];
+            d.R = ws + w.Raug[b] + static_cast<size_t>(i) * CH_MAXH * CH_LD;
+            d.A = ws + w.Aaug[b] + static_cast<size_t>(i - 1) * CH_MAXH * CH_LD;
+            d.C = grads[pidx_branch(ar, b, i)];
+            d.h = ar.h[i];
+            d.pw = ar.h[i - 1];
+            d.K = ed[b] + 1;
+            d.ldw = ar.h[i - 1] + ed[b];
+            maxh = d.h > maxh ? d.h : maxh;
+            maxpw = d.pw > maxpw ? d.pw : maxpw;
+          }
+        chain_du_kernel<<<dim3((maxpw + GN - 1) / GN, (maxh + GM - 1) / GM, np), 256, 0, st>>>(batch);
+        LAUNCH_CHECK();
+      }
+      return 0;
     }
     for (int i = ar.nb - 1; i >= 0; --i) {
       GemmProb q[9];
@@ -714,6 +1198,42 @@ __global__ void nerf_point_out_kernel(const float* __restrict__ rgb2, const floa
   draw[i * 4 + 3] = al2[n + i];
 }
 
+// raw = [rgb_linear(hv) + b (3), alpha_linear(h7) + b], draw = the same heads applied to the tangents (no bias)
+__global__ void nerf_point_heads_kernel(const float* __restrict__ h7, const float* __restrict__ t7, const float* __restrict__ hv,
+                                        const float* __restrict__ hvt, const float* __restrict__ wa, const float* __restrict__ ba,
+                                        const float* __restrict__ wr, const float* __restrict__ br, int n, float* __restrict__ raw,
+                                        float* __restrict__ draw) {
+  const int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (ray >= n) return;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // rgb (3), alpha, d rgb (3), d alpha
+  const float* a = h7 + static_cast<size_t>(ray) * 256;
+  const float* at = t7 + static_cast<size_t>(ray) * 256;
+  for (int c = lane; c < 256; c += 32) {
+    const float w = __ldg(wa + c);
+    v[3] = fmaf(a[c], w, v[3]);
+    v[7] = fmaf(at[c], w, v[7]);
+  }
+  const float* b = hv + static_cast<size_t>(ray) * 128;
+  const float* bt = hvt + static_cast<size_t>(ray) * 128;
+  for (int c = lane; c < 128; c += 32) {
+    const float x = b[c], xt = bt[c];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float w = __ldg(wr + ch * 128 + c);
+      v[ch] = fmaf(x, w, v[ch]);
+      v[4 + ch] = fmaf(xt, w, v[4 + ch]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+  if (lane == 0) {
+    *reinterpret_cast<float4*>(raw + static_cast<size_t>(ray) * 4) = make_float4(v[0] + __ldg(br), v[1] + __ldg(br + 1), v[2] + __ldg(br + 2), v[3] + __ldg(ba));
+    *reinterpret_cast<float4*>(draw + static_cast<size_t>(ray) * 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 extern "C" size_t b200nerf_nerf_point_ws_floats(int n_rays) {
   const size_t n = static_cast<size_t>(n_rays);
   return 2 * n * 64 + n * 32 + 3 * (2 * n * 256) + 2 * n * 4 + 2 * n + 256;
@@ -741,6 +1261,85 @@ extern "C" int b200nerf_nerf_point_jvp(const float* const* t, const float* rays_
     LAUNCH_CHECK();
     return 0;
   };
+  if (tgemm_enabled() && n >= 32) {
+    // Tensor-core path, every epilogue fused: the primal row block runs Linear + bias + ReLU as one problem, the tangent row block
+    // W t_{k-1} masked by the primal's post-activation (the `dact` epilogue with slope 0 IS relu_jvp's mask).  The tangent of layer
+    // k-1 needs the primal of layer k-1, so launch k carries {primal layer k, tangent layer k-1}: 11 grouped launches instead of
+    // 13 products + 11 activation launches.
+    const size_t blk = static_cast<size_t>(n) * 256;
+    float* hp[2] = {h0, h0 + blk};          // primal ping-pong
+    float* ht[2] = {h1, h1 + blk};          // tangent ping-pong
+    float* feat = h2;                       // feature_linear(h7) primal, then its tangent next to it
+    float* feat_t = h2 + blk;
+    const float* enc_t = enc + static_cast<size_t>(n) * 63;
+    auto primal = [&](int layer, const float* x, float* y) {
+      GemmProb q = prob_fwd(n, 256, y, 256, t[2 * layer + 1], 1, 0.f);
+      if (layer == 0) {
+        seg_fwd(q, enc, 63, t[0], 63, 0, 63);
+      } else if (layer == 5) {
+        seg_fwd(q, enc, 63, t[10], 319, 0, 63);
+        seg_fwd(q, x, 256, t[10], 319, 63, 256);
+      } else {
+        seg_fwd(q, x, 256, t[2 * layer], 256, 0, 256);
+      }
+      return q;
+    };
+    auto tangent = [&](int layer, const float* xt, const float* mask, float* yt) {
+      GemmProb q = prob_fwd(n, 256, yt, 256, nullptr, 0, 0.f);
+      q.dact = mask;
+      q.ld_dact = 256;
+      q.slope = 0.f;
+      if (layer == 0) {
+        seg_fwd(q, enc_t, 63, t[0], 63, 0, 63);
+      } else if (layer == 5) {
+        seg_fwd(q, enc_t, 63, t[10], 319, 0, 63);
+        seg_fwd(q, xt, 256, t[10], 319, 63, 256);
+      } else {
+        seg_fwd(q, xt, 256, t[2 * layer], 256, 0, 256);
+      }
+      return q;
+    };
+    {
+      GemmProb q = primal(0, nullptr, hp[0]);
+      if (tgemm_group(st, &q, 1)) return 1;
+    }
+    for (int k = 1; k <= 7; ++k) {   // h_k in hp[k & 1], t_k in ht[k & 1]
+      GemmProb q[2] = {primal(k, hp[(k - 1) & 1], hp[k & 1]), tangent(k - 1, ht[k & 1], hp[(k - 1) & 1], ht[(k - 1) & 1])};
+      if (tgemm_group(st, q, 2)) return 1;
+    }
+    {
+      // feature_linear(h7) (bias, no activation) + tangent of layer 7; h7 = hp[1], t6 = ht[0] -> t7 = ht[1]
+      GemmProb q[2];
+      q[0] = prob_fwd(n, 256, feat, 256, t[19], 0, 0.f);
+      seg_fwd(q[0], hp[1], 256, t[18], 256, 0, 256);
+      q[1] = tangent(7, ht[0], hp[1], ht[1]);
+      if (tgemm_group(st, q, 2)) return 1;
+    }
+    float* hv = hp[0];        // [n, 128] view-layer activations (h6 is dead)
+    float* hv_t = ht[0];      // [n, 128]
+    {
+      // views_linears.0 on cat([feature, gamma(viewdir)]) + ReLU; feature tangent = W_f t7 (no mask)
+      GemmProb q[2];
+      q[0] = prob_fwd(n, 128, hv, 128, t[17], 1, 0.f);
+      seg_fwd(q[0], feat, 256, t[16], 283, 0, 256);
+      seg_fwd(q[0], venc, 27, t[16], 283, 256, 27);
+      q[1] = prob_fwd(n, 256, feat_t, 256, nullptr, 0, 0.f);
+      seg_fwd(q[1], ht[1], 256, t[18], 256, 0, 256);
+      if (tgemm_group(st, q, 2)) return 1;
+    }
+    {
+      GemmProb q = prob_fwd(n, 128, hv_t, 128, nullptr, 0, 0.f);   // the view encoding has no tangent
+      q.dact = hv;
+      q.ld_dact = 128;
+      q.slope = 0.f;
+      seg_fwd(q, feat_t, 256, t[16], 283, 0, 256);
+      if (tgemm_group(st, &q, 1)) return 1;
+    }
+    // alpha_linear(h7) / rgb_linear(hv) and their tangents: eight dot products per ray, one warp per ray
+    nerf_point_heads_kernel<<<(n + 7) / 8, 256, 0, st>>>(hp[1], ht[1], hv, hv_t, t[20], t[21], t[22], t[23], n, out_raw, out_draw_dz);
+    LAUNCH_CHECK();
+    return 0;
+  }
   float* cur = h0;
   float* nxt = h1;
   // run_nerf_helpers.py:109-134: h = relu(L_i(h)); after layer 4, h = cat([input_pts, h])
@@ -856,6 +1455,68 @@ extern "C" int b200nerf_adam_step(float* param, const float* grad, float* exp_av
   const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
   adam_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- training losses
+// Trainer.core_optimization_loop (Trainer.py:525-538) for the DepthNet path: img_loss = mean((rgb - target)^2) with
+// rgb = sigmoid(raw rgb) (one sample per ray: the S == 1 quirk of raw2outputs), depth_net_loss = mean((z_dn - max_z)^2),
+// psnr = -10 log10(img_loss), and the gradient both losses send into z_dn -- d(depth loss)/dz + d(img loss)/d rgb * rgb(1-rgb) *
+// d raw / dz (the forward-mode tangent of b200nerf_nerf_point_jvp) -- in one pass instead of ~20 elementwise autograd launches.
+__global__ void __launch_bounds__(256) train_loss_kernel(const float* __restrict__ raw, const float* __restrict__ draw,
+                                                         const float* __restrict__ z, const float* __restrict__ max_z,
+                                                         const float* __restrict__ target, int n, float* __restrict__ acc,
+                                                         float* __restrict__ dz) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float img = 0.f, dn = 0.f;
+  if (i < n) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(raw) + i), dr = __ldg(reinterpret_cast<const float4*>(draw) + i);
+    const float rr[3] = {r.x, r.y, r.z}, dd[3] = {dr.x, dr.y, dr.z};
+    const float dzv = z[i] - max_z[i];
+    dn = dzv * dzv;
+    float gz = 2.0f * dzv / static_cast<float>(n);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float rgb = 1.0f / (1.0f + expf(-rr[c]));
+      const float diff = rgb - target[i * 3 + c];
+      img = fmaf(diff, diff, img);
+      gz = fmaf(2.0f * diff / (3.0f * static_cast<float>(n)) * rgb * (1.0f - rgb), dd[c], gz);
+    }
+    dz[i] = gz;
+  }
+  __shared__ float red[2][8];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    img += __shfl_xor_sync(0xffffffffu, img, off);
+    dn += __shfl_xor_sync(0xffffffffu, dn, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = img;
+    red[1][threadIdx.x >> 5] = dn;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+__global__ void train_loss_finish_kernel(const float* __restrict__ acc, int n, float* __restrict__ out) {
+  const float img = acc[0] / (3.0f * static_cast<float>(n));
+  out[0] = img;
+  out[1] = acc[1] / static_cast<float>(n);
+  out[2] = -10.0f * logf(img) / logf(10.0f);
+}
+extern "C" int b200nerf_train_loss(const float* raw, const float* draw_dz, const float* z_dn, const float* max_z, const float* target,
+                                   int n_rays, float* ws2, float* out_losses, float* out_dz, void* stream) {
+  if (n_rays <= 0) return b200_fail("b200nerf_train_loss: empty batch");
+  if (!raw || !draw_dz || !z_dn || !max_z || !target || !ws2 || !out_losses || !out_dz) return b200_fail("b200nerf_train_loss: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(ws2, 0, 2 * sizeof(float), st));
+  train_loss_kernel<<<(n_rays + 255) / 256, 256, 0, st>>>(raw, draw_dz, z_dn, max_z, target, n_rays, ws2, out_dz);
+  LAUNCH_CHECK();
+  train_loss_finish_kernel<<<1, 1, 0, st>>>(ws2, n_rays, out_losses);
   LAUNCH_CHECK();
   return 0;
 }

@@ -197,6 +197,11 @@ class Trainer:
         work on the current stream -- this is the part ``training.GraphedTrainStep`` captures in a CUDA graph."""
         import torch.nn.functional as F
 
+        from ... import training
+
+        fused = training.fused_render_and_backward(self, sampling_optimizer, render_kwargs_train, batch_rays, target_s)
+        if fused is not None:   # the standard configuration: six C calls, no autograd graph
+            return fused[0], fused[1], fused[2], None
         depth_net_rgb, depth_net_disp, extras = nerf_utils.render(self.H, self.W, self.K, chunk=self.chunk, rays=batch_rays,
                                                                   verbose=i < 10, retraw=True, **render_kwargs_train)
         sampling_optimizer.zero_grad()

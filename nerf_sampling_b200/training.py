@@ -141,6 +141,83 @@ def nerf_params(module) -> List[torch.nn.Parameter]:
     return [sd[k] for k in NERF_KEYS]
 
 
+def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, target_s):
+    """The DepthNet training render and both backward passes of ``Trainer.core_optimization_loop`` (Trainer.py:515-538) as six
+    C calls and no autograd graph: hierarchical arg-max target on the frozen NeRFs (tensor-core kernels), DepthNet forward with
+    saved activations, frozen fine NeRF at one sample per ray with its forward-mode d raw / d z, both losses and the gradient
+    they send into z in one kernel (``b200nerf_train_loss``), DepthNet backward into ONE flat gradient buffer whose address
+    never changes (so the optimizer's pointer table and ``parallel.allreduce_gradients`` see the same tensors every step).
+
+    Returns ``(loss, depth_net_loss, psnr)`` as 0-dim tensors, or ``None`` when the configuration is not the standard one
+    (foreign DepthNet / NeRF modules, optimizer over other parameters): the caller then takes the autograd route, which
+    computes the same thing through ``DepthNetTrainFn`` / ``NerfPointFn`` / ``CompositeSingleFn``."""
+    from . import ops
+    from .depth_nets.depth_net import DepthNet
+
+    dn = render_kwargs.get("depth_network")
+    net = render_kwargs.get("network_fine") if render_kwargs.get("network_fine") is not None else render_kwargs.get("network_fn")
+    if not isinstance(dn, DepthNet) or not hasattr(net, "query") or not render_kwargs.get("use_viewdirs", False):
+        return None
+    params = depthnet_params(dn)
+    opt_params = [p for g in optimizer.param_groups for p in g["params"]]
+    if len(opt_params) != len(params) or any(a is not b for a, b in zip(opt_params, params)):
+        return None
+    if any((not p.requires_grad) or p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous() for p in params):
+        return None
+    L = _lib.lib()
+    rays_o, rays_d = batch_rays[0].contiguous().float(), batch_rays[1].contiguous().float()
+    n, dev = rays_o.shape[0], rays_o.device
+    target = target_s.contiguous().float()
+    hidden, cat = depthnet_arch(dn)
+    cache = dn.__dict__.get("_b200_train_cache")
+    if cache is None or cache["dev"] != dev or cache["ptrs"] != [p.data_ptr() for p in params]:
+        flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+        grads, off = [], 0
+        for p in params:
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        cache = dn.__dict__["_b200_train_cache"] = dict(dev=dev, ptrs=[p.data_ptr() for p in params], flat=flat, grads=grads, bounds={})
+    bounds = cache["bounds"].get((n, float(render_kwargs["near"]), float(render_kwargs["far"])))
+    if bounds is None:
+        bounds = cache["bounds"][(n, float(render_kwargs["near"]), float(render_kwargs["far"]))] = (
+            torch.full((n, 1), float(render_kwargs["near"]), device=dev), torch.full((n, 1), float(render_kwargs["far"]), device=dev))
+    with torch.no_grad(), torch.cuda.device(dev):
+        viewdirs = ops.normalize_dirs(rays_d)
+        kw = render_kwargs
+        c = trainer.sample_coarse_points(near=bounds[0], far=bounds[1], perturb=kw["perturb"], N_rays=n, N_samples=kw["N_samples"],
+                                         viewdirs=viewdirs, network_fn=kw["network_fn"], network_query_fn=kw["network_query_fn"],
+                                         rays_o=rays_o, rays_d=rays_d, raw_noise_std=kw["raw_noise_std"], white_bkgd=kw["white_bkgd"],
+                                         pytest=False, lindisp=kw.get("lindisp", False))
+        f = trainer.sample_fine_points(z_vals=c[5], weights=c[6], perturb=kw["perturb"], pytest=False, rays_d=rays_d, rays_o=rays_o,
+                                       rgb_map=c[0], disp_map=c[1], acc_map=c[2], network_fn=kw["network_fn"],
+                                       network_fine=kw["network_fine"], network_query_fn=kw["network_query_fn"], viewdirs=viewdirs,
+                                       raw_noise_std=kw["raw_noise_std"], white_bkgd=kw["white_bkgd"])
+        _, max_z, _, _ = ops.argmax_gather(f[11], f[7])
+        st = _stream()
+        ws = torch.empty(L.b200nerf_depthnet_train_ws_floats(n, len(hidden), _ints(hidden), len(cat), _ints(cat)), device=dev)
+        z = torch.empty(n, 1, device=dev)
+        p_arr = _ptrs(params)
+        nf = (float(dn.near), float(dn.far))
+        _lib.check(L.b200nerf_depthnet_train_fwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), rays_o.data_ptr(),
+                                                 rays_d.data_ptr(), n, float(dn.sphere_radius), nf[0], nf[1], ws.data_ptr(), z.data_ptr(), st))
+        ws_n = torch.empty(L.b200nerf_nerf_point_ws_floats(n), device=dev)
+        raw = torch.empty(n, 1, 4, device=dev)
+        draw = torch.empty(n, 4, device=dev)
+        _lib.check(L.b200nerf_nerf_point_jvp(_ptrs(nerf_params(net)), rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(),
+                                             z.data_ptr(), n, ws_n.data_ptr(), raw.data_ptr(), draw.data_ptr(), st))
+        losses = torch.empty(3, device=dev)
+        dz = torch.empty(n, device=dev)
+        ws2 = torch.empty(2, device=dev)
+        _lib.check(L.b200nerf_train_loss(raw.data_ptr(), draw.data_ptr(), z.data_ptr(), max_z.data_ptr(), target.data_ptr(), n,
+                                         ws2.data_ptr(), losses.data_ptr(), dz.data_ptr(), st))
+        _lib.check(L.b200nerf_depthnet_train_bwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), n, nf[0], nf[1], ws.data_ptr(),
+                                                 dz.data_ptr(), _ptrs(cache["grads"]), st))
+    for p, g in zip(params, cache["grads"]):
+        if p.grad is not g:
+            p.grad = g
+    return losses[0], losses[1], losses[2]
+
+
 class Adam(torch.optim.Optimizer):
     """torch.optim.Adam semantics (no weight decay, no amsgrad) on the library's fused kernel: ONE launch updates every
     tensor of a parameter group.  ``grad_scale`` multiplies every gradient first (1 / world_size after a sum all-reduce).

@@ -217,6 +217,42 @@ def test_training_step_4096_rays_all_gradients_vs_autograd(lib, oracle_models):
         p.grad = None
 
 
+def test_fused_training_step_equals_autograd_route(lib, oracle_models):
+    """training.fused_render_and_backward (six C calls, no autograd graph) against the autograd route through
+    DepthNetTrainFn / NerfPointFn / CompositeSingleFn on the same batch: same losses, same 82 gradients."""
+    from nerf_sampling_b200 import training
+    from nerf_sampling_b200.nerf_pytorch import nerf_utils
+    from nerf_sampling_b200.packing import PREC_FAST
+
+    H = W = 800
+    models = _models(oracle_models, PREC_FAST)
+    tr, kw = _trainer_kw(models)
+    kw["model_mode"] = "train"
+    tr.H, tr.W, tr.K, tr.chunk = H, W, O.intrinsics(H, W), 32768
+    packed, *_ = O.prepare_rays(H, W, O.intrinsics(H, W), c2w=O.pose_spherical(30.0, -30.0, 4.0)[:3, :4])
+    sel = torch.randperm(H * W, generator=torch.Generator().manual_seed(3))[:777]     # ragged: not a multiple of any tile
+    ro, rd = packed[sel, 0:3].contiguous().to(DEV), packed[sel, 3:6].contiguous().to(DEV)
+    target = torch.rand(777, 3, generator=torch.Generator().manual_seed(4)).to(DEV)
+    params = list(models[2].parameters())
+    opt = training.Adam(params, lr=1e-4)
+    out = training.fused_render_and_backward(tr, opt, kw, (ro, rd), target)
+    assert out is not None
+    fused = [p.grad.detach().clone() for p in params]
+    for p in params:
+        p.grad = None
+    rgb, _, ex = nerf_utils.render(H, W, tr.K, rays=(ro, rd), retraw=True, **kw)
+    img_loss = torch.mean((rgb - target) ** 2)
+    dn_loss = torch.nn.functional.mse_loss(ex["depth_net_z_vals"], ex["max_z_vals"])
+    torch.autograd.backward([dn_loss, img_loss])
+    assert abs(float(out[0]) - float(img_loss)) <= 1e-6 * max(1.0, float(img_loss))
+    assert abs(float(out[1]) - float(dn_loss)) <= 1e-6 * max(1.0, float(dn_loss))
+    assert abs(float(out[2]) - float(-10.0 * torch.log10(img_loss))) <= 1e-4
+    for p, g in zip(params, fused):
+        assert float((p.grad - g).abs().max()) <= 1e-5 * float(g.abs().max()) + 1e-12   # split-K atomics reorder the last bits
+    for p in params:
+        p.grad = None
+
+
 # ------------------------------------------------------------------------------------------- render.py flags and the -e sweep
 @pytest.mark.parametrize("mode,S,dist", [("uniform", 2, 0.3), ("uniform", 128, 1.0), ("gaussian", 32, 0.3), ("gaussian", 64, 0.5),
                                          ("gaussian", 2, 1.0), ("uniform", 32, 0.5), ("gaussian", 128, 0.1)])
