@@ -27,14 +27,13 @@ extern "C" {
 
 /* precision of the tensor-core MLPs */
 #define B200NERF_PREC_SPLIT 1 /* bf16 hi+lo operands, 3 MMAs / K16 block, ~16 mantissa bits (parity mode) */
-#define B200NERF_PREC_BF16 0  /* plain bf16 operands, 1 MMA / K16 block (PSNR-level parity only)           */
 #define B200NERF_PREC_FP16 2  /* plain fp16 operands, 1 MMA / K16 block, throughput kernel (PSNR-level parity)  */
 #define B200NERF_PREC_FAST 3  /* PREC_FP16 + split-precision re-evaluation of the guard band
                                  (b200nerf_nerf_mlp_guarded_fwd): meets the 1e-3 max-abs contract          */
 
 /* A packed NeRF on the device, as the fused render entry points take it. */
 typedef struct b200nerf_nerf_model {
-  const void* wpack;      /* slab stream of b200nerf_nerf_pack (SPLIT or BF16); NULL for PREC_FP16          */
+  const void* wpack;      /* slab stream of b200nerf_nerf_pack (PREC_SPLIT); NULL for PREC_FP16             */
   const void* wpack_fast; /* slab stream of b200nerf_nerf_pack_fast; NULL for SPLIT / BF16                   */
   const float* aux;       /* fp32 bias / head block                                                          */
   int prec;               /* B200NERF_PREC_*                                                                 */

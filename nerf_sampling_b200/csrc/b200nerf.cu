@@ -10,7 +10,7 @@
 
 #include "../../include/b200nerf.h"
 #include "host_common.h"
-#include "mlp_chain.cuh"
+#include "umma_selftest.cuh"
 #include "mlp_exact.cuh"
 #include "mlp_fast.cuh"
 #include "composite_tma.cuh"
@@ -58,26 +58,6 @@ static inline float bf2f(uint16_t h) {
   return f;
 }
 
-// W [N, ldw] fp32, columns [col0, col0+K) -> Kpad/16 slabs; one slab = hi [2][N/8][8 rows][8 k] bf16 (+ lo).
-static uint8_t* pack_linear(const float* W, int N, int K, int ldw, int col0, int Kpad, bool split, uint8_t* out) {
-  const size_t plane = static_cast<size_t>(N) * 32;
-  for (int k16 = 0; k16 < Kpad / 16; ++k16) {
-    uint16_t* hi = reinterpret_cast<uint16_t*>(out);
-    uint16_t* lo = reinterpret_cast<uint16_t*>(out + plane);
-    for (int kc = 0; kc < 2; ++kc)
-      for (int n = 0; n < N; ++n)
-        for (int e = 0; e < 8; ++e) {
-          const int k = k16 * 16 + kc * 8 + e;
-          const float w = k < K ? W[static_cast<size_t>(n) * ldw + col0 + k] : 0.f;
-          const size_t idx = static_cast<size_t>(kc) * N * 8 + static_cast<size_t>(n >> 3) * 64 + (n & 7) * 8 + e;
-          const uint16_t h = f2bf(w);
-          hi[idx] = h;
-          if (split) lo[idx] = f2bf(w - bf2f(h));
-        }
-    out += split ? 2 * plane : plane;
-  }
-  return out;
-}
 
 // NeRF aux block (float offsets)
 enum : uint32_t {
@@ -334,58 +314,26 @@ static int launch_exact(exact::ExactParams& p, const XProgram& pg, const void* w
 }
 
 
-// SPLIT precision runs on the pipelined exact kernel (mlp_exact.cuh) and its pack layout; B200NERF_EXACT_LEGACY=1 keeps the
-// sequential kernel (mlp_chain.cuh), which also serves the legacy PREC_BF16 mode.
-static bool use_pipelined_exact() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200NERF_EXACT_LEGACY");
-    v = (e && e[0] == '1') ? 0 : 1;
-  }
-  return v == 1;
-}
-
+// Split precision (bf16 hi + lo operands, 3 MMAs per K16 block) is the only mode of the exact kernel (mlp_exact.cuh).
 extern "C" size_t b200nerf_nerf_wpack_bytes(int prec) {
-  if (prec == B200NERF_PREC_SPLIT && use_pipelined_exact()) return nerf_xprogram(nullptr).pack_bytes();
-  // K16 slabs: skip part 4 + L0 4 + 7 trunk layers x 16 + feature 16 (N=256) and 18 view slabs (N=128)
-  const size_t per256 = prec == B200NERF_PREC_SPLIT ? 16384 : 8192;
-  return (4 + 4 + 7 * 16 + 16) * per256 + 18 * (per256 / 2);
+  if (prec != B200NERF_PREC_SPLIT) return 0;
+  return nerf_xprogram(nullptr).pack_bytes();
 }
 extern "C" size_t b200nerf_nerf_aux_floats(void) { return NERF_AUX_FLOATS; }
 
 extern "C" int b200nerf_nerf_pack(const float* const* t, int prec, void* h_wpack, float* h_aux) {
   if (!t || !h_wpack || !h_aux) return fail("b200nerf_nerf_pack: null argument");
-  const bool split = prec == B200NERF_PREC_SPLIT;
+  if (prec != B200NERF_PREC_SPLIT) return fail("b200nerf_nerf_pack: prec must be B200NERF_PREC_SPLIT");
   uint8_t* o = static_cast<uint8_t*>(h_wpack);
-  const float* W[8];
   const float* B[8];
-  for (int i = 0; i < 8; ++i) {
-    W[i] = t[2 * i];
-    B[i] = t[2 * i + 1];
-  }
-  const float *Wv = t[16], *Bv = t[17], *Wf = t[18], *Bf = t[19], *Wa = t[20], *Ba = t[21], *Wr = t[22], *Br = t[23];
-  const bool pipelined = split && use_pipelined_exact();
-  if (pipelined) {
-    const int rc = pack_xprogram(nerf_xprogram(t), o);
-    if (rc) return rc;
-  }
-  if (!pipelined) {
-    o = pack_linear(W[5], 256, 63, 319, 0, 64, split, o);   // skip-connection part of pts_linears.5 (input_pts columns)
-    o = pack_linear(W[0], 256, 63, 63, 0, 64, split, o);    // pts_linears.0
-    for (int i = 1; i <= 4; ++i) o = pack_linear(W[i], 256, 256, 256, 0, 256, split, o);
-    o = pack_linear(W[5], 256, 256, 319, 63, 256, split, o);  // hidden part of pts_linears.5
-    o = pack_linear(W[6], 256, 256, 256, 0, 256, split, o);
-    o = pack_linear(W[7], 256, 256, 256, 0, 256, split, o);
-    o = pack_linear(Wf, 256, 256, 256, 0, 256, split, o);
-    o = pack_linear(Wv, 128, 283, 283, 0, 288, split, o);   // [feature | view encoding] -> 128
-    if (static_cast<size_t>(o - static_cast<uint8_t*>(h_wpack)) != b200nerf_nerf_wpack_bytes(prec))
-      return fail("b200nerf_nerf_pack: internal size mismatch");
-  }
+  for (int i = 0; i < 8; ++i) B[i] = t[2 * i + 1];
+  const float *Bf = t[19], *Wa = t[20], *Ba = t[21], *Wr = t[22], *Br = t[23];
+  const int rc = pack_xprogram(nerf_xprogram(t), o);
+  if (rc) return rc;
   memset(h_aux, 0, NERF_AUX_FLOATS * sizeof(float));
   for (int i = 0; i < 8; ++i) memcpy(h_aux + NERF_B0 + 256 * i, B[i], 256 * sizeof(float));
   memcpy(h_aux + NERF_BF, Bf, 256 * sizeof(float));
-  if (pipelined) nerf_fold_view(t, h_aux + NERF_BV);   // the pipelined program runs the folded view layer
-  else memcpy(h_aux + NERF_BV, Bv, 128 * sizeof(float));
+  nerf_fold_view(t, h_aux + NERF_BV);   // the program runs the view layer with feature_linear folded in
   memcpy(h_aux + NERF_WA, Wa, 256 * sizeof(float));
   h_aux[NERF_BA] = Ba[0];
   memcpy(h_aux + NERF_WR, Wr, 384 * sizeof(float));
@@ -448,8 +396,8 @@ extern "C" size_t b200nerf_nerf_fast_wpack_bytes(void) { return fast::WPACK_BYTE
 
 extern "C" int b200nerf_nerf_pack_fast(const float* const* t, int prec, void* h_wpack) {
   if (!t || !h_wpack) return fail("b200nerf_nerf_pack_fast: null argument");
-  if (prec != B200NERF_PREC_FP16 && prec != B200NERF_PREC_BF16) return fail("b200nerf_nerf_pack_fast: prec must be FP16 or BF16");
-  const bool fp16 = prec == B200NERF_PREC_FP16;
+  if (prec != B200NERF_PREC_FP16) return fail("b200nerf_nerf_pack_fast: prec must be B200NERF_PREC_FP16");
+  const bool fp16 = true;
   uint8_t* o = static_cast<uint8_t*>(h_wpack);
   const float* W[8];
   for (int i = 0; i < 8; ++i) W[i] = t[2 * i];
@@ -486,13 +434,17 @@ extern "C" int b200nerf_nerf_pack_fast(const float* const* t, int prec, void* h_
   return 0;
 }
 
-// the pipelined kernel keeps all biases + the head in its 3080-float shared-memory block: up to 10 hidden layers
-static bool depthnet_pipelined(int n_hidden, int prec) {
-  return prec == B200NERF_PREC_SPLIT && use_pipelined_exact() && n_hidden <= 10;
+// the exact kernel keeps all biases + the head in its 3080-float shared-memory block: up to 10 hidden layers (the reference's
+// experiments build 10: run.py:104-109)
+constexpr int DEPTHNET_MAX_HIDDEN = 10;
+static int depthnet_check(const char* who, int n_hidden, int prec) {
+  if (prec != B200NERF_PREC_SPLIT) return fail("%s: prec must be B200NERF_PREC_SPLIT (the depth feeds the 2^9 octave of the encoding)", who);
+  if (n_hidden < 0 || n_hidden > DEPTHNET_MAX_HIDDEN) return fail("%s: n_hidden=%d out of range (0..%d)", who, n_hidden, DEPTHNET_MAX_HIDDEN);
+  return 0;
 }
 extern "C" size_t b200nerf_depthnet_wpack_bytes(int n_hidden, int prec) {
-  if (depthnet_pipelined(n_hidden, prec)) return depthnet_xprogram(nullptr, nullptr, n_hidden).pack_bytes();
-  return static_cast<size_t>(n_hidden + 1) * 16 * (prec == B200NERF_PREC_SPLIT ? 16384 : 8192);
+  if (prec != B200NERF_PREC_SPLIT || n_hidden < 0 || n_hidden > DEPTHNET_MAX_HIDDEN) return 0;
+  return depthnet_xprogram(nullptr, nullptr, n_hidden).pack_bytes();
 }
 extern "C" size_t b200nerf_depthnet_aux_floats(int n_hidden) { return static_cast<size_t>(n_hidden + 1) * 256 + 256 + 4; }
 
@@ -500,21 +452,11 @@ extern "C" int b200nerf_depthnet_pack(const float* h_w0, const float* h_b0, cons
                                       const float* h_head_w, const float* h_head_b, int prec, void* h_wpack, float* h_aux) {
   if (!h_w0 || !h_b0 || !h_head_w || !h_head_b || !h_wpack || !h_aux || (n_hidden > 0 && !h_hidden))
     return fail("b200nerf_depthnet_pack: null argument");
-  if (n_hidden < 0 || n_hidden + 1 > MAX_STEPS) return fail("b200nerf_depthnet_pack: n_hidden=%d out of range", n_hidden);
-  const bool split = prec == B200NERF_PREC_SPLIT;
-  uint8_t* o = static_cast<uint8_t*>(h_wpack);
-  const bool pipelined = depthnet_pipelined(n_hidden, prec);
-  if (pipelined) {
-    const int rc = pack_xprogram(depthnet_xprogram(h_w0, h_hidden, n_hidden), o);
-    if (rc) return rc;
-  } else {
-    o = pack_linear(h_w0, 256, 256, 256, 0, 256, split, o);
-  }
+  if (depthnet_check("b200nerf_depthnet_pack", n_hidden, prec)) return 1;
+  const int rc = pack_xprogram(depthnet_xprogram(h_w0, h_hidden, n_hidden), static_cast<uint8_t*>(h_wpack));
+  if (rc) return rc;
   memcpy(h_aux, h_b0, 256 * sizeof(float));
-  for (int i = 0; i < n_hidden; ++i) {
-    if (!pipelined) o = pack_linear(h_hidden[2 * i], 256, 256, 256, 0, 256, split, o);
-    memcpy(h_aux + 256 * (i + 1), h_hidden[2 * i + 1], 256 * sizeof(float));
-  }
+  for (int i = 0; i < n_hidden; ++i) memcpy(h_aux + 256 * (i + 1), h_hidden[2 * i + 1], 256 * sizeof(float));
   memcpy(h_aux + 256 * (n_hidden + 1), h_head_w, 256 * sizeof(float));
   float* hb = h_aux + 256 * (n_hidden + 2);
   hb[0] = h_head_b[0];
@@ -1002,93 +944,28 @@ extern "C" int b200nerf_composite_tile_fwd(const float* raw, const float* z, con
 }
 
 // ------------------------------------------------------------------------------------------- MLP launches
-template <bool SPLIT, int INPUT>
-static int launch_chain(const ChainParams& p, cudaStream_t st) {
-  static bool configured[B200_MAX_DEVICES] = {false};
-  constexpr int smem = chain_smem_bytes<SPLIT>();
-  const int dev = b200_device();
-  if (dev < 0) return fail("mlp_chain_kernel: no usable CUDA device");
-  if (!configured[dev]) {
-    CUDA_TRY(cudaFuncSetAttribute(mlp_chain_kernel<SPLIT, INPUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured[dev] = true;
-  }
-  const int sms = sm_count();
-  if (sms <= 0) return fail("no CUDA device");
-  const int tiles = (p.n_rows + TILE_M - 1) / TILE_M;
-  const int grid = tiles < sms ? tiles : sms;
-  mlp_chain_kernel<SPLIT, INPUT><<<grid, CHAIN_THREADS, smem, st>>>(p);
-  LAUNCH_CHECK();
-  return 0;
-}
-
-static Step make_step(int a_begin, int n_k16, int n, int acc_col, int accumulate, int wait_a, int epi, int act, uint32_t bias_off) {
-  Step s;
-  s.a_k16_begin = static_cast<uint16_t>(a_begin);
-  s.n_k16 = static_cast<uint16_t>(n_k16);
-  s.n = static_cast<uint16_t>(n);
-  s.acc_col = static_cast<uint16_t>(acc_col);
-  s.accumulate = static_cast<uint8_t>(accumulate);
-  s.wait_a = static_cast<uint8_t>(wait_a);
-  s.epi = static_cast<uint8_t>(epi);
-  s.act = static_cast<uint8_t>(act);
-  s.bias_off = bias_off;
-  return s;
-}
-
 // row_index / n_rows_dev != nullptr: evaluate only the listed sample points (at most list_cap of them), in place
-static int nerf_chain_launch(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,
-                             const float* viewdirs, const float* z, const float* pts, int n_rays, int S, float* out_raw,
-                             const int* row_index, const int* n_rows_dev, int list_cap, cudaStream_t st) {
-  if (prec == B200NERF_PREC_SPLIT && use_pipelined_exact()) {
-    exact::ExactParams xp;
-    memset(&xp, 0, sizeof(xp));
-    xp.aux = aux;
-    xp.n_rows = row_index ? list_cap : n_rays * S;
-    xp.S = S;
-    xp.rays_o = rays_o;
-    xp.rays_d = rays_d;
-    xp.viewdirs = viewdirs;
-    xp.z = z;
-    xp.pts = pts;
-    xp.out = out_raw;
-    xp.row_index = row_index;
-    xp.n_rows_dev = n_rows_dev;
-    xp.head_w_off = NERF_WA;
-    xp.head_b_off = NERF_BA;
-    xp.rgb_w_off = NERF_WR;
-    xp.rgb_b_off = NERF_BR;
-    return launch_exact<exact::IN_NERF>(xp, nerf_xprogram(nullptr), wpack, st);
-  }
-  ChainParams p;
-  memset(&p, 0, sizeof(p));
-  p.wpack = static_cast<const uint8_t*>(wpack);
-  p.aux = aux;
-  int n = 0;
-  // run_nerf_helpers.py:109-134.  TMEM: X = columns 0..255, Y = columns 256..511.
-  p.steps[n++] = make_step(0, 4, 256, 256, 0, 1, EPI_NONE, ACT_NONE, 0);              // enc(pts) . W5[:, :63]^T -> Y (kept for layer 5)
-  p.steps[n++] = make_step(0, 4, 256, 0, 0, 0, EPI_STORE, ACT_RELU, NERF_B0);         // layer 0
-  for (int i = 1; i <= 4; ++i) p.steps[n++] = make_step(0, 16, 256, 0, 0, 1, EPI_STORE, ACT_RELU, NERF_B0 + 256 * i);
-  p.steps[n++] = make_step(0, 16, 256, 256, 1, 1, EPI_STORE, ACT_RELU, NERF_B0 + 256 * 5);  // layer 5 = Y + h4 . W5[:, 63:]^T
-  p.steps[n++] = make_step(0, 16, 256, 0, 0, 1, EPI_STORE, ACT_RELU, NERF_B0 + 256 * 6);
-  p.steps[n++] = make_step(0, 16, 256, 0, 0, 1, EPI_STORE_ALPHA, ACT_RELU, NERF_B0 + 256 * 7);  // layer 7 + alpha_linear
-  p.steps[n++] = make_step(0, 16, 256, 0, 0, 1, EPI_STORE, ACT_NONE, NERF_BF);        // feature_linear (no activation)
-  p.steps[n++] = make_step(0, 18, 128, 0, 0, 1, EPI_NERF_OUT, ACT_RELU, NERF_BV);     // views_linears.0 + rgb_linear
-  p.n_steps = n;
-  p.n_rows = row_index ? list_cap : n_rays * S;
-  p.S = S;
-  p.rays_o = rays_o;
-  p.rays_d = rays_d;
-  p.viewdirs = viewdirs;
-  p.z = z;
-  p.pts = pts;
-  p.out = out_raw;
-  p.row_index = row_index;
-  p.n_rows_dev = n_rows_dev;
-  p.head_w_off = NERF_WA;
-  p.head_b_off = NERF_BA;
-  p.rgb_w_off = NERF_WR;
-  p.rgb_b_off = NERF_BR;
-  return prec == B200NERF_PREC_SPLIT ? launch_chain<true, IN_NERF>(p, st) : launch_chain<false, IN_NERF>(p, st);
+static int nerf_exact_launch(const void* wpack, const float* aux, const float* rays_o, const float* rays_d, const float* viewdirs,
+                             const float* z, const float* pts, int n_rays, int S, float* out_raw, const int* row_index,
+                             const int* n_rows_dev, int list_cap, cudaStream_t st) {
+  exact::ExactParams xp;
+  memset(&xp, 0, sizeof(xp));
+  xp.aux = aux;
+  xp.n_rows = row_index ? list_cap : n_rays * S;
+  xp.S = S;
+  xp.rays_o = rays_o;
+  xp.rays_d = rays_d;
+  xp.viewdirs = viewdirs;
+  xp.z = z;
+  xp.pts = pts;
+  xp.out = out_raw;
+  xp.row_index = row_index;
+  xp.n_rows_dev = n_rows_dev;
+  xp.head_w_off = NERF_WA;
+  xp.head_b_off = NERF_BA;
+  xp.rgb_w_off = NERF_WR;
+  xp.rgb_b_off = NERF_BR;
+  return launch_exact<exact::IN_NERF>(xp, nerf_xprogram(nullptr), wpack, st);
 }
 
 extern "C" int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,
@@ -1098,9 +975,9 @@ extern "C" int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int pr
   if (n_rays == 0) return 0;
   if (!wpack || !aux || !viewdirs || !out_raw) return fail("b200nerf_nerf_mlp_fwd: null argument");
   if (!pts && (!z || !rays_o || !rays_d)) return fail("b200nerf_nerf_mlp_fwd: need pts or (rays_o, rays_d, z)");
-  if (prec != B200NERF_PREC_SPLIT && prec != B200NERF_PREC_BF16) return fail("b200nerf_nerf_mlp_fwd: prec must be SPLIT or BF16");
+  if (prec != B200NERF_PREC_SPLIT) return fail("b200nerf_nerf_mlp_fwd: prec must be B200NERF_PREC_SPLIT");
   if (static_cast<long long>(n_rays) * S > 0x7fffff00LL) return fail("b200nerf_nerf_mlp_fwd: too many points for one call");
-  return nerf_chain_launch(wpack, aux, prec, rays_o, rays_d, viewdirs, z, pts, n_rays, S, out_raw, nullptr, nullptr, 0,
+  return nerf_exact_launch(wpack, aux, rays_o, rays_d, viewdirs, z, pts, n_rays, S, out_raw, nullptr, nullptr, 0,
                            static_cast<cudaStream_t>(stream));
 }
 
@@ -1110,42 +987,21 @@ extern "C" int b200nerf_depthnet_fwd(const void* wpack, const float* aux, int n_
   if (n_rays < 0) return fail("b200nerf_depthnet_fwd: bad n_rays");
   if (n_rays == 0) return 0;
   if (!wpack || !aux || !rays_o || !rays_d || !out_z) return fail("b200nerf_depthnet_fwd: null argument");
-  if (n_hidden < 0 || n_hidden + 1 > MAX_STEPS) return fail("b200nerf_depthnet_fwd: n_hidden=%d out of range", n_hidden);
-  if (depthnet_pipelined(n_hidden, prec)) {
-    exact::ExactParams xp;
-    memset(&xp, 0, sizeof(xp));
-    xp.aux = aux;
-    xp.n_rows = n_rays;
-    xp.S = 1;
-    xp.rays_o = rays_o;
-    xp.rays_d = rays_d;
-    xp.out = out_z;
-    xp.head_w_off = 256 * (n_hidden + 1);
-    xp.head_b_off = 256 * (n_hidden + 2);
-    xp.radius = radius;
-    xp.near = near_;
-    xp.far = far_;
-    return launch_exact<exact::IN_DEPTHNET>(xp, depthnet_xprogram(nullptr, nullptr, n_hidden), wpack, static_cast<cudaStream_t>(stream));
-  }
-  ChainParams p;
-  memset(&p, 0, sizeof(p));
-  p.wpack = static_cast<const uint8_t*>(wpack);
-  p.aux = aux;
-  for (int i = 0; i <= n_hidden; ++i)
-    p.steps[i] = make_step(0, 16, 256, 0, 0, 1, i == n_hidden ? EPI_DEPTH_OUT : EPI_STORE, ACT_LEAKY, 256 * i);
-  p.n_steps = n_hidden + 1;
-  p.n_rows = n_rays;
-  p.S = 1;
-  p.rays_o = rays_o;
-  p.rays_d = rays_d;
-  p.out = out_z;
-  p.head_w_off = 256 * (n_hidden + 1);
-  p.head_b_off = 256 * (n_hidden + 2);
-  p.radius = radius;
-  p.near = near_;
-  p.far = far_;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return prec == B200NERF_PREC_SPLIT ? launch_chain<true, IN_DEPTHNET>(p, st) : launch_chain<false, IN_DEPTHNET>(p, st);
+  if (depthnet_check("b200nerf_depthnet_fwd", n_hidden, prec)) return 1;
+  exact::ExactParams xp;
+  memset(&xp, 0, sizeof(xp));
+  xp.aux = aux;
+  xp.n_rows = n_rays;
+  xp.S = 1;
+  xp.rays_o = rays_o;
+  xp.rays_d = rays_d;
+  xp.out = out_z;
+  xp.head_w_off = 256 * (n_hidden + 1);
+  xp.head_b_off = 256 * (n_hidden + 2);
+  xp.radius = radius;
+  xp.near = near_;
+  xp.far = far_;
+  return launch_exact<exact::IN_DEPTHNET>(xp, depthnet_xprogram(nullptr, nullptr, n_hidden), wpack, static_cast<cudaStream_t>(stream));
 }
 
 
@@ -1225,7 +1081,7 @@ extern "C" int b200nerf_nerf_mlp_fast_fwd(const void* wpack_fast, const float* a
   if (n_rays == 0) return 0;
   if (!wpack_fast || !aux || !viewdirs || !out_raw) return fail("b200nerf_nerf_mlp_fast_fwd: null argument");
   if (!pts && (!z || !rays_o || !rays_d)) return fail("b200nerf_nerf_mlp_fast_fwd: need pts or (rays_o, rays_d, z)");
-  if (prec != B200NERF_PREC_FP16 && prec != B200NERF_PREC_BF16) return fail("b200nerf_nerf_mlp_fast_fwd: prec must be FP16 or BF16");
+  if (prec != B200NERF_PREC_FP16) return fail("b200nerf_nerf_mlp_fast_fwd: prec must be B200NERF_PREC_FP16");
   if (static_cast<long long>(n_rays) * S > 0x7ffff000LL) return fail("b200nerf_nerf_mlp_fast_fwd: too many points for one call");
   if (guard_count && (!guard_list || guard_cap <= 0)) return fail("b200nerf_nerf_mlp_fast_fwd: guard list missing");
   fast::FastParams p;
@@ -1246,7 +1102,7 @@ extern "C" int b200nerf_nerf_mlp_fast_fwd(const void* wpack_fast, const float* a
   p.guard_kappa = guard_kappa;
   p.timeline = g_timeline;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return prec == B200NERF_PREC_FP16 ? launch_fast<true>(p, st) : launch_fast<false>(p, st);
+  return launch_fast<true>(p, st);
 }
 
 extern "C" int b200nerf_nerf_mlp_guarded_fwd(const void* wpack_fast, const void* wpack_split, const float* aux, int prec,
@@ -1262,8 +1118,7 @@ extern "C" int b200nerf_nerf_mlp_guarded_fwd(const void* wpack_fast, const void*
                                       ws_guard + 4, n_rays, guard_kappa, stream);
   if (rc) return rc;
   // re-evaluate the flagged points in split precision, in place
-  return nerf_chain_launch(wpack_split, aux, B200NERF_PREC_SPLIT, rays_o, rays_d, viewdirs, z, pts, n_rays, S, out_raw,
-                           ws_guard + 4, ws_guard, n_rays, st);
+  return nerf_exact_launch(wpack_split, aux, rays_o, rays_d, viewdirs, z, pts, n_rays, S, out_raw, ws_guard + 4, ws_guard, n_rays, st);
 }
 
 // ------------------------------------------------------------------------------------------- fused render
@@ -1273,7 +1128,6 @@ extern "C" int b200nerf_nerf_query(const b200nerf_nerf_model* nerf, const float*
   if (!nerf) return fail("b200nerf_nerf_query: null model");
   switch (nerf->prec) {
     case B200NERF_PREC_SPLIT:
-    case B200NERF_PREC_BF16:
       return b200nerf_nerf_mlp_fwd(nerf->wpack, nerf->aux, nerf->prec, rays_o, rays_d, viewdirs, z, pts, n_rays, S, out_raw, stream);
     case B200NERF_PREC_FP16:
       return b200nerf_nerf_mlp_fast_fwd(nerf->wpack_fast, nerf->aux, B200NERF_PREC_FP16, rays_o, rays_d, viewdirs, z, pts, n_rays, S,

@@ -2,7 +2,7 @@
 // bits) on tcgen05 tensor cores, pipelined inside ONE 128-row tile per CTA, SMs paired as 2-CTA clusters.
 //
 // Used where the single 16-bit pass of mlp_fast.cuh is not enough: DepthNet.forward (its depth feeds the 2^9 octave of the
-// NeRF encoding), the guard band of the fast NeRF pass, and PREC_SPLIT.  Reference semantics as in mlp_chain.cuh
+// NeRF encoding), the guard band of the fast NeRF pass, and PREC_SPLIT.  Reference semantics:
 // (run_nerf_helpers.py:109-134, trainers/Trainer.py:789-806, depth_nets/depth_net.py:117-169).
 //
 // Two operand planes (hi, lo) of one tile already fill shared memory, so there is no second tile to ping-pong with.

@@ -22,7 +22,7 @@
 // (dist = 1e10, trainers/sampling_trainer.py:178-180), so a rounding error that flips the sign of a tiny sigma
 // flips the pixel.  The final epilogue therefore appends every last-of-ray sample with
 // |sigma| < kappa * sum_i |h7_i * w_alpha_i| to a list; the caller re-evaluates those points with the
-// split-precision kernel (mlp_chain.cuh) and overwrites them.
+// split-precision kernel (mlp_exact.cuh) and overwrites them.
 #pragma once
 #include <type_traits>
 

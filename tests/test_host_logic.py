@@ -39,22 +39,6 @@ def bf16_split(w):
     return hi, lo
 
 
-def decode_slabs(buf: torch.Tensor, n: int, kpad: int, split: bool):
-    """Inverse of the slab layout: per K16 block, hi plane [2][n/8][8][8] bf16 then lo plane."""
-    plane = n * 16
-    per = plane * (2 if split else 1)
-    u = buf.view(torch.bfloat16)
-    out_hi = torch.zeros(n, kpad, dtype=torch.bfloat16)
-    out_lo = torch.zeros(n, kpad, dtype=torch.bfloat16)
-    for k16 in range(kpad // 16):
-        blk = u[k16 * per : (k16 + 1) * per]
-        hi = blk[:plane].view(2, n // 8, 8, 8).permute(1, 2, 0, 3).reshape(n, 16)
-        out_hi[:, k16 * 16 : (k16 + 1) * 16] = hi
-        if split:
-            out_lo[:, k16 * 16 : (k16 + 1) * 16] = blk[plane:].view(2, n // 8, 8, 8).permute(1, 2, 0, 3).reshape(n, 16)
-    return out_hi, out_lo
-
-
 def _piece(buf, n_rows):
     """[2 k chunks][n_rows/8 groups][8 rows][8 k] 16-bit piece -> [n_rows, 16]."""
     return buf.view(2, n_rows // 8, 8, 8).permute(1, 2, 0, 3).reshape(n_rows, 16)
@@ -156,52 +140,6 @@ def test_nerf_pack_fast_layout(lib, oracle_models):
     assert off * 2 + 512 == wpack.numel()
 
 
-@pytest.mark.parametrize("prec", [0])
-def test_nerf_pack_layout(lib, oracle_models, prec):
-    from nerf_sampling_b200.packing import NERF_KEYS
-
-    _, fine, _ = oracle_models
-    host = [fine[k].contiguous() for k in NERF_KEYS]
-    arr = (C.c_void_p * 24)(*[t.data_ptr() for t in host])
-    wpack = torch.zeros(lib.b200nerf_nerf_wpack_bytes(prec), dtype=torch.uint8)
-    aux = torch.zeros(lib.b200nerf_nerf_aux_floats(), dtype=torch.float32)
-    assert lib.b200nerf_nerf_pack(C.cast(arr, C.c_void_p), prec, wpack.data_ptr(), aux.data_ptr()) == 0
-    split = prec == 1
-    per256 = 16384 if split else 8192
-    # stream order: W5[:, :63], W0, W1..W4, W5[:, 63:], W6, W7, feature (N=256); views (N=128, K=288)
-    w5 = fine["pts_linears.5.weight"]
-    want = [(w5[:, :63], 64), (fine["pts_linears.0.weight"], 64)]
-    want += [(fine[f"pts_linears.{i}.weight"], 256) for i in (1, 2, 3, 4)]
-    want += [(w5[:, 63:], 256), (fine["pts_linears.6.weight"], 256), (fine["pts_linears.7.weight"], 256),
-             (fine["feature_linear.weight"], 256)]
-    off = 0
-    for w, kpad in want:
-        nb = (kpad // 16) * per256
-        hi, lo = decode_slabs(wpack[off : off + nb], 256, kpad, split)
-        ref = torch.zeros(256, kpad)
-        ref[:, : w.shape[1]] = w
-        rh, rl = bf16_split(ref)
-        assert torch.equal(hi, rh)
-        if split:
-            assert torch.equal(lo, rl)
-            assert float((hi.float() + lo.float() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
-        off += nb
-    hi, lo = decode_slabs(wpack[off:], 128, 288, split)
-    ref = torch.zeros(128, 288)
-    ref[:, :283] = fine["views_linears.0.weight"]
-    assert torch.equal(hi, bf16_split(ref)[0])
-    assert off + 18 * per256 // 2 == wpack.numel()
-    # aux block
-    assert torch.equal(aux[0:256], fine["pts_linears.0.bias"])
-    assert torch.equal(aux[1792:2048], fine["pts_linears.7.bias"])
-    assert torch.equal(aux[2048:2304], fine["feature_linear.bias"])
-    assert torch.equal(aux[2304:2432], fine["views_linears.0.bias"])
-    assert torch.equal(aux[2432:2688], fine["alpha_linear.weight"][0])
-    assert float(aux[2688]) == float(fine["alpha_linear.bias"])
-    assert torch.equal(aux[2692:3076].view(3, 128), fine["rgb_linear.weight"])
-    assert torch.equal(aux[3076:3079], fine["rgb_linear.bias"])
-
-
 def kernel_input_layout(rays_o, rays_d, radius=2.0):
     """[enc(o)|0|enc(d)|0|enc(hit_near)|0|enc(hit_far)|0] -- the DepthNet kernel's 256-wide input."""
     _, hits = O.sphere_intersections(rays_o, rays_d, torch.tensor([radius]))
@@ -256,11 +194,8 @@ def test_depthnet_pack_roundtrip(lib):
                     assert torch.equal(_piece(u[off + 1024 : off + 2048], 64), bf16_split(w)[1])
                     off += 2048
     assert torch.equal(pk.aux[768:1024], pk.folded[3])  # head weights after 3 bias rows
-    # the legacy (sequential kernel) slab layout is still produced for PREC_BF16
-    pk0 = PackedDepthNet(dn, "cpu", prec=0)
-    assert pk0.wpack.numel() == 3 * 16 * 8192
-    hi, _ = decode_slabs(pk0.wpack[: 16 * 8192], 256, 256, False)
-    assert torch.equal(hi, bf16_split(w0)[0])
+    # only split precision exists: the predicted depth feeds the 2^9 octave of the NeRF encoding
+    assert lib.b200nerf_depthnet_wpack_bytes(2, 0) == 0 and lib.b200nerf_nerf_wpack_bytes(0) == 0
 
 
 # --------------------------------------------------------------------------------------------- module shells

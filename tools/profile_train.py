@@ -1,6 +1,6 @@
-"""Two eager training steps (config #5 shapes) for ncu: `ncu --set full -k regex:tgemm_kernel --launch-skip 45 -c 4 python tools/profile_train.py`
-captures the grouped backward launches of the first step (launch order: 10 branch-forward groups, cat_layers.0, 9 cat layers, the
-NeRF point JVP products, 9 cat backward groups, cat_layers.0 backward, 10 branch backward groups)."""
+"""Two eager training steps (config #5 shapes) for ncu: `ncu --set full -k regex:"tgemm|chain_" --launch-skip 36 -c 36 python tools/profile_train.py`
+captures the 33 grouped-GEMM and 3 chain launches of the second step (launch order: chain_fwd, branch product, cat_layers.0, 9 cat layers, the
+11 NeRF point JVP groups, 9 cat backward groups, cat_layers.0 backward, the G reduction, chain_bwd, chain_du)."""
 import os
 import sys
 
