@@ -614,12 +614,15 @@ def main():
                                                        2.0, 2.0, 6.0, mean.data_ptr(), z.data_ptr(), raw.data_ptr(), guard.data_ptr(),
                                                        tiles[0].data_ptr(), acc.data_ptr(), depth.data_ptr(), None, st))
             dist.all_gather_into_tensor(gathered[0], tiles[0])
-            h_out.copy_(gathered[0], non_blocking=True)
+            if rank == 0:
+                h_out.copy_(gathered[0], non_blocking=True)       # the driver rank receives all N images ...
+            else:
+                h_out[:n_rays].copy_(tiles[0], non_blocking=True)  # ... every other rank its own
             flush.zero_()
             main_stream.synchronize()   # the gathered host images are valid on return, like the single-GPU host call
 
         e2e_api_name = ("pinned host rays -> H2D -> b200nerf_render_depthnet_tile -> NCCL all_gather of the rgb|disp tiles -> D2H of "
-                        "all N images on every rank")
+                        "all N images on rank 0 (own image on the other ranks)")
         d2h = world * n_rays * 16
 
     e2e_step(0)
@@ -642,20 +645,20 @@ def main():
     hwf = [H, W, float(K[0][0])]
     shard = "views" if world > 1 else None
     with torch.no_grad():
-        nerf_utils.render_path(api_poses[: 2 * world], hwf, K, REF_CHUNK, kw, shard=shard)   # warms the pinned ring and NCCL
+        nerf_utils.render_path(api_poses[: 2 * world], hwf, K, REF_CHUNK, kw, shard=shard, dst=0)   # warms the pinned ring and NCCL
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        api_rgbs, _, _ = nerf_utils.render_path(api_poses, hwf, K, REF_CHUNK, kw, shard=shard)
+        api_rgbs, _, _ = nerf_utils.render_path(api_poses, hwf, K, REF_CHUNK, kw, shard=shard, dst=0)
         api_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(api_s, op=dist.ReduceOp.MAX)
     e2e_api = {"value": n_api * n_rays / float(api_s), "unit": "rays/s", "ms_per_view": 1e3 * float(api_s) / n_api * world, "views": n_api,
-               "api": "nerf_utils.render_path(poses, chunk=32768" + (", shard='views')" if world > 1 else ")") + " -> numpy rgbs/disps",
+               "api": "nerf_utils.render_path(poses, chunk=32768" + (", shard='views', dst=0)" if world > 1 else ")") + " -> numpy rgbs/disps",
                "h2d_bytes_per_step": 48, "d2h_bytes_per_step": (world if world > 1 else 1) * n_rays * 16,
                "note": "rays are generated from the 3x4 pose on the device (get_rays is row a1 of the path); the image stack is "
-                       "returned on every rank"}
+                       "returned on rank 0"}
 
     extra, strong, parity, eager = {}, None, None, None
     if not args.no_extra:
@@ -664,18 +667,18 @@ def main():
             # strong scaling: ONE view split N ways, gather included (render_path(shard='rays') schedule, device-timed)
             with torch.no_grad():
                 sp = torch.stack([pose_for_step(80 + i) for i in range(8)])
-                nerf_utils.render_path(sp[:2], hwf, K, REF_CHUNK, kw, shard="rays")
+                nerf_utils.render_path(sp[:2], hwf, K, REF_CHUNK, kw, shard="rays", dst=0)
                 torch.cuda.synchronize()
                 dist.barrier()
                 t0 = time.perf_counter()
-                nerf_utils.render_path(sp, hwf, K, REF_CHUNK, kw, shard="rays")
+                nerf_utils.render_path(sp, hwf, K, REF_CHUNK, kw, shard="rays", dst=0)
                 s_s = torch.tensor([time.perf_counter() - t0], device=dev)
             dist.all_reduce(s_s, op=dist.ReduceOp.MAX)
             strong = {"value": 8 * n_rays / float(s_s), "unit": "rays/s", "ms_per_view": 1e3 * float(s_s) / 8, "rays_per_gpu_per_view": n_rays // world,
-                      "scaling": "strong", "api": "nerf_utils.render_path(shard='rays') -> numpy on every rank, 8 views, wall clock",
+                      "scaling": "strong", "api": "nerf_utils.render_path(shard='rays', dst=0) -> numpy on rank 0, 8 views, wall clock",
                       "limiter": "per view each rank runs the same four launches on 1/N of the rays: the fixed per-launch cost (persistent-"
-                                 "kernel prologue/tail, ~74 CTA pairs x 2 tiles = 37,888 rays per wave of the MLP kernel) and the D2H of the "
-                                 "full image on every rank do not shrink with N"}
+                                 "kernel prologue/tail, 74 CTA pairs x 4 tiles of 128 points = 592 rays per wave of the MLP kernel, DepthNet's "
+                                 "one-tile-ahead staging) and the D2H + host unload of the full image on rank 0 do not shrink with N"}
         extra["config4"] = bench_config4(models, dev, world, rank)
         extra["config5"] = bench_config5(models, dev, world, rank)
         if rank == 0 and world == 1:

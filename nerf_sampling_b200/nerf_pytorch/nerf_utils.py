@@ -190,7 +190,7 @@ def _render_tile(H, W, K, c2w, lo, hi, chunk, render_kwargs, want_extras, out=No
 
 
 def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=False, save_scene_data=False, gt_imgs=None,
-                savedir=None, render_factor=0, group=None, shard=None):
+                savedir=None, render_factor=0, group=None, shard=None, dst=None):
     """Render a list of camera poses (nerf_utils.py:258-360) -> (rgbs [n,H,W,3], disps [n,H,W], mean PSNR) as numpy.
 
     Same results as the reference's loop, different schedule: view k+1 is rendered while view k's pixels travel to pinned
@@ -202,7 +202,9 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
     ``parallel.shard_bounds(H*W, world, rank)`` of EVERY view (latency / strong scaling).  Either way a rank writes its
     finished pixels as one [n_local, 4] rgb|disp tile, the tiles are all-gathered with NCCL on a side stream while the next
     view renders (double-buffered), and every rank returns the full image stack.  Rays are independent, so the sharded images
-    are bit-identical to the single-GPU ones.  ``shard=None`` (default) renders every pose on the calling rank.
+    are bit-identical to the single-GPU ones.  ``shard=None`` (default) renders every pose on the calling rank.  ``dst=r`` keeps the
+    host copy (and the PNG / PSNR work) on rank ``r`` only -- the other ranks return empty image stacks -- which is what a driver
+    script that saves from rank 0 wants; ``dst=None`` returns the full stack on every rank.
 
     ``wandb_log`` switches ``trainer.compare_nerf`` on like the reference (:294-295; the ray plots themselves are the host
     application's); ``save_scene_data`` collects ``depth_net_pts`` / ``depth_net_weights`` for this call only."""
@@ -241,8 +243,9 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
     dev = torch.device("cuda", torch.cuda.current_device())
     main = torch.cuda.current_stream()
     side = _side_stream(dev)
-    rgbs = np.empty((n, H, W, 3), np.float32)
-    disps = np.empty((n, H, W), np.float32)
+    to_host = (not sharded) or dst is None or dst == rank
+    rgbs = np.empty((n if to_host else 0, H, W, 3), np.float32)
+    disps = np.empty((n if to_host else 0, H, W), np.float32)
     pool = concurrent.futures.ThreadPoolExecutor(max_workers=4)
     all_pts, all_weights, mses = [], [], []
     if savedir is not None:
@@ -304,10 +307,13 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
                 with torch.cuda.stream(side):
                     side.wait_event(ready)
                     dist.all_gather_into_tensor(gathered[b].view(world * per, 4), tiles[b], group=group)
-                    host.copy_(gathered[b], non_blocking=True)
+                    if to_host:
+                        host.copy_(gathered[b], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(side)
                 reusable[b] = ev
+                if not to_host:
+                    continue
                 if shard == "views":
                     ring.busy[k] = pool.submit(unload, [r * world + q for q in range(world)], host, ev)
                 else:
@@ -322,7 +328,7 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
         trainer.save_scene_data = prev_ssd
 
     total_psnr = 0.0
-    if gt_imgs is not None and render_factor == 0:
+    if gt_imgs is not None and render_factor == 0 and to_host:
         lines = []
         for i in range(n):
             psnr = -10.0 * np.log10(np.mean(np.square(rgbs[i] - np.asarray(gt_imgs[i])[..., :3])))
