@@ -216,6 +216,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
   uint8_t* smem = tg_smem_ + ((128u - (smem_u32(tg_smem_) & 127u)) & 127u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  // Programmatic dependent launch: let the NEXT launch of the stream become resident and run its prologue (barrier init, TMEM
+  // allocation, problem decode) under this one's main loop; it blocks at griddepcontrol.wait below until this grid has completed.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const bool stamp = g.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   if (stamp) g.dbg[0] = gtimer();
   int pi = 0;
@@ -253,6 +256,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above touched only this CTA's own state; the operands (and C / dact) may be outputs of the previous launch
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = tmem_slot;
   constexpr uint32_t idesc = idesc_tf32(BM, BN);
 

@@ -210,7 +210,27 @@ static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
     if (splits > 1 && !q.beta && !q.c_zeroed)
       CUDA_TRY(cudaMemset2DAsync(q.C, static_cast<size_t>(q.ldc) * sizeof(float), 0, static_cast<size_t>(q.N) * sizeof(float), q.M, st));
   }
-  tg::tgemm_kernel<<<cta, tg::CTA_THREADS, tg::SMEM_BYTES, st>>>(g);
+  {
+    // programmatic stream serialization: this launch may start its prologue while the previous kernel of the stream drains
+    // (tgemm_kernel executes griddepcontrol.wait before it reads global memory); B200NERF_PDL=0 turns it off for A/B runs
+    static int pdl = -1;
+    if (pdl < 0) {
+      const char* e = getenv("B200NERF_PDL");
+      pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.gridDim = dim3(cta);
+    cfg.blockDim = dim3(tg::CTA_THREADS);
+    cfg.dynamicSmemBytes = tg::SMEM_BYTES;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, tg::tgemm_kernel, g));
+  }
   LAUNCH_CHECK();
   return 0;
 }
