@@ -139,6 +139,11 @@ int b200nerf_nerf_mlp_guarded_fwd(const void* wpack_fast, const void* wpack_spli
                                   const float* pts, int n_rays, int S, float guard_kappa, int* ws_guard, float* out_raw,
                                   void* stream);
 
+/* Tuning knob: cap the persistent grids of the MLP kernels (b200nerf_nerf_* / b200nerf_depthnet_fwd launched by the calling host
+ * thread) at n_sms CTAs so that work on another stream finds free SMs beside them; 0 removes the cap.  Returns the previous value.
+ * Results do not depend on it (tiles are distributed grid-stride). */
+int b200nerf_set_sm_limit(int n_sms);
+
 /* Precision dispatch over the three entry points above.  ws_guard (n_rays + 4 ints) is needed for PREC_FAST only. */
 int b200nerf_nerf_query(const b200nerf_nerf_model* nerf, const float* rays_o, const float* rays_d, const float* viewdirs,
                         const float* z, const float* pts, int n_rays, int S, int* ws_guard, float* out_raw, void* stream);

@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200nerf_composite_fwd": (I, [P, P, P, P, I, I, I, P, P, P, P, P, P, P]),
     "b200nerf_composite_tile_fwd": (I, [P, P, P, P, I, I, I, P, P, P, P, P, P]),
     "b200nerf_render_depthnet_tile": (I, [P, P, I, I, P, P, P, P, I, I, I, P, F, F, F, P, P, P, P, P, P, P, P, P]),
+    "b200nerf_set_sm_limit": (I, [I]),
     "b200nerf_nerf_query": (I, [P, P, P, P, P, P, I, I, P, P, P]),
     "b200nerf_render_depthnet": (I, [P, P, I, I, P, P, P, P, I, I, I, P, F, F, F, P, P, P, P, P, P, P, P, P, P]),
     "b200nerf_render_host_ws_bytes": (SZ, [I, I]),

@@ -35,6 +35,16 @@ extern "C" int b200nerf_version(void) { return B200NERF_VERSION; }
 extern "C" const char* b200nerf_last_error(void) { return g_err; }
 extern "C" unsigned long long b200nerf_launch_count(void) { return g_b200_launches.load(); }
 
+// Cap of the persistent MLP grids (0 = all SMs).  A persistent kernel that owns every SM serialises anything launched on another
+// stream behind it; the training step caps the frozen target render so that the latency-bound DepthNet / JVP launch chain of the
+// same step runs beside it (training.fused_render_and_backward).  Per host thread, like the current device.
+static thread_local int g_sm_limit = 0;
+extern "C" int b200nerf_set_sm_limit(int n_sms) {
+  const int prev = g_sm_limit;
+  g_sm_limit = n_sms > 0 ? n_sms : 0;
+  return prev;
+}
+
 static int sm_count() {
   static int n[B200_MAX_DEVICES] = {0};
   const int dev = b200_device();
@@ -304,6 +314,7 @@ static int launch_exact(exact::ExactParams& p, const XProgram& pg, const void* w
   const int tiles = (p.n_rows + exact::TILE_M - 1) / exact::TILE_M;
   int grid = ((tiles + exact::NCTA - 1) / exact::NCTA) * exact::NCTA;
   if (grid > grid_cap) grid = grid_cap;
+  if (g_sm_limit >= exact::NCTA && grid > g_sm_limit) grid = (g_sm_limit / exact::NCTA) * exact::NCTA;
   cfg.gridDim = dim3(grid);
   exact::TMap tm;
   const int rc = make_exact_tmap(wpack, pg.pack_bytes(), &tm);
@@ -1060,6 +1071,7 @@ static int launch_fast(const fast::FastParams& p, cudaStream_t st) {
   const int units = (tiles + 2 * NCTA - 1) / (2 * NCTA);
   int grid = units * NCTA;
   if (grid > grid_cap) grid = grid_cap;
+  if (g_sm_limit >= NCTA && grid > g_sm_limit) grid = (g_sm_limit / NCTA) * NCTA;
   cfg.gridDim = dim3(grid);
   fast::TMap tm_full;
   const int rc = make_piece_tmap(p.wpack, 16, &tm_full);   // one ring stage: 8 KB of this CTA's weight pieces

@@ -141,6 +141,19 @@ def nerf_params(module) -> List[torch.nn.Parameter]:
     return [sd[k] for k in NERF_KEYS]
 
 
+# Persistent-grid cap (in SMs) of the frozen target render while the DepthNet / JVP chain of the same step runs on a side stream;
+# 0 runs the step on one stream.  B200NERF_TARGET_SMS overrides (measurement).
+TARGET_SM_LIMIT = int(__import__("os").environ.get("B200NERF_TARGET_SMS", "128"))
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    s = _SIDE_STREAMS.get(dev)
+    if s is None:
+        s = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
 def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, target_s):
     """The DepthNet training render and both backward passes of ``Trainer.core_optimization_loop`` (Trainer.py:515-538) as six
     C calls and no autograd graph: hierarchical arg-max target on the frozen NeRFs (tensor-core kernels), DepthNet forward with
@@ -184,27 +197,46 @@ def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, tar
     with torch.no_grad(), torch.cuda.device(dev):
         viewdirs = ops.normalize_dirs(rays_d)
         kw = render_kwargs
-        c = trainer.sample_coarse_points(near=bounds[0], far=bounds[1], perturb=kw["perturb"], N_rays=n, N_samples=kw["N_samples"],
-                                         viewdirs=viewdirs, network_fn=kw["network_fn"], network_query_fn=kw["network_query_fn"],
-                                         rays_o=rays_o, rays_d=rays_d, raw_noise_std=kw["raw_noise_std"], white_bkgd=kw["white_bkgd"],
-                                         pytest=False, lindisp=kw.get("lindisp", False))
-        f = trainer.sample_fine_points(z_vals=c[5], weights=c[6], perturb=kw["perturb"], pytest=False, rays_d=rays_d, rays_o=rays_o,
-                                       rgb_map=c[0], disp_map=c[1], acc_map=c[2], network_fn=kw["network_fn"],
-                                       network_fine=kw["network_fine"], network_query_fn=kw["network_query_fn"], viewdirs=viewdirs,
-                                       raw_noise_std=kw["raw_noise_std"], white_bkgd=kw["white_bkgd"])
-        _, max_z, _, _ = ops.argmax_gather(f[11], f[7])
-        st = _stream()
-        ws = torch.empty(L.b200nerf_depthnet_train_ws_floats(n, len(hidden), _ints(hidden), len(cat), _ints(cat)), device=dev)
-        z = torch.empty(n, 1, device=dev)
+        hier = dict(near=bounds[0], far=bounds[1])
         p_arr = _ptrs(params)
         nf = (float(dn.near), float(dn.far))
-        _lib.check(L.b200nerf_depthnet_train_fwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), rays_o.data_ptr(),
-                                                 rays_d.data_ptr(), n, float(dn.sphere_radius), nf[0], nf[1], ws.data_ptr(), z.data_ptr(), st))
+        main = torch.cuda.current_stream()
+        # Two independent halves until the losses: the frozen hierarchical target (throughput-bound persistent kernels) and the
+        # DepthNet forward + NeRF point JVP (a ~25-launch latency-bound chain).  The chain runs on a side stream beside the target,
+        # whose persistent grids are capped so that it finds free SMs (TARGET_SM_LIMIT; 0 = one stream, no cap).
+        side = _side_stream(dev) if TARGET_SM_LIMIT > 0 else None
+        # every buffer is allocated on the main stream (the side stream only runs kernels between the two wait_stream calls), so the
+        # caching allocator never sees a cross-stream hand-off
+        ws = torch.empty(L.b200nerf_depthnet_train_ws_floats(n, len(hidden), _ints(hidden), len(cat), _ints(cat)), device=dev)
+        z = torch.empty(n, 1, device=dev)
         ws_n = torch.empty(L.b200nerf_nerf_point_ws_floats(n), device=dev)
         raw = torch.empty(n, 1, 4, device=dev)
         draw = torch.empty(n, 4, device=dev)
+        if side is not None:
+            side.wait_stream(main)
+        st = side.cuda_stream if side is not None else main.cuda_stream
+        _lib.check(L.b200nerf_depthnet_train_fwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), rays_o.data_ptr(),
+                                                 rays_d.data_ptr(), n, float(dn.sphere_radius), nf[0], nf[1], ws.data_ptr(),
+                                                 z.data_ptr(), st))
         _lib.check(L.b200nerf_nerf_point_jvp(_ptrs(nerf_params(net)), rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(),
                                              z.data_ptr(), n, ws_n.data_ptr(), raw.data_ptr(), draw.data_ptr(), st))
+        prev_limit = L.b200nerf_set_sm_limit(TARGET_SM_LIMIT) if side is not None else 0
+        try:
+            c = trainer.sample_coarse_points(near=hier["near"], far=hier["far"], perturb=kw["perturb"], N_rays=n, N_samples=kw["N_samples"],
+                                             viewdirs=viewdirs, network_fn=kw["network_fn"], network_query_fn=kw["network_query_fn"],
+                                             rays_o=rays_o, rays_d=rays_d, raw_noise_std=kw["raw_noise_std"], white_bkgd=kw["white_bkgd"],
+                                             pytest=False, lindisp=kw.get("lindisp", False))
+            f = trainer.sample_fine_points(z_vals=c[5], weights=c[6], perturb=kw["perturb"], pytest=False, rays_d=rays_d, rays_o=rays_o,
+                                           rgb_map=c[0], disp_map=c[1], acc_map=c[2], network_fn=kw["network_fn"],
+                                           network_fine=kw["network_fine"], network_query_fn=kw["network_query_fn"], viewdirs=viewdirs,
+                                           raw_noise_std=kw["raw_noise_std"], white_bkgd=kw["white_bkgd"])
+            _, max_z, _, _ = ops.argmax_gather(f[11], f[7])
+        finally:
+            if side is not None:
+                L.b200nerf_set_sm_limit(prev_limit)
+        if side is not None:
+            main.wait_stream(side)
+        st = main.cuda_stream
         losses = torch.empty(3, device=dev)
         dz = torch.empty(n, device=dev)
         ws2 = torch.empty(2, device=dev)
