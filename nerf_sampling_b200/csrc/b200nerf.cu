@@ -319,7 +319,42 @@ static int launch_exact(exact::ExactParams& p, const XProgram& pg, const void* w
   exact::TMap tm;
   const int rc = make_exact_tmap(wpack, pg.pack_bytes(), &tm);
   if (rc) return rc;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p, tm));
+  if (b200_sync_check()) {
+    const cudaError_t e0 = cudaDeviceSynchronize();
+    if (e0 != cudaSuccess) return fail("a kernel launched BEFORE mlp_exact_kernel (not by this library's checked launches) failed: %s", cudaGetErrorString(e0));
+    // debugging aid: every pointer the kernel dereferences must lie inside a live device allocation that covers the bytes it needs
+    struct Need { const char* name; const void* ptr; size_t bytes; };
+    const size_t n = static_cast<size_t>(p.n_rows);
+    const Need needs[] = {
+        {"wpack", wpack, pg.pack_bytes()}, {"aux", p.aux, exact::AUX_FLOATS * sizeof(float)},
+        {"rays_o", p.rays_o, INPUT == exact::IN_DEPTHNET ? n * 12 : 0}, {"rays_d", p.rays_d, INPUT == exact::IN_DEPTHNET ? n * 12 : 0},
+        {"out", p.out, INPUT == exact::IN_DEPTHNET ? n * 4 : 0}, {"scratch", p.scratch, INPUT == exact::IN_DEPTHNET ? static_cast<size_t>(grid) * 2 * 32 * exact::KC_STRIDE : 0}};
+    for (const Need& nd : needs) {
+      if (!nd.bytes) continue;
+      CUdeviceptr base = 0;
+      size_t size = 0;
+      typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+      static RangeFn range_fn = nullptr;
+      if (!range_fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+          range_fn = reinterpret_cast<RangeFn>(sym);
+      }
+      if (!range_fn) break;
+      const CUresult r = range_fn(&base, &size, reinterpret_cast<CUdeviceptr>(nd.ptr));
+      if (r != CUDA_SUCCESS) return fail("mlp_exact_kernel: %s = %p is not inside a device allocation (cuMemGetAddressRange %d)", nd.name, nd.ptr, static_cast<int>(r));
+      const size_t off = reinterpret_cast<CUdeviceptr>(nd.ptr) - base;
+      if (off + nd.bytes > size)
+        return fail("mlp_exact_kernel: %s needs %zu bytes at offset %zu of an allocation of %zu bytes", nd.name, nd.bytes, off, size);
+    }
+  }
+  {
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, tm);
+    if (e != cudaSuccess)
+      return fail("mlp_exact_kernel<%s> launch failed: %s (rows %d, grid %d, index list %d)", INPUT == exact::IN_DEPTHNET ? "DEPTHNET" : "NERF",
+                  cudaGetErrorString(e), p.n_rows, grid, p.row_index != nullptr);
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -457,7 +492,13 @@ extern "C" size_t b200nerf_depthnet_wpack_bytes(int n_hidden, int prec) {
   if (prec != B200NERF_PREC_SPLIT || n_hidden < 0 || n_hidden > DEPTHNET_MAX_HIDDEN) return 0;
   return depthnet_xprogram(nullptr, nullptr, n_hidden).pack_bytes();
 }
-extern "C" size_t b200nerf_depthnet_aux_floats(int n_hidden) { return static_cast<size_t>(n_hidden + 1) * 256 + 256 + 4; }
+// The kernel stages a fixed-size aux block (exact::AUX_FLOATS = 3080 floats: eleven bias rows + head + 4) into shared memory whatever
+// the depth, so the block is always that big (the tail is zero).  Round 1 sized it by n_hidden, and a 9-hidden-layer net read
+// 1 KB past its 2,820 floats -- an illegal address whenever the block happened to end a mapped segment.
+extern "C" size_t b200nerf_depthnet_aux_floats(int n_hidden) {
+  const size_t need = static_cast<size_t>(n_hidden + 1) * 256 + 256 + 4;
+  return need > static_cast<size_t>(exact::AUX_FLOATS) ? need : static_cast<size_t>(exact::AUX_FLOATS);
+}
 
 extern "C" int b200nerf_depthnet_pack(const float* h_w0, const float* h_b0, const float* const* h_hidden, int n_hidden,
                                       const float* h_head_w, const float* h_head_b, int prec, void* h_wpack, float* h_aux) {
@@ -466,6 +507,7 @@ extern "C" int b200nerf_depthnet_pack(const float* h_w0, const float* h_b0, cons
   if (depthnet_check("b200nerf_depthnet_pack", n_hidden, prec)) return 1;
   const int rc = pack_xprogram(depthnet_xprogram(h_w0, h_hidden, n_hidden), static_cast<uint8_t*>(h_wpack));
   if (rc) return rc;
+  memset(h_aux, 0, b200nerf_depthnet_aux_floats(n_hidden) * sizeof(float));
   memcpy(h_aux, h_b0, 256 * sizeof(float));
   for (int i = 0; i < n_hidden; ++i) memcpy(h_aux + 256 * (i + 1), h_hidden[2 * i + 1], 256 * sizeof(float));
   memcpy(h_aux + 256 * (n_hidden + 1), h_head_w, 256 * sizeof(float));

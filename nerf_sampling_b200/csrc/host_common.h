@@ -1,6 +1,7 @@
 // Host-side plumbing shared by the translation units of libb200nerf.so: error string, launch counter, macros.
 #pragma once
 #include <atomic>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 int b200_fail(const char* fmt, ...);
@@ -22,8 +23,19 @@ static inline int b200_device() {
     if (e__ != cudaSuccess)                                                                              \
       return b200_fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);     \
   } while (0)
-#define LAUNCH_CHECK()            \
-  do {                            \
-    ++g_b200_launches;            \
-    CUDA_TRY(cudaGetLastError()); \
+// B200NERF_SYNC_CHECK=1 (debugging): synchronise the device after every launch of the library so that an asynchronous fault is
+// reported at the launch that caused it (file:line in b200nerf_last_error) instead of at some later call.
+static inline bool b200_sync_check() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200NERF_SYNC_CHECK");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+#define LAUNCH_CHECK()                                        \
+  do {                                                        \
+    ++g_b200_launches;                                        \
+    CUDA_TRY(cudaGetLastError());                             \
+    if (b200_sync_check()) CUDA_TRY(cudaDeviceSynchronize()); \
   } while (0)

@@ -196,6 +196,10 @@ def test_depthnet_pack_roundtrip(lib):
     assert torch.equal(pk.aux[768:1024], pk.folded[3])  # head weights after 3 bias rows
     # only split precision exists: the predicted depth feeds the 2^9 octave of the NeRF encoding
     assert lib.b200nerf_depthnet_wpack_bytes(2, 0) == 0 and lib.b200nerf_nerf_wpack_bytes(0) == 0
+    # the kernel stages a fixed 3080-float aux block whatever the depth: shallower nets must not get a shorter one (round 1 did,
+    # and a 10-layer DepthNet read 1 KB past its block), and the tail is zero
+    assert all(lib.b200nerf_depthnet_aux_floats(n) >= 3080 for n in range(0, 11))
+    assert pk.aux.numel() >= 3080 and float(pk.aux[3 * 256 + 256 + 4:].abs().max()) == 0.0
 
 
 # --------------------------------------------------------------------------------------------- module shells
