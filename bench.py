@@ -138,6 +138,13 @@ def intrinsics():
     return np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
 
 
+def workload_config(world: int):
+    """The part of `config` that names the workload: identical on both arms (ours and --impl reference)."""
+    return {"workload": f"800x800 lego-shaped view per GPU, DepthNet + {S} uniform samples/ray, 8x256 skip@4 NeRF "
+                        "(BASELINE config #2; #3 for N>1: one view of the batch per rank, tiles all-gathered)",
+            "rays_per_step_per_gpu": H * W, "samples_per_ray": S, "weights": "random-init seed 42"}
+
+
 def build_models(device, prec):
     """Random-init weights, seed 42, in the reference's construction order (coarse NeRF, fine NeRF, DepthNet)."""
     from nerf_sampling_b200.depth_nets import DepthNet
@@ -242,10 +249,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "rays_per_sec", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"800x800 lego-shaped view per GPU, DepthNet + {S} uniform samples/ray, 8x256 skip@4 NeRF "
-                               "(BASELINE config #2), on the host CPU", "rays_per_step": n, "samples_per_ray": S,
-                   "note": "each step is one 32,768-ray chunk of the view (the reference's own chunk size, nerf_utils.py:88), "
-                           "contiguous rays from the image centre; rays/s does not depend on how many chunks are rendered"},
+        "config": dict(workload_config(args.gpus), precision="fp32 (the reference's own torch CPU path)",
+                       sample_rays_per_step=n,
+                       note="each step is a bounded sample of the workload: one 32,768-ray chunk of the view (the reference's own "
+                            "chunk size, nerf_utils.py:88), contiguous rays from the image centre; rays/s does not depend on how "
+                            "many chunks are rendered"),
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": cpu.kind,
                          "sample": f"{n} rays x {S} samples per step, {len(times)} steps"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -693,12 +701,10 @@ def main():
             "dtype": {PREC_FAST: "fp16 operands, fp32 accumulate (+ bf16 hi/lo split re-evaluation of the guard band)",
                       PREC_FP16: "fp16", PREC_SPLIT: "bf16x2-split (bf16 hi+lo operands, fp32 accumulate)"}[prec],
             "data": "synthetic",
-            "config": {"workload": f"800x800 lego-shaped view per GPU, DepthNet + {S} uniform samples/ray, 8x256 skip@4 NeRF "
-                                   "(BASELINE config #2; #3 for N>1: one view of the batch per rank, tiles all-gathered)",
-                       "rays_per_step_per_gpu": n_rays, "samples_per_ray": S, "precision": args.prec, "weights": "random-init seed 42",
-                       "l2": "256 MiB flush between iterations + per-step working set 840 MB > 126 MB L2",
-                       "parallelism": (f"one view per rank x{world}; rgb|disp tiles written by the composite kernel, all_gather on a side "
-                                       "stream under the next view (double-buffered)") if world > 1 else "single GPU"},
+            "config": dict(workload_config(world), precision=args.prec,
+                           l2="256 MiB flush between iterations + per-step working set 840 MB > 126 MB L2",
+                           parallelism=(f"one view per rank x{world}; rgb|disp tiles written by the composite kernel, all_gather on a "
+                                        "side stream under the next view (double-buffered)") if world > 1 else "single GPU"),
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": 2 * n_rays * 12, "d2h_bytes_per_step": d2h,
                     "api": e2e_api_name, "steps": n_e2e, "views_rotated": n_sets},
             "e2e_api": e2e_api,

@@ -313,6 +313,25 @@ def test_compare_nerf_mode_whole_path(lib, oracle_models, b200_models, tmp_path)
     assert not tr.save_scene_data
 
 
+def test_sm_limit_does_not_change_results(lib, b200_models):
+    """b200nerf_set_sm_limit caps the persistent MLP grids (the training step uses it to leave SMs to a side stream): tiles are
+    distributed grid-stride, so a capped render is bit-identical to the uncapped one, and the knob restores."""
+    from nerf_sampling_b200 import ops
+
+    _, b_fine, b_dn = b200_models
+    c2w = O.pose_spherical(10.0, -30.0, 4.0)[:3, :4]
+    ro, rd, vd = ops.get_rays(96, 96, O.intrinsics(96, 96), c2w, DEV)
+    want = ops.render_depthnet(b_dn.packed(), b_fine.packed(), ro, rd, vd, 32, "uniform", 0.1)
+    prev = lib.b200nerf_set_sm_limit(20)
+    try:
+        got = ops.render_depthnet(b_dn.packed(), b_fine.packed(), ro, rd, vd, 32, "uniform", 0.1)
+    finally:
+        assert lib.b200nerf_set_sm_limit(prev) == 20
+    for k in ("rgb", "disp", "z", "raw", "weights"):
+        assert torch.equal(want[k], got[k]), k
+    assert lib.b200nerf_set_sm_limit(0) == prev == 0
+
+
 # ------------------------------------------------------------------------------------------- stale packs (ADVICE r1, high)
 def test_inference_after_adam_step_uses_updated_weights(lib, oracle_models):
     """The fused Adam writes parameters through raw pointers; the packed inference image must follow (it used to be cached on
