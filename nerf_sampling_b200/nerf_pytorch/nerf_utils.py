@@ -252,15 +252,15 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
         os.makedirs(savedir, exist_ok=True)
 
     def unload(views, host, ev):
-        """worker: wait for the D2H, de-interleave the rgb|disp pixels into the result arrays, encode PNGs."""
+        """worker: wait for the D2H, copy the planar rgb / disp slabs into the result arrays, encode PNGs."""
         ev.synchronize()
-        px = host.numpy()
+        h_rgb, h_disp = _planar(host)
+        h_rgb, h_disp = h_rgb.numpy(), h_disp.numpy()
         for j, i in enumerate(views):
             if i >= n:
                 continue
-            t = px[j].reshape(H, W, 4)
-            rgbs[i] = t[..., :3]
-            disps[i] = t[..., 3]
+            rgbs[i] = h_rgb[j].reshape(H, W, 3)
+            disps[i] = h_disp[j].reshape(H, W)
             if savedir is not None:
                 _write_png(os.path.join(savedir, "{:03d}.png".format(i)), run_nerf_helpers.to8b(rgbs[i]))
 
@@ -275,7 +275,7 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
                 ready.record(main)
                 with torch.cuda.stream(side):
                     side.wait_event(ready)
-                    host[0].copy_(tile, non_blocking=True)
+                    _to_host_planar(host, tile.view(1, n_rays, 4))
                     ev = torch.cuda.Event()
                     ev.record(side)
                 tile.record_stream(side)
@@ -308,7 +308,7 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
                     side.wait_event(ready)
                     dist.all_gather_into_tensor(gathered[b].view(world * per, 4), tiles[b], group=group)
                     if to_host:
-                        host.copy_(gathered[b], non_blocking=True)
+                        _to_host_planar(host, gathered[b])
                     ev = torch.cuda.Event()
                     ev.record(side)
                 reusable[b] = ev
@@ -344,21 +344,33 @@ def render_path(render_poses, hwf, K, chunk, render_kwargs, step=0, wandb_log=Fa
     return rgbs, disps, total_psnr / max(n, 1)
 
 
+def _planar(host):
+    """The two planes of a pinned slot [V, per, 4 floats]: rgb [V, per, 3] followed by disp [V, per].  The device-side rgb|disp
+    pixels are de-interleaved by the copy itself (a strided device read on the copy stream), so the host only memcpy's."""
+    v, per, _ = host.shape
+    flat = host.view(-1)
+    return flat[: v * per * 3].view(v, per, 3), flat[v * per * 3:].view(v, per)
+
+
+def _to_host_planar(host, px):
+    """px [V, per, 4] on the device -> the slot's planes, asynchronously on the current stream."""
+    h_rgb, h_disp = _planar(host)
+    h_rgb.copy_(px[..., :3], non_blocking=True)
+    h_disp.copy_(px[..., 3], non_blocking=True)
+
+
 def _unload_ray_shards(host, ev, world, n_rays, H, W, view, rgbs, disps, savedir):
     """worker for shard="rays": stitch the ranks' ray slices (padded to equal length for the all-gather) into view ``view``."""
-    import numpy as np
-
     from .. import parallel
 
     ev.synchronize()
-    px = host.numpy()
-    full = np.empty((n_rays, 4), np.float32)
+    h_rgb, h_disp = _planar(host)
+    h_rgb, h_disp = h_rgb.numpy(), h_disp.numpy()
+    out_rgb, out_disp = rgbs[view].reshape(n_rays, 3), disps[view].reshape(n_rays)
     for q in range(world):
         a, b = parallel.shard_bounds(n_rays, world, q)
-        full[a:b] = px[q, : b - a]
-    full = full.reshape(H, W, 4)
-    rgbs[view] = full[..., :3]
-    disps[view] = full[..., 3]
+        out_rgb[a:b] = h_rgb[q, : b - a]
+        out_disp[a:b] = h_disp[q, : b - a]
     if savedir is not None:
         _write_png(os.path.join(savedir, "{:03d}.png".format(view)), run_nerf_helpers.to8b(rgbs[view]))
 

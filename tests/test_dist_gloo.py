@@ -96,3 +96,31 @@ def test_gradient_allreduce_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def test_ray_shard_stitching_ragged():
+    """render_path(shard="rays"): the ranks' ray slices travel padded to equal length (all_gather needs equal tiles); the unload
+    worker stitches them back by shard_bounds.  Pure host logic: checked here with a fabricated gathered buffer."""
+    import numpy as np
+
+    from nerf_sampling_b200.nerf_pytorch import nerf_utils
+
+    class Done:
+        def synchronize(self):
+            pass
+
+    H, W = 7, 9                      # 63 rays over 4 ranks: 16 + 16 + 16 + 15
+    n, world = H * W, 4
+    full = np.random.default_rng(0).random((n, 4), dtype=np.float32)
+    per = (n + world - 1) // world
+    host = torch.full((world, per, 4), -1.0)
+    h_rgb, h_disp = nerf_utils._planar(host)        # the slot's layout: rgb plane [world, per, 3] then disp plane [world, per]
+    for r in range(world):
+        a, b = shard_bounds(n, world, r)
+        h_rgb[r, : b - a] = torch.from_numpy(full[a:b, :3])
+        h_disp[r, : b - a] = torch.from_numpy(full[a:b, 3])
+    rgbs = np.zeros((2, H, W, 3), np.float32)
+    disps = np.zeros((2, H, W), np.float32)
+    nerf_utils._unload_ray_shards(host, Done(), world, n, H, W, 1, rgbs, disps, None)
+    assert np.array_equal(rgbs[1], full[:, :3].reshape(H, W, 3)) and np.array_equal(disps[1], full[:, 3].reshape(H, W))
+    assert not rgbs[0].any()
