@@ -124,3 +124,4 @@ def test_ray_shard_stitching_ragged():
     nerf_utils._unload_ray_shards(host, Done(), world, n, H, W, 1, rgbs, disps, None)
     assert np.array_equal(rgbs[1], full[:, :3].reshape(H, W, 3)) and np.array_equal(disps[1], full[:, 3].reshape(H, W))
     assert not rgbs[0].any()
+
