@@ -304,48 +304,47 @@ static int colsum(cudaStream_t st, const float* dY, int n, int M, int ldy, float
 
 // ------------------------------------------------------------------------------------------- encodings
 // gamma(x) of a C-vector: [x, sin(2^0 x), cos(2^0 x), ...] (run_nerf_helpers.py:15-63), C*(1+2F) wide
-__device__ __forceinline__ void embed_row(const float* x, int C, int F, float* out) {
-  for (int c = 0; c < C; ++c) out[c] = x[c];
-  for (int j = 0; j < F; ++j) {
-    const float f = static_cast<float>(1 << j);
-    for (int c = 0; c < C; ++c) {
-      float s, co;
-      sincosf(x[c] * f, &s, &co);
-      out[C + j * 2 * C + c] = s;
-      out[C + j * 2 * C + C + c] = co;
-    }
-  }
-}
-
 // E[n, 252] = [gamma(o) 63 | gamma(d) 63 | gamma([hit_near, hit_far]) 126]; sphere hits in the reference's op order
-// (nerf_pytorch/utils.py:159-217), NaN when the ray misses
+// (nerf_pytorch/utils.py:159-217), NaN when the ray misses.  Twelve threads per ray -- (vector o / d / hit_near / hit_far) x channel --
+// so that a thread runs 10 accurate sincosf instead of 120 in a row (the kernel is latency-, not throughput-bound: 4096 rays).
 __global__ void depthnet_encode_kernel(const float* __restrict__ ro, const float* __restrict__ rd, int n, float radius,
                                        float* __restrict__ E) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t / 12, part = (t % 12) / 3, c = t % 3;
   if (i >= n) return;
   float o[3], d[3];
-  for (int t = 0; t < 3; ++t) {
-    o[t] = ro[i * 3 + t];
-    d[t] = rd[i * 3 + t];
+  for (int k = 0; k < 3; ++k) {
+    o[k] = ro[i * 3 + k];
+    d[k] = rd[i * 3 + k];
   }
-  const float dot_do = __fadd_rn(__fadd_rn(__fmul_rn(d[0], o[0]), __fmul_rn(d[1], o[1])), __fmul_rn(d[2], o[2]));
-  const float b = __fmul_rn(2.f, dot_do);
-  const float on = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(o[0], o[0]), __fmul_rn(o[1], o[1])), __fmul_rn(o[2], o[2])));
-  const float cc = __fadd_rn(__fmul_rn(on, on), -__fmul_rn(radius, radius));
-  const float a = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
-  const float delta = __fadd_rn(__fmul_rn(b, b), -__fmul_rn(__fmul_rn(4.f, a), cc));
-  const float sq = __fsqrt_rn(delta);
-  const float two_a = __fmul_rn(2.f, a);
-  const float t0 = __fdiv_rn(__fadd_rn(-b, -sq), two_a), t1 = __fdiv_rn(__fadd_rn(-b, sq), two_a);
-  float hits[6];
-  for (int t = 0; t < 3; ++t) {
-    hits[t] = __fadd_rn(o[t], __fmul_rn(t0, d[t]));
-    hits[3 + t] = __fadd_rn(o[t], __fmul_rn(t1, d[t]));
+  float x;
+  if (part == 0) {
+    x = o[c];
+  } else if (part == 1) {
+    x = d[c];
+  } else {
+    const float dot_do = __fadd_rn(__fadd_rn(__fmul_rn(d[0], o[0]), __fmul_rn(d[1], o[1])), __fmul_rn(d[2], o[2]));
+    const float b = __fmul_rn(2.f, dot_do);
+    const float on = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(o[0], o[0]), __fmul_rn(o[1], o[1])), __fmul_rn(o[2], o[2])));
+    const float cc = __fadd_rn(__fmul_rn(on, on), -__fmul_rn(radius, radius));
+    const float a = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
+    const float delta = __fadd_rn(__fmul_rn(b, b), -__fmul_rn(__fmul_rn(4.f, a), cc));
+    const float sq = __fsqrt_rn(delta);
+    const float two_a = __fmul_rn(2.f, a);
+    const float tt = part == 2 ? __fdiv_rn(__fadd_rn(-b, -sq), two_a) : __fdiv_rn(__fadd_rn(-b, sq), two_a);
+    x = __fadd_rn(o[c], __fmul_rn(tt, d[c]));
   }
-  float* e = E + static_cast<size_t>(i) * 252;
-  embed_row(o, 3, 10, e);
-  embed_row(d, 3, 10, e + 63);
-  embed_row(hits, 6, 10, e + 126);
+  // gamma of a C-vector is [x (C), sin(2^0 x) (C), cos(2^0 x) (C), ...]: o and d are 3-vectors, the two hit points one 6-vector
+  const int C = part < 2 ? 3 : 6;
+  const int ch = part < 2 ? c : (part - 2) * 3 + c;
+  float* e = E + static_cast<size_t>(i) * 252 + (part == 0 ? 0 : (part == 1 ? 63 : 126));
+  e[ch] = x;
+  for (int j = 0; j < 10; ++j) {
+    float sn, cs;
+    sincosf(x * static_cast<float>(1 << j), &sn, &cs);
+    e[C + j * 2 * C + ch] = sn;
+    e[C + j * 2 * C + C + ch] = cs;
+  }
 }
 
 // z = near*(1-s) + far*s, s = sigmoid(t)   (depth_net.py:165-168)
@@ -869,7 +868,7 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
   const int n = n_rays;
   const DnWs w = dn_layout(ar, n);
   float* E = ws + w.E;
-  depthnet_encode_kernel<<<(n + 127) / 128, 128, 0, st>>>(rays_o, rays_d, n, radius, E);
+  depthnet_encode_kernel<<<(12 * n + 191) / 192, 192, 0, st>>>(rays_o, rays_d, n, radius, E);
   LAUNCH_CHECK();
   const int ed[3] = {63, 63, 126}, eo[3] = {0, 63, 126};
   if (tgemm_enabled() && n >= 32) {
@@ -1161,35 +1160,40 @@ extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_bra
 }
 
 // ------------------------------------------------------------------------------------------- NeRF at one sample per ray + d/dz
-// rows 0..n-1 = primal gamma(p), rows n..2n-1 = tangent d gamma(p) / dz, p = o + d z; view encoding [n, 27]
+// rows 0..n-1 = primal gamma(p), rows n..2n-1 = tangent d gamma(p) / dz, p = o + d z; view encoding [n, 27].  Six threads per ray:
+// three position channels (10 sincosf each) and three view-direction channels (4 each).
 __global__ void nerf_point_encode_kernel(const float* __restrict__ ro, const float* __restrict__ rd, const float* __restrict__ vd,
                                          const float* __restrict__ z, int n, float* __restrict__ enc, float* __restrict__ venc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = t / 6, c = t % 3;
   if (i >= n) return;
-  float x[3], d[3], v[3];
-  for (int t = 0; t < 3; ++t) {
-    d[t] = rd[i * 3 + t];
-    x[t] = __fadd_rn(ro[i * 3 + t], __fmul_rn(d[t], z[i]));
-    v[t] = vd[i * 3 + t];
-  }
-  float* p = enc + static_cast<size_t>(i) * 63;
-  float* tg = enc + static_cast<size_t>(n + i) * 63;
-  for (int c = 0; c < 3; ++c) {
-    p[c] = x[c];
-    tg[c] = d[c];
-  }
-  for (int j = 0; j < 10; ++j) {
-    const float f = static_cast<float>(1 << j);
-    for (int c = 0; c < 3; ++c) {
+  if (t % 6 < 3) {
+    const float d = rd[i * 3 + c];
+    const float x = __fadd_rn(ro[i * 3 + c], __fmul_rn(d, z[i]));
+    float* p = enc + static_cast<size_t>(i) * 63;
+    float* tg = enc + static_cast<size_t>(n + i) * 63;
+    p[c] = x;
+    tg[c] = d;
+    for (int j = 0; j < 10; ++j) {
+      const float f = static_cast<float>(1 << j);
       float s, co;
-      sincosf(x[c] * f, &s, &co);
+      sincosf(x * f, &s, &co);
       p[3 + j * 6 + c] = s;
       p[3 + j * 6 + 3 + c] = co;
-      tg[3 + j * 6 + c] = f * co * d[c];
-      tg[3 + j * 6 + 3 + c] = -f * s * d[c];
+      tg[3 + j * 6 + c] = f * co * d;
+      tg[3 + j * 6 + 3 + c] = -f * s * d;
+    }
+  } else {
+    const float v = vd[i * 3 + c];
+    float* e = venc + static_cast<size_t>(i) * 27;
+    e[c] = v;
+    for (int j = 0; j < 4; ++j) {
+      float s, co;
+      sincosf(v * static_cast<float>(1 << j), &s, &co);
+      e[3 + j * 6 + c] = s;
+      e[3 + j * 6 + 3 + c] = co;
     }
   }
-  embed_row(v, 3, 4, venc + static_cast<size_t>(i) * 27);
 }
 // primal rows: h = relu(y + b); tangent rows: t = (y_primal + b > 0) ? y_tangent : 0        (in place, Y is [2n, M])
 __global__ void relu_jvp_kernel(float* __restrict__ Y, const float* __restrict__ bias, int n, int M, int relu) {
@@ -1273,7 +1277,7 @@ extern "C" int b200nerf_nerf_point_jvp(const float* const* t, const float* rays_
   float* h2 = h1 + static_cast<size_t>(n2) * 256;
   float* rgb2 = h2 + static_cast<size_t>(n2) * 256;  // [2n, 3]
   float* al2 = rgb2 + static_cast<size_t>(n2) * 4;   // [2n]
-  nerf_point_encode_kernel<<<(n + 127) / 128, 128, 0, st>>>(rays_o, rays_d, viewdirs, z, n, enc, venc);
+  nerf_point_encode_kernel<<<(6 * n + 191) / 192, 192, 0, st>>>(rays_o, rays_d, viewdirs, z, n, enc, venc);
   LAUNCH_CHECK();
   auto act = [&](float* Y, const float* bias, int M, int relu) -> int {
     const size_t tot = static_cast<size_t>(n) * M;
