@@ -233,6 +233,18 @@ int b200nerf_depthnet_train_bwd(const float* const* params, int n_branch, const 
                                 int n_rays, float near_, float far_, float* ws, const float* dz, float* const* grads,
                                 void* stream);
 
+/* The same backward split at the losses (Trainer.py:525-538: both losses reach DepthNet through ONE scalar per ray, dz, and the
+ * backward is linear in it).  b200nerf_depthnet_train_jac runs BEFORE the losses exist: it zeroes `grads` and walks the sequential
+ * input-gradient chain with a unit upstream gradient, leaving J_j = d z / d(pre-activation of cat layer j) in `ws`.
+ * b200nerf_depthnet_train_bwd_jac then forms every gradient from dz and the J_j as independent products (one grouped launch) plus
+ * the weight-only branch chain.  Same results as b200nerf_depthnet_train_bwd up to rounding; where the split does not apply
+ * (CUDA-core GEMM path, literal branches, fewer than 32 rays) _jac does nothing and _bwd_jac IS b200nerf_depthnet_train_bwd. */
+int b200nerf_depthnet_train_jac(const float* const* params, int n_branch, const int* hidden, int n_cat, const int* cat_hidden,
+                                int n_rays, float near_, float far_, float* ws, float* const* grads, void* stream);
+int b200nerf_depthnet_train_bwd_jac(const float* const* params, int n_branch, const int* hidden, int n_cat, const int* cat_hidden,
+                                    int n_rays, float near_, float far_, float* ws, const float* dz, float* const* grads,
+                                    void* stream);
+
 /* The frozen NeRF at ONE sample per ray, p = o + d z (nerf_utils.py:693-715), in fp32, together with d raw / d z
  * (forward-mode derivative along the ray: what loss.backward() propagates from the colour into DepthNet's depth).
  * `params` = the 24 fp32 device tensors in the order of b200nerf_nerf_pack; ws: b200nerf_nerf_point_ws_floats() floats;
@@ -240,6 +252,15 @@ int b200nerf_depthnet_train_bwd(const float* const* params, int n_branch, const 
 size_t b200nerf_nerf_point_ws_floats(int n_rays);
 int b200nerf_nerf_point_jvp(const float* const* params, const float* rays_o, const float* rays_d, const float* viewdirs,
                             const float* z, int n_rays, float* ws, float* out_raw, float* out_draw_dz, void* stream);
+
+/* The same two outputs from the PACKED split-precision model (b200nerf_nerf_pack: bf16 hi + lo operands, three MMAs per block,
+ * fp32 accumulate -- the precision of B200NERF_PREC_SPLIT inference) in two launches of the fused tensor-core MLP kernel instead
+ * of ~13 grouped products: a primal pass that also records the ReLU masks, and a tangent pass t_k = mask_k * (W_k t_{k-1}).
+ * ws: b200nerf_nerf_point_jvp_packed_ws_bytes() bytes (the masks). */
+size_t b200nerf_nerf_point_jvp_packed_ws_bytes(int n_rays);
+int b200nerf_nerf_point_jvp_packed(const void* wpack, const float* aux, const float* rays_o, const float* rays_d,
+                                   const float* viewdirs, const float* z, int n_rays, void* ws, float* out_raw,
+                                   float* out_draw_dz, void* stream);
 
 /* torch.optim.Adam (no weight decay, no amsgrad) on one tensor; the gradient is multiplied by grad_scale first
  * (1/world_size after a sum all-reduce).  step counts from 1. */

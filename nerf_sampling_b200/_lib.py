@@ -60,8 +60,12 @@ SIGNATURES = {
     "b200nerf_depthnet_n_params": (I, [I, I]),
     "b200nerf_depthnet_train_fwd": (I, [P, I, P, I, P, P, P, I, F, F, F, P, P, P]),
     "b200nerf_depthnet_train_bwd": (I, [P, I, P, I, P, I, F, F, P, P, P, P]),
+    "b200nerf_depthnet_train_jac": (I, [P, I, P, I, P, I, F, F, P, P, P]),
+    "b200nerf_depthnet_train_bwd_jac": (I, [P, I, P, I, P, I, F, F, P, P, P, P]),
     "b200nerf_nerf_point_ws_floats": (SZ, [I]),
     "b200nerf_nerf_point_jvp": (I, [P, P, P, P, P, I, P, P, P, P]),
+    "b200nerf_nerf_point_jvp_packed_ws_bytes": (SZ, [I]),
+    "b200nerf_nerf_point_jvp_packed": (I, [P, P, P, P, P, P, I, P, P, P, P]),
     "b200nerf_train_loss": (I, [P, P, P, P, P, I, P, P, P, P]),
     "b200nerf_adam_step": (I, [P, P, P, P, SZ, F, F, F, F, I, F, P]),
     "b200nerf_adam_step_multi": (I, [P, I, F, F, F, F, I, F, P]),

@@ -352,7 +352,8 @@ static int launch_exact(exact::ExactParams& p, const XProgram& pg, const void* w
   {
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, tm);
     if (e != cudaSuccess)
-      return fail("mlp_exact_kernel<%s> launch failed: %s (rows %d, grid %d, index list %d)", INPUT == exact::IN_DEPTHNET ? "DEPTHNET" : "NERF",
+      return fail("mlp_exact_kernel<%s> launch failed: %s (rows %d, grid %d, index list %d)",
+                  INPUT == exact::IN_DEPTHNET ? "DEPTHNET" : (INPUT == exact::IN_NERF ? "NERF" : (INPUT == exact::IN_NERF_MASK ? "NERF+masks" : "NERF tangent")),
                   cudaGetErrorString(e), p.n_rows, grid, p.row_index != nullptr);
   }
   LAUNCH_CHECK();
@@ -1019,6 +1020,39 @@ static int nerf_exact_launch(const void* wpack, const float* aux, const float* r
   xp.rgb_w_off = NERF_WR;
   xp.rgb_b_off = NERF_BR;
   return launch_exact<exact::IN_NERF>(xp, nerf_xprogram(nullptr), wpack, st);
+}
+
+// raw and d raw / d z at ONE sample per ray on the split-precision kernel: a primal pass that also records the ReLU masks, then
+// the tangent pass t_k = mask_k * (W_k t_{k-1}) over the same packed weights (mlp_exact.cuh, IN_NERF_MASK / IN_NERF_TAN)
+extern "C" size_t b200nerf_nerf_point_jvp_packed_ws_bytes(int n_rays) {
+  return static_cast<size_t>(exact::MAX_STEPS) * static_cast<size_t>(n_rays > 0 ? n_rays : 0) * 4 * sizeof(unsigned long long);
+}
+extern "C" int b200nerf_nerf_point_jvp_packed(const void* wpack, const float* aux, const float* rays_o, const float* rays_d,
+                                              const float* viewdirs, const float* z, int n_rays, void* ws, float* out_raw,
+                                              float* out_draw_dz, void* stream) {
+  if (n_rays <= 0) return 0;
+  if (!wpack || !aux || !rays_o || !rays_d || !viewdirs || !z || !ws || !out_raw || !out_draw_dz)
+    return fail("b200nerf_nerf_point_jvp_packed: null argument");
+  exact::ExactParams xp;
+  memset(&xp, 0, sizeof(xp));
+  xp.aux = aux;
+  xp.n_rows = n_rays;
+  xp.S = 1;
+  xp.rays_o = rays_o;
+  xp.rays_d = rays_d;
+  xp.viewdirs = viewdirs;
+  xp.z = z;
+  xp.mask = static_cast<unsigned long long*>(ws);
+  xp.head_w_off = NERF_WA;
+  xp.head_b_off = NERF_BA;
+  xp.rgb_w_off = NERF_WR;
+  xp.rgb_b_off = NERF_BR;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const XProgram pg = nerf_xprogram(nullptr);
+  xp.out = out_raw;
+  if (launch_exact<exact::IN_NERF_MASK>(xp, pg, wpack, st)) return 1;
+  xp.out = out_draw_dz;
+  return launch_exact<exact::IN_NERF_TAN>(xp, pg, wpack, st);
 }
 
 extern "C" int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,

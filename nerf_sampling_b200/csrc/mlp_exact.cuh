@@ -41,8 +41,12 @@ constexpr int NCTA = 2;
 constexpr int MAX_STEPS = 12;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, PRO_WARP0 = 12, PRO_WARPS = 4;
 
-enum : int { IN_NERF = 0, IN_DEPTHNET = 1 };
-enum : uint8_t { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
+// IN_NERF_MASK / IN_NERF_TAN: the training render's forward-mode derivative d raw / d z at one sample per ray (nerf_utils.py:693-715
+// under Trainer.core_optimization_loop) as two passes over the SAME packed weights.  The primal pass is IN_NERF plus one 64-bit
+// word per (layer, row, 64 columns) of ReLU masks; the tangent pass feeds d gamma(o + d z) / dz through the layers without biases,
+// t_k = mask_k * (W_k t_{k-1}), and writes the heads applied to the tangents.
+enum : int { IN_NERF = 0, IN_DEPTHNET = 1, IN_NERF_MASK = 2, IN_NERF_TAN = 3 };
+enum : uint8_t { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_MASK = 3 };
 enum : uint8_t {
   EPI_STORE = 0,        // bias + activation -> next layer's operand (hi/lo planes)
   EPI_STORE_ALPHA = 1,  // as EPI_STORE (ReLU) + this thread's part of the sigma head (N = 1), fp32
@@ -83,6 +87,7 @@ struct ExactParams {
   const int* row_index;   // NeRF, optional: row i evaluates sample point row_index[i] and writes it in place
   const int* n_rows_dev;  // optional: actual row count on the device
   uint8_t* scratch;       // DepthNet: per-CTA staging image of the next tile's encoded input (2 planes x 64 KB)
+  unsigned long long* mask;   // IN_NERF_MASK writes / IN_NERF_TAN reads: [step][row][4] words, bit c = output column 64 g + c is > 0
   uint32_t head_w_off, head_b_off;   // sigma head (NeRF) / depth head (DepthNet): 256 weights + bias
   uint32_t rgb_w_off, rgb_b_off;     // rgb head [3,128] + bias
   float radius, near, far;
@@ -148,6 +153,36 @@ __device__ __forceinline__ void encode_store(const float (&x)[3], uint8_t* dst) 
   }
 }
 
+// d/dz of that encoding at x = o + d z: [d, f cos(f x) d, -f sin(f x) d, ...]
+template <int NF, int NCHUNK>
+__device__ __forceinline__ void encode_tangent_store(const float (&x)[3], const float (&d)[3], uint8_t* dst) {
+  constexpr int NCOL = 3 + 6 * NF;
+  float sn[NF][3], cs[NF][3];
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+    const float f = static_cast<float>(1 << j);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      float s_, c_;
+      sincosf(x[t] * f, &s_, &c_);
+      sn[j][t] = -f * s_ * d[t];   // tangent of the cos column
+      cs[j][t] = f * c_ * d[t];    // tangent of the sin column
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < NCHUNK; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int cc = ch * 8 + i;
+      if (cc < 3) v[i] = d[cc];
+      else if (cc < NCOL) v[i] = ((cc - 3) % 6) < 3 ? cs[(cc - 3) / 6][(cc - 3) % 6] : sn[(cc - 3) / 6][(cc - 3) % 6 - 3];
+      else v[i] = 0.f;
+    }
+    store_split8(dst + ch * KC_STRIDE, v);
+  }
+}
+
 // the same encoding written to a staging image whose lo plane sits `lo_off` bytes after the hi plane
 template <int NF, int NCHUNK>
 __device__ __forceinline__ void encode_store_img(const float (&x)[3], uint8_t* dst, int lo_off) {
@@ -188,9 +223,11 @@ __device__ __forceinline__ float act_apply(float x) {
 }
 
 // 64 accumulator columns of one row: + bias, activation, optional heads, optional hi/lo operand store
-template <int EPI, int ACT>
+// WM: collect the ReLU mask of the 64 columns into `mask`; ACT_MASK: no bias, column c passes iff bit c of `mask` is set
+template <int EPI, int ACT, bool WM = false>
 __device__ __forceinline__ void epi_cols64(const uint32_t (&va)[32], const uint32_t (&vb)[32], const float* bias, const float* hw,
-                                           const float* wr, uint8_t* dst, float& hsum, float& rs, float& gs, float& bs) {
+                                           const float* wr, uint8_t* dst, float& hsum, float& rs, float& gs, float& bs,
+                                           unsigned long long& mask) {
   constexpr bool STORE = EPI == EPI_STORE || EPI == EPI_STORE_ALPHA;
   constexpr bool HEAD1 = EPI == EPI_STORE_ALPHA || EPI == EPI_DEPTH_OUT;
 #pragma unroll
@@ -200,8 +237,20 @@ __device__ __forceinline__ void epi_cols64(const uint32_t (&va)[32], const uint3
       const int c = cc * 32 + j;
       const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
       float x[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      if (ACT == ACT_MASK) {
+        const uint32_t m8 = static_cast<uint32_t>(mask >> c) & 0xffu;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = act_apply<ACT>(__uint_as_float(cc == 0 ? va[j + i] : vb[j + i]) + x[i]);
+        for (int i = 0; i < 8; ++i) x[i] = (m8 >> i) & 1u ? __uint_as_float(cc == 0 ? va[j + i] : vb[j + i]) : 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = act_apply<ACT>(__uint_as_float(cc == 0 ? va[j + i] : vb[j + i]) + x[i]);
+      }
+      if (WM) {
+        uint32_t m8 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m8 |= (x[i] > 0.f ? 1u : 0u) << i;
+        mask |= static_cast<unsigned long long>(m8) << c;
+      }
       if (HEAD1) {
         const float4 w0 = *reinterpret_cast<const float4*>(hw + c), w1 = *reinterpret_cast<const float4*>(hw + c + 4);
         const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -259,6 +308,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
     mbar_init(&tail->tmem_free_b, EPI_WARPS * NCTA);
     mbar_init(&tail->ready_p, (INPUT == IN_DEPTHNET ? 1 : PRO_WARPS) * NCTA);
     mbar_init(&tail->ready_v, (INPUT == IN_DEPTHNET ? 1 : PRO_WARPS) * NCTA);
+    static_assert(INPUT == IN_NERF || INPUT == IN_DEPTHNET || INPUT == IN_NERF_MASK || INPUT == IN_NERF_TAN, "input mode");
     mbar_init(&tail->in_full[0], 1);
     mbar_init(&tail->in_full[1], 1);
     mbar_init(&tail->free_p, 1);
@@ -413,11 +463,15 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
       const int tile = (cluster_id + u * n_clusters) * NCTA + static_cast<int>(rank);
       const int lrow = tile * TILE_M + row;
       const bool valid = lrow < n_rows;
-      if (INPUT == IN_NERF) {
+      if (INPUT != IN_DEPTHNET) {
         const int grow = valid ? (p.row_index != nullptr ? __ldg(p.row_index + lrow) : lrow) : 0;
         const int ray = grow / p.S;
-        float x[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f};
+        float x[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
         if (valid) {
+          if (INPUT == IN_NERF_TAN) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) dir[t] = __ldg(p.rays_d + ray * 3 + t);
+          }
           if (p.pts != nullptr) {
 #pragma unroll
             for (int t = 0; t < 3; ++t) x[t] = __ldg(p.pts + static_cast<size_t>(grow) * 3 + t);
@@ -434,7 +488,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
           mbar_wait_lean(free_p_addr, (u - 1) & 1u);    // the previous tile's skip layer no longer reads gamma(pts)
           tc_fence_after();
         }
-        encode_store<10, 8>(x, act + ENC_KB * 2 * KC_STRIDE + row_off);
+        if (INPUT == IN_NERF_TAN) encode_tangent_store<10, 8>(x, dir, act + ENC_KB * 2 * KC_STRIDE + row_off);
+        else encode_store<10, 8>(x, act + ENC_KB * 2 * KC_STRIDE + row_off);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(rp_bar);
@@ -442,7 +497,13 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
           mbar_wait_lean(free_v_addr, (u - 1) & 1u);    // ... nor its view layer gamma(viewdir)
           tc_fence_after();
         }
-        encode_store<4, 4>(v, act + VIEW_KB * 2 * KC_STRIDE + row_off);
+        if (INPUT == IN_NERF_TAN) {   // the view direction does not depend on z: a zero block
+          const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) store_split8(act + VIEW_KB * 2 * KC_STRIDE + row_off + ch * KC_STRIDE, zero8);
+        } else {
+          encode_store<4, 4>(v, act + VIEW_KB * 2 * KC_STRIDE + row_off);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(rv_bar);
@@ -518,7 +579,8 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
       const int tile = (cluster_id + u * n_clusters) * NCTA + static_cast<int>(rank);
       const int lrow = tile * TILE_M + row;
       const bool valid = lrow < n_rows;
-      const int grow = (INPUT == IN_NERF && p.row_index != nullptr) ? (valid ? __ldg(p.row_index + lrow) : 0) : lrow;
+      const int grow = (INPUT != IN_DEPTHNET && p.row_index != nullptr) ? (valid ? __ldg(p.row_index + lrow) : 0) : lrow;
+      constexpr bool TAN = INPUT == IN_NERF_TAN, WM = INPUT == IN_NERF_MASK;
 #pragma unroll 1
       for (int s = 0; s < p.n_steps; ++s) {
         const XStep st = p.steps[s];
@@ -528,6 +590,9 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
           tc_fence_after();
           const int col0 = half * 128 + sub * 64;           // first accumulator / layer-output column of this thread
           const float* bias = saux + st.bias_off + col0;
+          unsigned long long mbits = 0ull;
+          const size_t midx = ((static_cast<size_t>(s) * p.n_rows + static_cast<size_t>(lrow)) << 2) + (col0 >> 6);
+          if (TAN && valid) mbits = __ldg(p.mask + midx);
           uint32_t va[32], vb[32];
           tmem_ld_32x32b_x32(t_lane + col0, va);
           tmem_ld_32x32b_x32(t_lane + col0 + 32, vb);
@@ -544,17 +609,22 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
           const float* wr = saux + p.rgb_w_off + col0;
           uint8_t* dst = act + (col0 >> 3) * KC_STRIDE + row_off;
           float hsum = 0.f, rs = 0.f, gs = 0.f, bs = 0.f;
-          if (st.epi == EPI_STORE) {
-            if (st.act == ACT_RELU) epi_cols64<EPI_STORE, ACT_RELU>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs);
-            else if (st.act == ACT_LEAKY) epi_cols64<EPI_STORE, ACT_LEAKY>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs);
-            else epi_cols64<EPI_STORE, ACT_NONE>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs);
+          if (TAN) {
+            if (st.epi == EPI_STORE) epi_cols64<EPI_STORE, ACT_MASK>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
+            else if (st.epi == EPI_STORE_ALPHA) epi_cols64<EPI_STORE_ALPHA, ACT_MASK>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
+            else epi_cols64<EPI_NERF_OUT, ACT_MASK>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
+          } else if (st.epi == EPI_STORE) {
+            if (st.act == ACT_RELU) epi_cols64<EPI_STORE, ACT_RELU, WM>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
+            else if (st.act == ACT_LEAKY) epi_cols64<EPI_STORE, ACT_LEAKY>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
+            else epi_cols64<EPI_STORE, ACT_NONE>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
           } else if (st.epi == EPI_STORE_ALPHA) {
-            epi_cols64<EPI_STORE_ALPHA, ACT_RELU>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs);
+            epi_cols64<EPI_STORE_ALPHA, ACT_RELU, WM>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
           } else if (st.epi == EPI_NERF_OUT) {
-            epi_cols64<EPI_NERF_OUT, ACT_RELU>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs);
+            epi_cols64<EPI_NERF_OUT, ACT_RELU, WM>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
           } else {
-            epi_cols64<EPI_DEPTH_OUT, ACT_LEAKY>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs);
+            epi_cols64<EPI_DEPTH_OUT, ACT_LEAKY>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
           }
+          if (WM && valid) p.mask[midx] = mbits;
           if (head1) tail->head_part[half * 2 + sub][row] = hsum;
           if (st.epi == EPI_NERF_OUT) {
             if (sub == 1) {
@@ -563,7 +633,12 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
               tail->rgb_part[2][row] = bs;
             }
             named_bar_sync(2 + q, 64);   // the two warps of this lane quarter
-            if (sub == 0 && valid) {
+            if (TAN) {
+              if (sub == 0 && valid)
+                reinterpret_cast<float4*>(p.out)[grow] =
+                    make_float4(rs + tail->rgb_part[0][row], gs + tail->rgb_part[1][row], bs + tail->rgb_part[2][row],
+                                tail->head_part[0][row] + tail->head_part[1][row] + tail->head_part[2][row] + tail->head_part[3][row]);
+            } else if (sub == 0 && valid) {
               float4 o4;
               o4.x = rs + tail->rgb_part[0][row] + saux[p.rgb_b_off];
               o4.y = gs + tail->rgb_part[1][row] + saux[p.rgb_b_off + 1];

@@ -42,7 +42,7 @@ constexpr int PLANE_B = (KC / 4) * LBO_B;      //  9,344 B
 constexpr int STAGE_BYTES = 2 * PLANE_A + 2 * PLANE_B;   // hi + lo of both operands: 55,808 B
 constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 128;
 constexpr uint32_t TMEM_COLS = 64;
-constexpr int MAX_SEG = 4, MAX_PROB = 9;
+constexpr int MAX_SEG = 4, MAX_PROB = 16;
 constexpr int QA = BM * (KC / 4) / THREADS;    // k-quads per thread and chunk: 4 of A ...
 constexpr int QB = BN * (KC / 4) / THREADS;    // ... 2 of B
 
@@ -60,6 +60,7 @@ struct Prob {
   const float* bias;
   float* colsum;        // db[m] += sum_k A(m,k) (A must be k-strided, i.e. sAm == 1); pre-zeroed by the caller
   const float* dact;    // epilogue *= (dact[m*ld_dact + n] > 0 ? 1 : slope)
+  const float* kscale;  // A_0(m,k) *= kscale[k] (segment 0 only): the per-ray factor of a weight gradient whose dY is dz[r] * J[r, :]
   int M, N, nseg, ldc, beta, act, ld_dact;
   float slope;
   int tiles_x, tiles_y, splits, k_per, cta_begin;   // splits > 1 only with nseg == 1; k_per a multiple of KC
@@ -69,7 +70,7 @@ struct Group {
   long long* dbg;   // diagnostics: CTA 0 writes %globaltimer stamps of its phases here (null in normal use)
   Prob prob[MAX_PROB];
 };
-static_assert(sizeof(Group) <= 4000, "kernel parameter space");
+static_assert(sizeof(Group) <= 32000, "kernel parameter space (32,764 bytes since CUDA 12.1)");
 
 // kind::tf32 instruction descriptor: D = f32, A = B = TF32 (format 2), both K-major
 __host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
@@ -190,6 +191,11 @@ struct OpLoader {
     p0 += KC * sk;
   }
 
+  // k-quad index (within the chunk) of this thread's quad i, for the mapping `m` the chunk was loaded with
+  __device__ __forceinline__ int kquad(int m, int i, int tid) const {
+    return m == RVEC ? (tid >> 5) : ((m == KVEC || m == KSCALAR) ? (tid & 7) : (tid / R + (THREADS / R) * i));
+  }
+
   // hi / lo split and 16-byte stores into the UMMA planes
   __device__ __forceinline__ void store(const float (&v)[Q][4], uint8_t* hi_plane, uint8_t* lo_plane) const {
 #pragma unroll
@@ -302,11 +308,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
   };
   int a_mode;   // the mapping of the chunk held in va (the segment may change under it)
   int a_off0, a_offstride, b_off0, b_offstride;
+  int a_k0 = 0, a_kend = 0;            // k range of the chunk held in va (kscale)
+  float ks[4] = {1.f, 1.f, 1.f, 1.f};  // RVEC: the chunk's four factors of this warp's k-quad, fetched with the operands
+  const float* const kscale = P.kscale;
   auto prefetch = [&]() {   // loads chunk (cs, ck) into registers and advances the walk
     a_mode = la.mode;
     a_off0 = la.off0; a_offstride = la.offstride; b_off0 = lb.off0; b_offstride = lb.offstride;
     la.load(va, ck, ce, tid);
     lb.load(vb, ck, ce, tid);
+    if (kscale) {
+      a_k0 = ck; a_kend = ce;
+      if (a_mode == RVEC) {
+        const int kb = ck + warp * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ks[j] = kb + j < ce ? __ldg(kscale + kb + j) : 0.f;
+      }
+    }
     ck += KC;
     if (ck >= ce && !split && cs + 1 < P.nseg) {
       ++cs;
@@ -330,6 +347,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
     uint8_t* b_hi = a_lo + PLANE_A;
     uint8_t* b_lo = b_hi + PLANE_B;
     if (c >= 2) mbar_wait(&mma_done[s], static_cast<uint32_t>((c >> 1) - 1) & 1u);   // the MMAs that read this stage have retired
+    if (kscale) {   // before the split and the column sums: dW = sum_r (dz_r J[r, :])^T x[r, :], db = sum_r dz_r J[r, :]
+      if (a_mode == RVEC) {
+#pragma unroll
+        for (int i = 0; i < QA; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) va[i][j] *= ks[j];
+      } else {
+#pragma unroll
+        for (int i = 0; i < QA; ++i) {
+          const int kb = a_k0 + la.kquad(a_mode, i, tid) * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) va[i][j] *= kb + j < a_kend ? __ldg(kscale + kb + j) : 0.f;
+        }
+      }
+    }
     {
       OpLoader<BM, QA, LBO_A> sa = la;
       sa.off0 = a_off0; sa.offstride = a_offstride;

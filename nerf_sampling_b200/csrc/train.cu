@@ -123,6 +123,7 @@ struct GemmProb {
   float* colsum = nullptr;       // += column sums of A^T, i.e. sum_k A(m,k) (bias gradient); target pre-zeroed
   const float* dact = nullptr;   // epilogue *= LeakyReLU'(dact)
   int ld_dact = 0;
+  const float* kscale = nullptr; // A(m,k) *= kscale[k]: the per-ray factor dz_r of a weight gradient built from a unit-upstream Jacobian
   bool c_zeroed = false;         // C is known to be zero: a split-K launch needs no memset
   void add(const float* A, long sAm, long sAk, const float* B, long sBk, long sBn, int K) {
     seg[nseg++] = GemmSeg{A, sAm, sAk, B, sBk, sBn, K};
@@ -186,7 +187,8 @@ static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
       S.vecB = a.sBk == 1 && (a.sBn & 3) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0;
     }
     if (q.colsum && q.seg[0].sAk == 1) return b200_fail("tgemm_group: colsum needs a k-strided A");
-    P.C = q.C; P.bias = q.bias; P.colsum = q.colsum; P.dact = q.dact;
+    P.C = q.C; P.bias = q.bias; P.colsum = q.colsum; P.dact = q.dact; P.kscale = q.kscale;
+    if (q.kscale && q.nseg != 1) return b200_fail("tgemm_group: kscale needs a single K segment");
     P.M = q.M; P.N = q.N; P.nseg = q.nseg; P.ldc = q.ldc; P.beta = q.beta; P.act = q.act; P.ld_dact = q.ld_dact; P.slope = q.slope;
     P.tiles_x = (q.N + tg::BN - 1) / tg::BN;
     P.tiles_y = (q.M + tg::BM - 1) / tg::BM;
@@ -380,7 +382,8 @@ __global__ void depth_head_fused_kernel(const float* __restrict__ a, int n, int 
   }
 }
 // Its backward in one pass over a_last: dt = dz (far - near) s (1 - s);  g[r, c] = dt w[c] LeakyReLU'(a_last[r, c]) (the gradient of
-// the last cat layer's pre-activation);  dw[c] += sum_r dt a_last[r, c];  db += sum_r dt  (dw / db pre-zeroed)
+// the last cat layer's pre-activation);  dw[c] += sum_r dt a_last[r, c];  db += sum_r dt  (dw / db pre-zeroed).  dz == nullptr: unit
+// upstream gradient (the Jacobian pass); g / dw / db == nullptr: that output is skipped.
 constexpr int HEAD_ROWS = 32;
 __global__ void __launch_bounds__(256) depth_head_bwd_fused_kernel(const float* __restrict__ dz, const float* __restrict__ s,
                                                                    const float* __restrict__ a, const float* __restrict__ w, int n, int cl,
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(256) depth_head_bwd_fused_kernel(const float* 
   const int r0 = blockIdx.x * HEAD_ROWS;
   if (threadIdx.x < HEAD_ROWS) {
     const int r = r0 + threadIdx.x;
-    dts[threadIdx.x] = r < n ? dz[r] * (far_ - near_) * s[r] * (1.0f - s[r]) : 0.f;
+    dts[threadIdx.x] = r < n ? (dz ? dz[r] : 1.0f) * (far_ - near_) * s[r] * (1.0f - s[r]) : 0.f;
   }
   __syncthreads();
   for (int c = threadIdx.x; c < cl; c += blockDim.x) {
@@ -401,12 +404,12 @@ __global__ void __launch_bounds__(256) depth_head_bwd_fused_kernel(const float* 
       const int r = r0 + q;
       if (r >= n) break;
       const float av = a[static_cast<size_t>(r) * cl + c];
-      g[static_cast<size_t>(r) * cl + c] = dts[q] * wc * (av > 0.f ? 1.0f : slope);
+      if (g) g[static_cast<size_t>(r) * cl + c] = dts[q] * wc * (av > 0.f ? 1.0f : slope);
       acc = fmaf(dts[q], av, acc);
     }
-    atomicAdd(dw + c, acc);
+    if (dw) atomicAdd(dw + c, acc);
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && db) {
     float t = 0.f;
     for (int q = 0; q < HEAD_ROWS; ++q) t += dts[q];
     atomicAdd(db, t);
@@ -756,6 +759,7 @@ struct DnWs {             // float offsets into the workspace
   std::vector<size_t> a;       // cat layer outputs (post activation)
   size_t g0, g1, g2;           // gradient scratch, [n, maxw] each
   size_t gx[6];                // per-branch ping/pong scratch of the grouped backward
+  std::vector<size_t> jac;     // J_j = d z / d(pre-activation of cat layer j) per ray (the split backward)
   size_t Aaug[3], Raug[3], G[3], gv[3], c_last[3];   // collapsed-branch chain matrices (weights only, no ray dimension)
 };
 static DnWs dn_layout(const DnArch& ar, size_t n) {
@@ -775,6 +779,7 @@ static DnWs dn_layout(const DnArch& ar, size_t n) {
   w.g1 = take(n * maxw);
   w.g2 = take(n * maxw);
   for (int i = 0; i < 6; ++i) w.gx[i] = take(n * maxw);
+  for (int j = 0; j < ar.nc; ++j) w.jac.push_back(take(n * ar.c[j]));
   for (int b = 0; b < 3; ++b) {
     w.Aaug[b] = take(static_cast<size_t>(ar.nb) * CH_MAXH * CH_LD);
     w.Raug[b] = take(static_cast<size_t>(ar.nb) * CH_MAXH * CH_LD);
@@ -963,6 +968,68 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
   return 0;
 }
 
+// Weight gradients are split-K sums and bias gradients column sums added atomically: the gradient tensors are zeroed first -- one
+// memset when the caller laid them out back to back (training.py does), else one each.
+static int zero_grads(const DnArch& ar, float* const* grads, cudaStream_t st) {
+  std::vector<size_t> numel;
+  const int ed[3] = {63, 63, 126};
+  const int hl = ar.h[ar.nb - 1], cl = ar.c[ar.nc - 1];
+  for (int b = 0; b < 3; ++b)
+    for (int i = 0; i < ar.nb; ++i) {
+      numel.push_back(static_cast<size_t>(ar.h[i]) * ((i == 0 ? ed[b] : ar.h[i - 1]) + ed[b]));
+      numel.push_back(ar.h[i]);
+    }
+  for (int j = 0; j < ar.nc; ++j) {
+    numel.push_back(static_cast<size_t>(ar.c[j]) * (j == 0 ? 3 * hl + 252 : ar.c[j - 1]));
+    numel.push_back(ar.c[j]);
+  }
+  numel.push_back(cl);   // the head: its gradients are atomic sums of the fused head kernel
+  numel.push_back(1);
+  const size_t n_body = numel.size();
+  bool flat = true;
+  size_t total = 0;
+  for (size_t k = 0; k < n_body; ++k) {
+    if (k + 1 < n_body && grads[k + 1] != grads[k] + numel[k]) flat = false;
+    total += numel[k];
+  }
+  if (flat) {
+    CUDA_TRY(cudaMemsetAsync(grads[0], 0, total * sizeof(float), st));
+  } else {
+    for (size_t k = 0; k < n_body; ++k) CUDA_TRY(cudaMemsetAsync(grads[k], 0, numel[k] * sizeof(float), st));
+  }
+  return 0;
+}
+// The collapsed branches' backward behind the ray reduction (G = D^T e, g = D^T 1 already in the workspace): the R recurrence over the
+// weights (writes dV_i, db_i, dU_0), then the 3 (L-1) small dU_i products in one launch.
+static int chain_backward(const DnArch& ar, const DnWs& w, float* ws, const float* const* params, float* const* grads, cudaStream_t st) {
+  const int ed[3] = {63, 63, 126};
+  const ChainParams cp = chain_params(ar, w, ws, params, grads);
+  if (chain_configure()) return 1;
+  chain_bwd_kernel<<<chain_ctas(cp), CH_THREADS, CH_SMEM_BYTES, st>>>(cp);
+  LAUNCH_CHECK();
+  if (ar.nb > 1) {
+    DuBatch batch;
+    memset(&batch, 0, sizeof(batch));
+    int np = 0, maxh = 0, maxpw = 0;
+    for (int b = 0; b < 3; ++b)
+      for (int i = 1; i < ar.nb; ++i) {
+        DuProb& d = batch.p[np++];
+        d.R = ws + w.Raug[b] + static_cast<size_t>(i) * CH_MAXH * CH_LD;
+        d.A = ws + w.Aaug[b] + static_cast<size_t>(i - 1) * CH_MAXH * CH_LD;
+        d.C = grads[pidx_branch(ar, b, i)];
+        d.h = ar.h[i];
+        d.pw = ar.h[i - 1];
+        d.K = ed[b] + 1;
+        d.ldw = ar.h[i - 1] + ed[b];
+        maxh = d.h > maxh ? d.h : maxh;
+        maxpw = d.pw > maxpw ? d.pw : maxpw;
+      }
+    chain_du_kernel<<<dim3((maxpw + GN - 1) / GN, (maxh + GM - 1) / GM, np), 256, 0, st>>>(batch);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_branch, const int* hidden, int n_cat,
                                            const int* cat_hidden, int n_rays, float near_, float far_, float* ws, const float* dz,
                                            float* const* grads, void* stream) {
@@ -989,35 +1056,7 @@ extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_bra
     if (lin_dgrad(st, n, 1, cl, dt, 1, params[ph], cl, 0, g, cl, 0)) return 1;
   }
   if (tensor_path) {
-    // tensor-core path.  Weight gradients are split-K sums and bias gradients column sums added atomically: zero the
-    // gradient tensors first -- one memset when the caller laid them out back to back (training.py does), else one each.
-    {
-      std::vector<size_t> numel;
-      const int ed[3] = {63, 63, 126};
-      for (int b = 0; b < 3; ++b)
-        for (int i = 0; i < ar.nb; ++i) {
-          numel.push_back(static_cast<size_t>(ar.h[i]) * ((i == 0 ? ed[b] : ar.h[i - 1]) + ed[b]));
-          numel.push_back(ar.h[i]);
-        }
-      for (int j = 0; j < ar.nc; ++j) {
-        numel.push_back(static_cast<size_t>(ar.c[j]) * (j == 0 ? 3 * hl + 252 : ar.c[j - 1]));
-        numel.push_back(ar.c[j]);
-      }
-      numel.push_back(cl);   // the head: its gradients are atomic sums of the fused head kernel below
-      numel.push_back(1);
-      const size_t n_body = numel.size();
-      bool flat = true;
-      size_t total = 0;
-      for (size_t k = 0; k < n_body; ++k) {
-        if (k + 1 < n_body && grads[k + 1] != grads[k] + numel[k]) flat = false;
-        total += numel[k];
-      }
-      if (flat) {
-        CUDA_TRY(cudaMemsetAsync(grads[0], 0, total * sizeof(float), st));
-      } else {
-        for (size_t k = 0; k < n_body; ++k) CUDA_TRY(cudaMemsetAsync(grads[k], 0, numel[k] * sizeof(float), st));
-      }
-    }
+    if (zero_grads(ar, grads, st)) return 1;
     // head backward + LeakyReLU' of the last cat layer, one pass: g = d(pre-activation of the last cat layer)
     depth_head_bwd_fused_kernel<<<(n + HEAD_ROWS - 1) / HEAD_ROWS, 256, 0, st>>>(dz, ws + w.s, ws + w.a[ar.nc - 1], params[ph], n, cl, near_,
                                                                               far_, 0.01f, g, grads[ph], grads[ph + 1]);
@@ -1059,30 +1098,7 @@ extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_bra
       for (int b = 0; b < 3; ++b)
         q[b] = prob_wgrad(n, hl, ed[b], cur[b], hl, E + eo[b], 252, ws + w.G[b], CH_LD, 0, ws + w.gv[b], true);
       if (tgemm_group(st, q, 3)) return 1;
-      const ChainParams cp = chain_params(ar, w, ws, params, grads);
-      if (chain_configure()) return 1;
-      chain_bwd_kernel<<<chain_ctas(cp), CH_THREADS, CH_SMEM_BYTES, st>>>(cp);
-      LAUNCH_CHECK();
-      if (ar.nb > 1) {
-        DuBatch batch;
-        memset(&batch, 0, sizeof(batch));
-        int np = 0, maxh = 0, maxpw = 0;
-        for (int b = 0; b < 3; ++b)
-          for (int i = 1; i < ar.nb; ++i) {
-            DuProb& d = batch.p[np++];
-            d.R = ws + w.Raug[b] + static_cast<size_t>(i) * CH_MAXH * CH_LD;
-            d.A = ws + w.Aaug[b] + static_cast<size_t>(i - 1) * CH_MAXH * CH_LD;
-            d.C = grads[pidx_branch(ar, b, i)];
-            d.h = ar.h[i];
-            d.pw = ar.h[i - 1];
-            d.K = ed[b] + 1;
-            d.ldw = ar.h[i - 1] + ed[b];
-            maxh = d.h > maxh ? d.h : maxh;
-            maxpw = d.pw > maxpw ? d.pw : maxpw;
-          }
-        chain_du_kernel<<<dim3((maxpw + GN - 1) / GN, (maxh + GM - 1) / GM, np), 256, 0, st>>>(batch);
-        LAUNCH_CHECK();
-      }
+      if (chain_backward(ar, w, ws, params, grads, st)) return 1;
       return 0;
     }
     for (int i = ar.nb - 1; i >= 0; --i) {
@@ -1157,6 +1173,84 @@ extern "C" int b200nerf_depthnet_train_bwd(const float* const* params, int n_bra
     }
   }
   return 0;
+}
+
+// ---- the same backward, split at the losses ----------------------------------------------------------------------------------
+// Both losses reach DepthNet through ONE scalar per ray (dz = dLoss/dz_r), and the backward is linear in it:
+//   dLoss/d(pre_j)[r, :] = dz_r J_j[r, :],   J_j = d z / d(pre-activation of cat layer j)   (dz-independent).
+// The layer-by-layer input-gradient chain -- the sequential part -- therefore runs with a unit upstream gradient BEFORE the losses
+// are known (b200nerf_depthnet_train_jac: beside the frozen target render, off the step's critical path), and what remains after
+// the losses are INDEPENDENT products,  dW_j = sum_r (dz_r J_j[r, :])^T x_{j-1}[r, :],  db_j = sum_r dz_r J_j[r, :],  one grouped
+// launch with dz applied to the k (ray) index of the A operand in the loader (tgemm `kscale`), then the weight-only branch chain.
+static bool split_backward_ok(const DnArch& ar, int n, const float* const* params) {
+  return tgemm_enabled() && n >= 32 && can_collapse(ar, n, params);
+}
+extern "C" int b200nerf_depthnet_train_jac(const float* const* params, int n_branch, const int* hidden, int n_cat, const int* cat_hidden,
+                                           int n_rays, float near_, float far_, float* ws, float* const* grads, void* stream) {
+  if (n_rays <= 0) return 0;
+  if (!params || !ws || !grads) return b200_fail("b200nerf_depthnet_train_jac: null argument");
+  DnArch ar;
+  if (dn_arch(n_branch, hidden, n_cat, cat_hidden, &ar)) return 1;
+  if (!split_backward_ok(ar, n_rays, params)) return 0;   // b200nerf_depthnet_train_bwd_jac then runs the one-pass backward
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = n_rays;
+  const DnWs w = dn_layout(ar, n);
+  const int cl = ar.c[ar.nc - 1], hl = ar.h[ar.nb - 1];
+  const int ph = pidx_head(ar);
+  if (zero_grads(ar, grads, st)) return 1;
+  CUDA_TRY(cudaMemsetAsync(ws + w.G[0], 0, (w.gv[2] + CH_MAXH - w.G[0]) * sizeof(float), st));
+  depth_head_bwd_fused_kernel<<<(n + HEAD_ROWS - 1) / HEAD_ROWS, 256, 0, st>>>(nullptr, ws + w.s, ws + w.a[ar.nc - 1], params[ph], n, cl, near_,
+                                                                            far_, 0.01f, ws + w.jac[ar.nc - 1], nullptr, nullptr);
+  LAUNCH_CHECK();
+  for (int j = ar.nc - 1; j >= 1; --j) {
+    const int pc = pidx_cat(ar, j);
+    GemmProb q = prob_dgrad(n, ar.c[j], ar.c[j - 1], ws + w.jac[j], ar.c[j], params[pc], ar.c[j - 1], 0, ws + w.jac[j - 1], ar.c[j - 1],
+                            ws + w.a[j - 1], ar.c[j - 1], 0.01f);
+    if (tgemm_group(st, &q, 1)) return 1;
+  }
+  const int pc0 = pidx_cat(ar, 0), ldw0 = 3 * hl + 252;
+  GemmProb q[3];
+  for (int b = 0; b < 3; ++b) q[b] = prob_dgrad(n, ar.c[0], hl, ws + w.jac[0], ar.c[0], params[pc0], ldw0, b * hl, ws + w.gx[2 * b], hl);
+  return tgemm_group(st, q, 3);
+}
+extern "C" int b200nerf_depthnet_train_bwd_jac(const float* const* params, int n_branch, const int* hidden, int n_cat,
+                                               const int* cat_hidden, int n_rays, float near_, float far_, float* ws, const float* dz,
+                                               float* const* grads, void* stream) {
+  if (n_rays <= 0) return 0;
+  if (!params || !ws || !dz || !grads) return b200_fail("b200nerf_depthnet_train_bwd_jac: null argument");
+  DnArch ar;
+  if (dn_arch(n_branch, hidden, n_cat, cat_hidden, &ar)) return 1;
+  if (!split_backward_ok(ar, n_rays, params))
+    return b200nerf_depthnet_train_bwd(params, n_branch, hidden, n_cat, cat_hidden, n_rays, near_, far_, ws, dz, grads, stream);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = n_rays;
+  const DnWs w = dn_layout(ar, n);
+  const float* E = ws + w.E;
+  const int cl = ar.c[ar.nc - 1], hl = ar.h[ar.nb - 1];
+  const int ph = pidx_head(ar);
+  const int ed[3] = {63, 63, 126}, eo[3] = {0, 63, 126};
+  depth_head_bwd_fused_kernel<<<(n + HEAD_ROWS - 1) / HEAD_ROWS, 256, 0, st>>>(dz, ws + w.s, ws + w.a[ar.nc - 1], params[ph], n, cl, near_,
+                                                                            far_, 0.01f, nullptr, grads[ph], grads[ph + 1]);
+  LAUNCH_CHECK();
+  std::vector<GemmProb> q;
+  for (int j = ar.nc - 1; j >= 1; --j) {
+    const int pc = pidx_cat(ar, j);
+    q.push_back(prob_wgrad(n, ar.c[j], ar.c[j - 1], ws + w.jac[j], ar.c[j], ws + w.a[j - 1], ar.c[j - 1], grads[pc], ar.c[j - 1], 0, grads[pc + 1], true));
+  }
+  const int pc0 = pidx_cat(ar, 0), ldw0 = 3 * hl + 252;
+  for (int b = 0; b < 3; ++b)
+    q.push_back(prob_wgrad(n, ar.c[0], hl, ws + w.jac[0], ar.c[0], ws + w.xb[b][ar.nb - 1], hl, grads[pc0], ldw0, b * hl,
+                           b == 0 ? grads[pc0 + 1] : nullptr, true));
+  q.push_back(prob_wgrad(n, ar.c[0], 252, ws + w.jac[0], ar.c[0], E, 252, grads[pc0], ldw0, 3 * hl, nullptr, true));
+  // the branches' one reduction over the rays: G_b = D_b^T e_b, g_b = D_b^T 1 with D_b = dz * (J_0 W_cat0[:, b]) (pre-zeroed by _jac)
+  for (int b = 0; b < 3; ++b)
+    q.push_back(prob_wgrad(n, hl, ed[b], ws + w.gx[2 * b], hl, E + eo[b], 252, ws + w.G[b], CH_LD, 0, ws + w.gv[b], true));
+  for (GemmProb& p : q) p.kscale = dz;
+  for (size_t i = 0; i < q.size(); i += b200::tg::MAX_PROB) {
+    const int cnt = static_cast<int>(q.size() - i < static_cast<size_t>(b200::tg::MAX_PROB) ? q.size() - i : b200::tg::MAX_PROB);
+    if (tgemm_group(st, q.data() + i, cnt)) return 1;
+  }
+  return chain_backward(ar, w, ws, params, grads, st);
 }
 
 // ------------------------------------------------------------------------------------------- NeRF at one sample per ray + d/dz

@@ -87,21 +87,42 @@ class DepthNetTrainFn(torch.autograd.Function):
         return (None, None, None, None, None, None) + tuple(grads)
 
 
+# raw and d raw / d z of the frozen NeRF at one sample per ray: "split" = two launches of the fused split-precision tensor-core MLP
+# kernel over the model's packed weights (primal + ReLU masks, then the tangent pass; the precision of PREC_SPLIT inference:
+# bf16 hi + lo operands, fp32 accumulate), "fp32" = ~13 grouped 3xTF32 products over the fp32 tensors (b200nerf_nerf_point_jvp).
+JVP_MODE = __import__("os").environ.get("B200NERF_TRAIN_JVP", "split")
+
+
+def nerf_point_jvp(packed, params, rays_o, rays_d, viewdirs, z_flat, raw, draw, stream):
+    """Fills raw [n,1,4] and draw [n,4]; ``packed`` (a packing.PackedNeRF with a split-precision stream) selects the packed route.
+    Returns the workspace tensor, which must stay alive until the launches have run."""
+    L = _lib.lib()
+    n, dev = z_flat.shape[0], z_flat.device
+    if packed is not None and packed.wpack is not None and JVP_MODE == "split":
+        ws = torch.empty(L.b200nerf_nerf_point_jvp_packed_ws_bytes(n), dtype=torch.uint8, device=dev)
+        _lib.check(L.b200nerf_nerf_point_jvp_packed(packed.wpack.data_ptr(), packed.aux.data_ptr(), rays_o.data_ptr(), rays_d.data_ptr(),
+                                                    viewdirs.data_ptr(), z_flat.data_ptr(), n, ws.data_ptr(), raw.data_ptr(),
+                                                    draw.data_ptr(), stream))
+        return ws
+    ws = torch.empty(L.b200nerf_nerf_point_ws_floats(n), device=dev)
+    _lib.check(L.b200nerf_nerf_point_jvp(_ptrs(list(params)), rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(),
+                                         z_flat.data_ptr(), n, ws.data_ptr(), raw.data_ptr(), draw.data_ptr(), stream))
+    return ws
+
+
 class NerfPointFn(torch.autograd.Function):
-    """raw [N,1,4] of the frozen NeRF at p = o + d z (one sample per ray, fp32), differentiable w.r.t. z."""
+    """raw [N,1,4] of the frozen NeRF at p = o + d z (one sample per ray), differentiable w.r.t. z.  ``packed``: the model's
+    packing.PackedNeRF (split-precision route, see JVP_MODE) or None (fp32 route over ``params``)."""
 
     @staticmethod
-    def forward(ctx, z, rays_o, rays_d, viewdirs, *params):
-        L = _lib.lib()
+    def forward(ctx, z, rays_o, rays_d, viewdirs, packed, *params):
         n = z.shape[0]
         dev = z.device
-        ws = torch.empty(L.b200nerf_nerf_point_ws_floats(n), device=dev)
         raw = torch.empty(n, 1, 4, device=dev)
         draw = torch.empty(n, 4, device=dev)
         zz = z.detach().reshape(-1).contiguous().float()
         with torch.cuda.device(dev):
-            _lib.check(L.b200nerf_nerf_point_jvp(_ptrs(list(params)), rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(),
-                                                 zz.data_ptr(), n, ws.data_ptr(), raw.data_ptr(), draw.data_ptr(), _stream()))
+            nerf_point_jvp(packed, params, rays_o, rays_d, viewdirs, zz, raw, draw, _stream())
         ctx.save_for_backward(draw)
         ctx.zshape = z.shape
         return raw
@@ -110,7 +131,7 @@ class NerfPointFn(torch.autograd.Function):
     def backward(ctx, g_raw):
         (draw,) = ctx.saved_tensors
         gz = (g_raw.reshape(-1, 4) * draw).sum(-1).reshape(ctx.zshape)  # chain rule over the four outputs
-        return (gz, None, None, None) + (None,) * 24
+        return (gz, None, None, None, None) + (None,) * 24
 
 
 class CompositeSingleFn(torch.autograd.Function):
@@ -144,6 +165,12 @@ def nerf_params(module) -> List[torch.nn.Parameter]:
 # Persistent-grid cap (in SMs) of the frozen target render while the DepthNet / JVP chain of the same step runs on a side stream;
 # 0 runs the step on one stream.  B200NERF_TARGET_SMS overrides (measurement).
 TARGET_SM_LIMIT = int(__import__("os").environ.get("B200NERF_TARGET_SMS", "128"))
+# The backward split at the losses (b200nerf_depthnet_train_jac / _bwd_jac): the sequential input-gradient chain moves in front of
+# the losses, beside the target render.  That pays when the launches are throughput-bound (measured: 4096 rays 1.683 -> 1.644 ms)
+# and costs when they are latency-bound (512 rays 0.867 -> 0.881 ms), hence "auto" = from SPLIT_BACKWARD_MIN_RAYS rays per
+# process up; B200NERF_SPLIT_BACKWARD=0 / 1 forces the one-pass / the split form.
+SPLIT_BACKWARD = __import__("os").environ.get("B200NERF_SPLIT_BACKWARD", "auto")
+SPLIT_BACKWARD_MIN_RAYS = 2048
 _SIDE_STREAMS = {}
 
 
@@ -209,7 +236,8 @@ def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, tar
         # caching allocator never sees a cross-stream hand-off
         ws = torch.empty(L.b200nerf_depthnet_train_ws_floats(n, len(hidden), _ints(hidden), len(cat), _ints(cat)), device=dev)
         z = torch.empty(n, 1, device=dev)
-        ws_n = torch.empty(L.b200nerf_nerf_point_ws_floats(n), device=dev)
+        net_packed = net.packed() if hasattr(net, "packed") else None   # before the fork: a repack allocates and copies on the main stream
+        net_params = nerf_params(net)
         raw = torch.empty(n, 1, 4, device=dev)
         draw = torch.empty(n, 4, device=dev)
         if side is not None:
@@ -218,8 +246,13 @@ def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, tar
         _lib.check(L.b200nerf_depthnet_train_fwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), rays_o.data_ptr(),
                                                  rays_d.data_ptr(), n, float(dn.sphere_radius), nf[0], nf[1], ws.data_ptr(),
                                                  z.data_ptr(), st))
-        _lib.check(L.b200nerf_nerf_point_jvp(_ptrs(nerf_params(net)), rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(),
-                                             z.data_ptr(), n, ws_n.data_ptr(), raw.data_ptr(), draw.data_ptr(), st))
+        ws_n = nerf_point_jvp(net_packed, net_params, rays_o, rays_d, viewdirs, z.reshape(-1), raw, draw, st)   # noqa: F841 (kept alive)
+        g_arr = _ptrs(cache["grads"])
+        split_bwd = SPLIT_BACKWARD == "1" or (SPLIT_BACKWARD == "auto" and n >= SPLIT_BACKWARD_MIN_RAYS)
+        if split_bwd:
+            # the backward's sequential half (input-gradient chain with a unit upstream gradient) does not need the losses
+            _lib.check(L.b200nerf_depthnet_train_jac(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), n, nf[0], nf[1],
+                                                     ws.data_ptr(), g_arr, st))
         prev_limit = L.b200nerf_set_sm_limit(TARGET_SM_LIMIT) if side is not None else 0
         try:
             c = trainer.sample_coarse_points(near=hier["near"], far=hier["far"], perturb=kw["perturb"], N_rays=n, N_samples=kw["N_samples"],
@@ -242,8 +275,8 @@ def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, tar
         ws2 = torch.empty(2, device=dev)
         _lib.check(L.b200nerf_train_loss(raw.data_ptr(), draw.data_ptr(), z.data_ptr(), max_z.data_ptr(), target.data_ptr(), n,
                                          ws2.data_ptr(), losses.data_ptr(), dz.data_ptr(), st))
-        _lib.check(L.b200nerf_depthnet_train_bwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), n, nf[0], nf[1], ws.data_ptr(),
-                                                 dz.data_ptr(), _ptrs(cache["grads"]), st))
+        bwd = L.b200nerf_depthnet_train_bwd_jac if split_bwd else L.b200nerf_depthnet_train_bwd
+        _lib.check(bwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), n, nf[0], nf[1], ws.data_ptr(), dz.data_ptr(), g_arr, st))
     for p, g in zip(params, cache["grads"]):
         if p.grad is not g:
             p.grad = g

@@ -253,6 +253,47 @@ def test_fused_training_step_equals_autograd_route(lib, oracle_models):
         p.grad = None
 
 
+@pytest.mark.parametrize("n", [4096, 1000, 77])
+def test_split_backward_equals_one_pass_backward(lib, oracle_models, n):
+    """b200nerf_depthnet_train_jac + _bwd_jac (unit-upstream input-gradient chain before the losses, every weight gradient as an
+    independent dz-scaled product after them) against b200nerf_depthnet_train_bwd on the same activations and a random dz:
+    all 82 tensors, ragged ray counts (tail K chunks of the dz-scaled reduction)."""
+    import ctypes as C
+
+    from nerf_sampling_b200 import _lib, training
+    from nerf_sampling_b200.packing import PREC_FAST
+
+    models = _models(oracle_models, PREC_FAST)
+    dn = models[2]
+    params = training.depthnet_params(dn)
+    hidden, cat = training.depthnet_arch(dn)
+    L = _lib.lib()
+    packed, *_ = O.prepare_rays(800, 800, O.intrinsics(800, 800), c2w=O.pose_spherical(50.0, -30.0, 4.0)[:3, :4])
+    sel = torch.randperm(640000, generator=torch.Generator().manual_seed(n))[:n]
+    ro, rd = packed[sel, 0:3].contiguous().to(DEV), packed[sel, 3:6].contiguous().to(DEV)
+    ints = lambda v: (C.c_int * len(v))(*v)
+    ptrs = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    ws = torch.empty(L.b200nerf_depthnet_train_ws_floats(n, len(hidden), ints(hidden), len(cat), ints(cat)), device=DEV)
+    z = torch.empty(n, 1, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.b200nerf_depthnet_train_fwd(ptrs(params), len(hidden), ints(hidden), len(cat), ints(cat), ro.data_ptr(), rd.data_ptr(), n,
+                                             float(dn.sphere_radius), float(dn.near), float(dn.far), ws.data_ptr(), z.data_ptr(), st))
+    dz = (torch.randn(n, generator=torch.Generator().manual_seed(7)) / n).to(DEV)
+    g_one = [torch.full_like(p, 3.0) for p in params]     # "written, not accumulated": stale contents must not leak
+    g_two = [torch.full_like(p, -5.0) for p in params]
+    args = (len(hidden), ints(hidden), len(cat), ints(cat), n, float(dn.near), float(dn.far), ws.data_ptr())
+    _lib.check(L.b200nerf_depthnet_train_bwd(ptrs(params), *args, dz.data_ptr(), ptrs(g_one), st))
+    _lib.check(L.b200nerf_depthnet_train_jac(ptrs(params), *args, ptrs(g_two), st))
+    _lib.check(L.b200nerf_depthnet_train_bwd_jac(ptrs(params), *args, dz.data_ptr(), ptrs(g_two), st))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for a, b in zip(g_one, g_two):
+        assert bool(torch.isfinite(b).all())
+        worst = max(worst, float((a - b).abs().max()) / (float(a.abs().max()) + 1e-20))
+    print(f"split backward vs one-pass backward, {n} rays: worst tensor rel max-abs difference {worst:.2e}")
+    assert worst <= 2e-5      # both are 3xTF32 chains (2^-20 per link); they round differently, not less accurately
+
+
 # ------------------------------------------------------------------------------------------- render.py flags and the -e sweep
 @pytest.mark.parametrize("mode,S,dist", [("uniform", 2, 0.3), ("uniform", 128, 1.0), ("gaussian", 32, 0.3), ("gaussian", 64, 0.5),
                                          ("gaussian", 2, 1.0), ("uniform", 32, 0.5), ("gaussian", 128, 0.1)])
