@@ -238,12 +238,14 @@ int b200nerf_depthnet_train_bwd(const float* const* params, int n_branch, const 
  * input-gradient chain with a unit upstream gradient, leaving J_j = d z / d(pre-activation of cat layer j) in `ws`.
  * b200nerf_depthnet_train_bwd_jac then forms every gradient from dz and the J_j as independent products (one grouped launch) plus
  * the weight-only branch chain.  Same results as b200nerf_depthnet_train_bwd up to rounding; where the split does not apply
- * (CUDA-core GEMM path, literal branches, fewer than 32 rays) _jac does nothing and _bwd_jac IS b200nerf_depthnet_train_bwd. */
+ * (CUDA-core GEMM path, literal branches, fewer than 32 rays) _jac does nothing and _bwd_jac IS b200nerf_depthnet_train_bwd.
+ * stream_aux (optional, another stream of the same device): the weight-only branch chain runs there beside the cat layers' weight
+ * gradients; `stream` waits for it before the call's work is complete (event fork / join, capturable in a CUDA graph). */
 int b200nerf_depthnet_train_jac(const float* const* params, int n_branch, const int* hidden, int n_cat, const int* cat_hidden,
                                 int n_rays, float near_, float far_, float* ws, float* const* grads, void* stream);
 int b200nerf_depthnet_train_bwd_jac(const float* const* params, int n_branch, const int* hidden, int n_cat, const int* cat_hidden,
                                     int n_rays, float near_, float far_, float* ws, const float* dz, float* const* grads,
-                                    void* stream);
+                                    void* stream, void* stream_aux);
 
 /* The frozen NeRF at ONE sample per ray, p = o + d z (nerf_utils.py:693-715), in fp32, together with d raw / d z
  * (forward-mode derivative along the ray: what loss.backward() propagates from the colour into DepthNet's depth).

@@ -61,7 +61,7 @@ SIGNATURES = {
     "b200nerf_depthnet_train_fwd": (I, [P, I, P, I, P, P, P, I, F, F, F, P, P, P]),
     "b200nerf_depthnet_train_bwd": (I, [P, I, P, I, P, I, F, F, P, P, P, P]),
     "b200nerf_depthnet_train_jac": (I, [P, I, P, I, P, I, F, F, P, P, P]),
-    "b200nerf_depthnet_train_bwd_jac": (I, [P, I, P, I, P, I, F, F, P, P, P, P]),
+    "b200nerf_depthnet_train_bwd_jac": (I, [P, I, P, I, P, I, F, F, P, P, P, P, P]),
     "b200nerf_nerf_point_ws_floats": (SZ, [I]),
     "b200nerf_nerf_point_jvp": (I, [P, P, P, P, P, I, P, P, P, P]),
     "b200nerf_nerf_point_jvp_packed_ws_bytes": (SZ, [I]),

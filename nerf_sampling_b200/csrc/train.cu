@@ -1213,26 +1213,60 @@ extern "C" int b200nerf_depthnet_train_jac(const float* const* params, int n_bra
   for (int b = 0; b < 3; ++b) q[b] = prob_dgrad(n, ar.c[0], hl, ws + w.jac[0], ar.c[0], params[pc0], ldw0, b * hl, ws + w.gx[2 * b], hl);
   return tgemm_group(st, q, 3);
 }
+// fork / join events of the split backward's second stream, one pair per device and host thread
+static int fork_events(cudaEvent_t* fork, cudaEvent_t* join) {
+  static thread_local cudaEvent_t ev[B200_MAX_DEVICES][2] = {};
+  const int dev = b200_device();
+  if (dev < 0) return b200_fail("split backward: no usable CUDA device");
+  for (int i = 0; i < 2; ++i)
+    if (!ev[dev][i]) CUDA_TRY(cudaEventCreateWithFlags(&ev[dev][i], cudaEventDisableTiming));
+  *fork = ev[dev][0];
+  *join = ev[dev][1];
+  return 0;
+}
 extern "C" int b200nerf_depthnet_train_bwd_jac(const float* const* params, int n_branch, const int* hidden, int n_cat,
                                                const int* cat_hidden, int n_rays, float near_, float far_, float* ws, const float* dz,
-                                               float* const* grads, void* stream) {
+                                               float* const* grads, void* stream, void* stream_aux) {
   if (n_rays <= 0) return 0;
   if (!params || !ws || !dz || !grads) return b200_fail("b200nerf_depthnet_train_bwd_jac: null argument");
   DnArch ar;
   if (dn_arch(n_branch, hidden, n_cat, cat_hidden, &ar)) return 1;
   if (!split_backward_ok(ar, n_rays, params))
     return b200nerf_depthnet_train_bwd(params, n_branch, hidden, n_cat, cat_hidden, n_rays, near_, far_, ws, dz, grads, stream);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStream_t st = static_cast<cudaStream_t>(stream), sa = static_cast<cudaStream_t>(stream_aux);
+  const bool fork = sa != nullptr && sa != st;
   const int n = n_rays;
   const DnWs w = dn_layout(ar, n);
   const float* E = ws + w.E;
   const int cl = ar.c[ar.nc - 1], hl = ar.h[ar.nb - 1];
   const int ph = pidx_head(ar);
   const int ed[3] = {63, 63, 126}, eo[3] = {0, 63, 126};
+  auto launch_all = [&](std::vector<GemmProb>& q) -> int {
+    for (GemmProb& p : q) p.kscale = dz;
+    for (size_t i = 0; i < q.size(); i += b200::tg::MAX_PROB) {
+      const int cnt = static_cast<int>(q.size() - i < static_cast<size_t>(b200::tg::MAX_PROB) ? q.size() - i : b200::tg::MAX_PROB);
+      if (tgemm_group(st, q.data() + i, cnt)) return 1;
+    }
+    return 0;
+  };
+  // the branches' one reduction over the rays: G_b = D_b^T e_b, g_b = D_b^T 1 with D_b = dz * (J_0 W_cat0[:, b]) (pre-zeroed by _jac)
+  std::vector<GemmProb> qg, q;
+  for (int b = 0; b < 3; ++b)
+    qg.push_back(prob_wgrad(n, hl, ed[b], ws + w.gx[2 * b], hl, E + eo[b], 252, ws + w.G[b], CH_LD, 0, ws + w.gv[b], true));
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (fork) {
+    // The weight-only branch chain (chain_bwd + chain_du: ~100 us on 64 SMs, whatever the batch) needs only G: it runs on the second
+    // stream beside the cat layers' weight gradients instead of after them.
+    if (fork_events(&ev_fork, &ev_join)) return 1;
+    if (launch_all(qg)) return 1;
+    CUDA_TRY(cudaEventRecord(ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(sa, ev_fork, 0));
+    if (chain_backward(ar, w, ws, params, grads, sa)) return 1;
+    CUDA_TRY(cudaEventRecord(ev_join, sa));
+  }
   depth_head_bwd_fused_kernel<<<(n + HEAD_ROWS - 1) / HEAD_ROWS, 256, 0, st>>>(dz, ws + w.s, ws + w.a[ar.nc - 1], params[ph], n, cl, near_,
                                                                             far_, 0.01f, nullptr, grads[ph], grads[ph + 1]);
   LAUNCH_CHECK();
-  std::vector<GemmProb> q;
   for (int j = ar.nc - 1; j >= 1; --j) {
     const int pc = pidx_cat(ar, j);
     q.push_back(prob_wgrad(n, ar.c[j], ar.c[j - 1], ws + w.jac[j], ar.c[j], ws + w.a[j - 1], ar.c[j - 1], grads[pc], ar.c[j - 1], 0, grads[pc + 1], true));
@@ -1242,13 +1276,11 @@ extern "C" int b200nerf_depthnet_train_bwd_jac(const float* const* params, int n
     q.push_back(prob_wgrad(n, ar.c[0], hl, ws + w.jac[0], ar.c[0], ws + w.xb[b][ar.nb - 1], hl, grads[pc0], ldw0, b * hl,
                            b == 0 ? grads[pc0 + 1] : nullptr, true));
   q.push_back(prob_wgrad(n, ar.c[0], 252, ws + w.jac[0], ar.c[0], E, 252, grads[pc0], ldw0, 3 * hl, nullptr, true));
-  // the branches' one reduction over the rays: G_b = D_b^T e_b, g_b = D_b^T 1 with D_b = dz * (J_0 W_cat0[:, b]) (pre-zeroed by _jac)
-  for (int b = 0; b < 3; ++b)
-    q.push_back(prob_wgrad(n, hl, ed[b], ws + w.gx[2 * b], hl, E + eo[b], 252, ws + w.G[b], CH_LD, 0, ws + w.gv[b], true));
-  for (GemmProb& p : q) p.kscale = dz;
-  for (size_t i = 0; i < q.size(); i += b200::tg::MAX_PROB) {
-    const int cnt = static_cast<int>(q.size() - i < static_cast<size_t>(b200::tg::MAX_PROB) ? q.size() - i : b200::tg::MAX_PROB);
-    if (tgemm_group(st, q.data() + i, cnt)) return 1;
+  if (!fork) q.insert(q.end(), qg.begin(), qg.end());
+  if (launch_all(q)) return 1;
+  if (fork) {
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));
+    return 0;
   }
   return chain_backward(ar, w, ws, params, grads, st);
 }

@@ -165,19 +165,21 @@ def nerf_params(module) -> List[torch.nn.Parameter]:
 # Persistent-grid cap (in SMs) of the frozen target render while the DepthNet / JVP chain of the same step runs on a side stream;
 # 0 runs the step on one stream.  B200NERF_TARGET_SMS overrides (measurement).
 TARGET_SM_LIMIT = int(__import__("os").environ.get("B200NERF_TARGET_SMS", "128"))
-# The backward split at the losses (b200nerf_depthnet_train_jac / _bwd_jac): the sequential input-gradient chain moves in front of
-# the losses, beside the target render.  That pays when the launches are throughput-bound (measured: 4096 rays 1.683 -> 1.644 ms)
-# and costs when they are latency-bound (512 rays 0.867 -> 0.881 ms), hence "auto" = from SPLIT_BACKWARD_MIN_RAYS rays per
-# process up; B200NERF_SPLIT_BACKWARD=0 / 1 forces the one-pass / the split form.
-SPLIT_BACKWARD = __import__("os").environ.get("B200NERF_SPLIT_BACKWARD", "auto")
-SPLIT_BACKWARD_MIN_RAYS = 2048
+# The backward split at the losses (b200nerf_depthnet_train_jac / _bwd_jac): the sequential input-gradient chain runs with a unit
+# upstream gradient in front of the losses -- on a third stream beside d raw / d z (THIRD_STREAM) -- and the weight-only branch
+# chain beside the weight gradients after them (FORK_BRANCH_CHAIN).  Measured per graphed step, one-pass -> split:
+# 512 rays 0.858 -> 0.759 ms, 1024 0.984 -> 0.831, 2048 1.202 -> 1.065, 4096 1.672 -> 1.600.  B200NERF_SPLIT_BACKWARD=0 keeps the
+# one-pass backward (A/B runs); the autograd route (DepthNetTrainFn) always uses it.
+SPLIT_BACKWARD = __import__("os").environ.get("B200NERF_SPLIT_BACKWARD", "1") != "0"
+THIRD_STREAM = __import__("os").environ.get("B200NERF_THIRD_STREAM", "1") != "0"
+FORK_BRANCH_CHAIN = __import__("os").environ.get("B200NERF_FORK_BRANCH_CHAIN", "1") != "0"
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev):
-    s = _SIDE_STREAMS.get(dev)
+def _side_stream(dev, which=0):
+    s = _SIDE_STREAMS.get((dev, which))
     if s is None:
-        s = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        s = _SIDE_STREAMS[(dev, which)] = torch.cuda.Stream(device=dev)
     return s
 
 
@@ -246,13 +248,17 @@ def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, tar
         _lib.check(L.b200nerf_depthnet_train_fwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), rays_o.data_ptr(),
                                                  rays_d.data_ptr(), n, float(dn.sphere_radius), nf[0], nf[1], ws.data_ptr(),
                                                  z.data_ptr(), st))
-        ws_n = nerf_point_jvp(net_packed, net_params, rays_o, rays_d, viewdirs, z.reshape(-1), raw, draw, st)   # noqa: F841 (kept alive)
         g_arr = _ptrs(cache["grads"])
-        split_bwd = SPLIT_BACKWARD == "1" or (SPLIT_BACKWARD == "auto" and n >= SPLIT_BACKWARD_MIN_RAYS)
+        split_bwd = SPLIT_BACKWARD
+        side2 = _side_stream(dev, 1) if (side is not None and split_bwd and THIRD_STREAM) else None
+        if side2 is not None:
+            side2.wait_stream(side)
+        ws_n = nerf_point_jvp(net_packed, net_params, rays_o, rays_d, viewdirs, z.reshape(-1), raw, draw, st)   # noqa: F841 (kept alive)
         if split_bwd:
-            # the backward's sequential half (input-gradient chain with a unit upstream gradient) does not need the losses
+            # the backward's sequential half (input-gradient chain with a unit upstream gradient) needs neither the losses nor the
+            # colour path: it runs beside d raw / d z on a third stream
             _lib.check(L.b200nerf_depthnet_train_jac(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), n, nf[0], nf[1],
-                                                     ws.data_ptr(), g_arr, st))
+                                                     ws.data_ptr(), g_arr, side2.cuda_stream if side2 is not None else st))
         prev_limit = L.b200nerf_set_sm_limit(TARGET_SM_LIMIT) if side is not None else 0
         try:
             c = trainer.sample_coarse_points(near=hier["near"], far=hier["far"], perturb=kw["perturb"], N_rays=n, N_samples=kw["N_samples"],
@@ -269,14 +275,21 @@ def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, tar
                 L.b200nerf_set_sm_limit(prev_limit)
         if side is not None:
             main.wait_stream(side)
+        if side2 is not None:
+            main.wait_stream(side2)
         st = main.cuda_stream
         losses = torch.empty(3, device=dev)
         dz = torch.empty(n, device=dev)
         ws2 = torch.empty(2, device=dev)
         _lib.check(L.b200nerf_train_loss(raw.data_ptr(), draw.data_ptr(), z.data_ptr(), max_z.data_ptr(), target.data_ptr(), n,
                                          ws2.data_ptr(), losses.data_ptr(), dz.data_ptr(), st))
-        bwd = L.b200nerf_depthnet_train_bwd_jac if split_bwd else L.b200nerf_depthnet_train_bwd
-        _lib.check(bwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), n, nf[0], nf[1], ws.data_ptr(), dz.data_ptr(), g_arr, st))
+        if split_bwd:
+            aux = side.cuda_stream if (side is not None and FORK_BRANCH_CHAIN) else None   # idle after the join above
+            _lib.check(L.b200nerf_depthnet_train_bwd_jac(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), n, nf[0], nf[1],
+                                                         ws.data_ptr(), dz.data_ptr(), g_arr, st, aux))
+        else:
+            _lib.check(L.b200nerf_depthnet_train_bwd(p_arr, len(hidden), _ints(hidden), len(cat), _ints(cat), n, nf[0], nf[1],
+                                                     ws.data_ptr(), dz.data_ptr(), g_arr, st))
     for p, g in zip(params, cache["grads"]):
         if p.grad is not g:
             p.grad = g
