@@ -40,7 +40,12 @@ constexpr int LBO_B = (BN / 8) * SBO + 16;     // 1,168
 constexpr int PLANE_A = (KC / 4) * LBO_A;      // 18,560 B
 constexpr int PLANE_B = (KC / 4) * LBO_B;      //  9,344 B
 constexpr int STAGE_BYTES = 2 * PLANE_A + 2 * PLANE_B;   // hi + lo of both operands: 55,808 B
-constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 128;
+// fp32 staging ring between global memory and the split: every loader thread owns QA + QB + 1 16-byte slots per stage (its k-quads
+// of A and B and its kscale factors), filled by cp.async, NSTG chunks deep
+constexpr int NSTG = 3;
+constexpr int STG_SLOTS = BM * (KC / 4) / THREADS + BN * (KC / 4) / THREADS + 1;   // 4 + 2 + 1
+constexpr int STG_BYTES = STG_SLOTS * THREADS * 16;                                // 28,672 B
+constexpr int SMEM_BYTES = 2 * STAGE_BYTES + NSTG * STG_BYTES + 128;
 constexpr uint32_t TMEM_COLS = 64;
 constexpr int MAX_SEG = 4, MAX_PROB = 16;
 constexpr int QA = BM * (KC / 4) / THREADS;    // k-quads per thread and chunk: 4 of A ...
@@ -107,10 +112,26 @@ __device__ __forceinline__ int row_off(int r) { return (r & 7) * 16 + (r >> 3) *
 // and chunk, which made the kernel issue-bound -- ncu: 48 % issue-active with the tensor pipe at 9 %.)
 enum : int { KVEC = 0, KSCALAR = 1, RVEC = 2, RSCALAR = 3 };
 
+// cp.async (LDGSTS): global -> shared without a register in between, completion counted per GROUP (wait_group N = all but the N
+// youngest groups have landed) -- unlike register loads, whose scoreboards count every outstanding load of the thread, so that
+// waiting for the older of two chunks in flight also waits for the younger.  src_bytes < size zero-fills the rest.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <int R, int Q, int LBO>
 struct OpLoader {
   const float* p0;   // quad 0 at the current chunk
   const float* src;  // segment base (generic path)
+  const float* safe; // a valid, 16-byte aligned address of the operand: source of the zero-filling copies (no byte of it is read)
   long qstride;      // elements between this thread's consecutive quads
   long sk, srow;
   int off0, offstride;   // shared-memory byte offset of quad 0, stride to the next quads
@@ -118,7 +139,7 @@ struct OpLoader {
 
   __device__ __forceinline__ void setup(const float* base, long srow_, long sk_, int vec, int row0_, int row_lim_, int k0, int tid,
                                         bool allow_rvec) {
-    src = base; srow = srow_; sk = sk_; row0 = row0_; row_lim = row_lim_;
+    src = base; safe = base; srow = srow_; sk = sk_; row0 = row0_; row_lim = row_lim_;
     rows_full = row0_ + R <= row_lim_;
     const int lane = tid & 31, warp = tid >> 5;
     if (sk_ == 1) {
@@ -131,6 +152,7 @@ struct OpLoader {
     } else if (allow_rvec && Q == 4 && R == 128 && srow_ == 1 && (sk_ & 3) == 0 && rows_full &&
                ((reinterpret_cast<uintptr_t>(base + row0_) & 15) == 0)) {
       mode = RVEC;                                             // quad i: row 4 lane + i, kq = warp
+      safe = base + (row0_ + 4 * lane);
       p0 = base + (row0_ + 4 * lane) + (k0 + warp * 4) * sk_;
       qstride = 0;
       off0 = row_off(4 * lane) + warp * LBO;
@@ -145,35 +167,28 @@ struct OpLoader {
     }
   }
 
-  // chunk [k0, k0 + KC) of the segment, valid k < k_end
-  __device__ __forceinline__ void load(float (&v)[Q][4], int k0, int k_end, int tid) {
+  // chunk [k0, k0 + KC) of the segment, valid k < k_end: cp.async of this thread's quads into its staging slots (slot i at
+  // stg + i * THREADS * 16; shared-memory byte address).  RVEC stores the micro-tile untransposed: slot kk = rows 4 lane .. + 3 at k = kk.
+  __device__ __forceinline__ void issue(uint32_t stg, int k0, int k_end, int tid) {
+    constexpr uint32_t SLOT = THREADS * 16;
     if (mode == RVEC) {
       const int kb = k0 + (tid >> 5) * 4;
-      float4 t[4];
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        t[kk] = kb + kk < k_end ? __ldg(reinterpret_cast<const float4*>(p0 + kk * sk)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        v[0 % Q][kk] = t[kk].x; v[1 % Q][kk] = t[kk].y; v[2 % Q][kk] = t[kk].z; v[3 % Q][kk] = t[kk].w;
-      }
+      for (int kk = 0; kk < 4; ++kk) cp_async16(stg + kk * SLOT, kb + kk < k_end ? p0 + kk * sk : safe, kb + kk < k_end ? 16u : 0u);
     } else if (rows_full && k0 + KC <= k_end) {
       if (mode == KVEC) {
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(p0 + i * qstride));
-          v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
-        }
+        for (int i = 0; i < Q; ++i) cp_async16(stg + i * SLOT, p0 + i * qstride, 16u);
       } else if (mode == KSCALAR) {
 #pragma unroll
         for (int i = 0; i < Q; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[i][j] = __ldg(p0 + i * qstride + j);
+          for (int j = 0; j < 4; ++j) cp_async4(stg + i * SLOT + j * 4, p0 + i * qstride + j, 4u);
       } else {
 #pragma unroll
         for (int i = 0; i < Q; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[i][j] = __ldg(p0 + i * qstride + j * sk);
+          for (int j = 0; j < 4; ++j) cp_async4(stg + i * SLOT + j * 4, p0 + i * qstride + j * sk, 4u);
       }
     } else {
       // edge tile / tail chunk: bounds-checked, same quad mapping
@@ -185,10 +200,29 @@ struct OpLoader {
         const int gr = row0 + r, gk = k0 + kq * 4;
         const float* s = src + gr * srow + gk * sk;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[i][j] = (gr < row_lim && gk + j < k_end) ? __ldg(s + j * sk) : 0.f;
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = gr < row_lim && gk + j < k_end;
+          cp_async4(stg + i * SLOT + j * 4, ok ? s + j * sk : src, ok ? 4u : 0u);
+        }
       }
     }
     p0 += KC * sk;
+  }
+  // the chunk's quads from the staging slots (after cp.async.wait_group); `m` = the mapping the chunk was issued with
+  __device__ __forceinline__ static void fetch(float (&v)[Q][4], const uint8_t* stg, int m) {
+    constexpr int SLOT = THREADS * 16;
+    float4 t[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) t[i] = *reinterpret_cast<const float4*>(stg + i * SLOT);
+    if (m == RVEC) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        v[0 % Q][kk] = t[kk % Q].x; v[1 % Q][kk] = t[kk % Q].y; v[2 % Q][kk] = t[kk % Q].z; v[3 % Q][kk] = t[kk % Q].w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < Q; ++i) { v[i][0] = t[i].x; v[i][1] = t[i].y; v[i][2] = t[i].z; v[i][3] = t[i].w; }
+    }
   }
 
   // k-quad index (within the chunk) of this thread's quad i, for the mapping `m` the chunk was loaded with
@@ -213,7 +247,7 @@ struct OpLoader {
   }
 };
 
-__global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_constant__ Group g) {
+__global__ void __launch_bounds__(CTA_THREADS, 1) tgemm_kernel(const __grid_constant__ Group g) {
   extern __shared__ __align__(128) uint8_t tg_smem_[];
   __shared__ uint64_t mma_done[2];   // stage s: its MMAs have retired (tcgen05.commit)
   __shared__ uint64_t full[2];       // stage s: all eight loader warps have stored (and proxy-fenced) their quads
@@ -274,6 +308,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
         const int s = c & 1;
         const uint32_t a_hi = smem_u32(smem) + s * STAGE_BYTES, a_lo = a_hi + PLANE_A, b_hi = a_lo + PLANE_A, b_lo = b_hi + PLANE_B;
         mbar_wait(&full[s], static_cast<uint32_t>(c >> 1) & 1u);
+        // The generic-proxy -> async-proxy fence of the loaders' st.shared sits HERE, on the consumer side of the release / acquire
+        // pair (a proxy fence anywhere along the causality path orders the two proxies).  In the loader threads it compiles to
+        // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC.S, and the MEMBAR drains the thread's in-flight global loads: one full load latency per
+        // chunk (1.05 us per chunk; 0.41 us for the one chunk of a CTA that had no load in flight).
+        fence_proxy_async_smem();
         tc_fence_after();
 #pragma unroll
         for (int j = 0; j < KC / 8; ++j) {
@@ -298,7 +337,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
 
   // ---- loader warps
   if (stamp) g.dbg[1] = gtimer();
-  float va[QA][4], vb[QB][4];
+  // NSTG - 1 chunks in flight through the staging ring: the copies of chunk c + 2 are issued at the hand-off of chunk c.  Only the
+  // mapping of a chunk in flight lives in registers (the segment may change under it).
+  struct ChunkMeta {
+    int a_mode, a_off0, a_offstride, b_off0, b_offstride, a_k0, a_kend;
+  };
+  ChunkMeta r0, r1;
   OpLoader<BM, QA, LBO_A> la;
   OpLoader<BN, QB, LBO_B> lb;
   auto open_segment = [&]() {
@@ -306,24 +350,31 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
     la.setup(S.A, S.sAm, S.sAk, S.vecA, m0, P.M, ck, tid, true);
     lb.setup(S.B, S.sBn, S.sBk, S.vecB, n0, P.N, ck, tid, false);
   };
-  int a_mode;   // the mapping of the chunk held in va (the segment may change under it)
-  int a_off0, a_offstride, b_off0, b_offstride;
-  int a_k0 = 0, a_kend = 0;            // k range of the chunk held in va (kscale)
-  float ks[4] = {1.f, 1.f, 1.f, 1.f};  // RVEC: the chunk's four factors of this warp's k-quad, fetched with the operands
   const float* const kscale = P.kscale;
-  auto prefetch = [&]() {   // loads chunk (cs, ck) into registers and advances the walk
-    a_mode = la.mode;
-    a_off0 = la.off0; a_offstride = la.offstride; b_off0 = lb.off0; b_offstride = lb.offstride;
-    la.load(va, ck, ce, tid);
-    lb.load(vb, ck, ce, tid);
+  uint8_t* const stg_base = smem + 2 * STAGE_BYTES + tid * 16;
+  const bool ks_vec = kscale != nullptr && (reinterpret_cast<uintptr_t>(kscale) & 15) == 0;
+  int issued = 0;
+  auto prefetch = [&](ChunkMeta& R) {   // issues the copies of chunk (cs, ck) into staging stage `issued % NSTG` and advances the walk
+    const uint32_t stg = smem_u32(stg_base) + static_cast<uint32_t>(issued % NSTG) * STG_BYTES;
+    ++issued;
+    R.a_mode = la.mode;
+    R.a_off0 = la.off0; R.a_offstride = la.offstride; R.b_off0 = lb.off0; R.b_offstride = lb.offstride;
+    la.issue(stg, ck, ce, tid);
+    lb.issue(stg + QA * THREADS * 16, ck, ce, tid);
     if (kscale) {
-      a_k0 = ck; a_kend = ce;
-      if (a_mode == RVEC) {
+      R.a_k0 = ck; R.a_kend = ce;
+      if (R.a_mode == RVEC) {   // the four factors of this warp's k-quad ride in slot QA + QB
         const int kb = ck + warp * 4;
+        const uint32_t dst = stg + (QA + QB) * THREADS * 16;
+        if (ks_vec && kb + 4 <= ce) {
+          cp_async16(dst, kscale + kb, 16u);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ks[j] = kb + j < ce ? __ldg(kscale + kb + j) : 0.f;
+          for (int j = 0; j < 4; ++j) cp_async4(dst + j * 4, kb + j < ce ? kscale + kb + j : kscale, kb + j < ce ? 4u : 0u);
+        }
       }
     }
+    cp_async_commit();
     ck += KC;
     if (ck >= ce && !split && cs + 1 < P.nseg) {
       ++cs;
@@ -336,19 +387,24 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
     for (int i = tid; i < BM; i += THREADS) colsum_red[i] = 0.f;
     named_bar_sync(1, THREADS);
   }
-  open_segment();
-  prefetch();
   float csum[4] = {0.f, 0.f, 0.f, 0.f};
-
-  for (int c = 0; c < nchunks; ++c) {
+  int a_mode = KVEC;
+  auto hand_off = [&](int c, ChunkMeta& R) {   // chunk c (mapping in R) -> operand stage c & 1; then R describes chunk c + 2
     const int s = c & 1;
     uint8_t* a_hi = smem + s * STAGE_BYTES;
     uint8_t* a_lo = a_hi + PLANE_A;
     uint8_t* b_hi = a_lo + PLANE_A;
     uint8_t* b_lo = b_hi + PLANE_B;
-    if (c >= 2) mbar_wait(&mma_done[s], static_cast<uint32_t>((c >> 1) - 1) & 1u);   // the MMAs that read this stage have retired
+    const uint8_t* stg = stg_base + (c % NSTG) * STG_BYTES;
+    if (c + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();   // this thread's copies of chunk c have landed
+    float va[QA][4], vb[QB][4];
+    OpLoader<BM, QA, LBO_A>::fetch(va, stg, R.a_mode);
+    OpLoader<BN, QB, LBO_B>::fetch(vb, stg + QA * THREADS * 16, KVEC);
+    a_mode = R.a_mode;
     if (kscale) {   // before the split and the column sums: dW = sum_r (dz_r J[r, :])^T x[r, :], db = sum_r dz_r J[r, :]
-      if (a_mode == RVEC) {
+      if (R.a_mode == RVEC) {
+        const float4 k4 = *reinterpret_cast<const float4*>(stg + (QA + QB) * THREADS * 16);
+        const float ks[4] = {k4.x, k4.y, k4.z, k4.w};
 #pragma unroll
         for (int i = 0; i < QA; ++i)
 #pragma unroll
@@ -356,32 +412,39 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) tgemm_kernel(const __grid_cons
       } else {
 #pragma unroll
         for (int i = 0; i < QA; ++i) {
-          const int kb = a_k0 + la.kquad(a_mode, i, tid) * 4;
+          const int kb = R.a_k0 + la.kquad(R.a_mode, i, tid) * 4;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) va[i][j] *= kb + j < a_kend ? __ldg(kscale + kb + j) : 0.f;
+          for (int j = 0; j < 4; ++j) va[i][j] *= kb + j < R.a_kend ? __ldg(kscale + kb + j) : 0.f;
         }
       }
     }
+    if (c >= 2) mbar_wait(&mma_done[s], static_cast<uint32_t>((c >> 1) - 1) & 1u);   // the MMAs that read this stage have retired
     {
       OpLoader<BM, QA, LBO_A> sa = la;
-      sa.off0 = a_off0; sa.offstride = a_offstride;
+      sa.off0 = R.a_off0; sa.offstride = R.a_offstride;
       sa.store(va, a_hi, a_lo);
       OpLoader<BN, QB, LBO_B> sb = lb;
-      sb.off0 = b_off0; sb.offstride = b_offstride;
+      sb.off0 = R.b_off0; sb.offstride = R.b_offstride;
       sb.store(vb, b_hi, b_lo);
     }
     if (P.colsum) {   // k-strided A: RVEC -> quad i is row 4 lane + i; RSCALAR -> every quad is row tid & 127
 #pragma unroll
       for (int i = 0; i < QA; ++i) {
         const float t = (va[i][0] + va[i][1]) + (va[i][2] + va[i][3]);
-        if (a_mode == RVEC) csum[i] += t; else csum[0] += t;
+        if (R.a_mode == RVEC) csum[i] += t; else csum[0] += t;
       }
     }
-    if (c + 1 < nchunks) prefetch();   // in flight while the MMA warp works and the next stage is waited for
-    fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&full[s]);
+    if (lane == 0) mbar_arrive(&full[s]);   // release: the MMA warp's acquire + proxy fence make the stores visible to the tensor core
     if (stamp && c < 12) g.dbg[4 + c] = gtimer();
+    if (c + 2 < nchunks) prefetch(R);   // into the staging stage chunk c - 1 has left
+  };
+  open_segment();
+  prefetch(r0);
+  if (nchunks > 1) prefetch(r1);
+  for (int c = 0; c < nchunks; c += 2) {
+    hand_off(c, r0);
+    if (c + 1 < nchunks) hand_off(c + 1, r1);
   }
 
   if (P.colsum) {
