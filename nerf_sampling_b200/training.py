@@ -326,23 +326,65 @@ class Adam(torch.optim.Optimizer):
             bufs[gi] = buf
         return buf
 
+    def _rows(self, group):
+        rows, dev = [], None
+        for p in group["params"]:
+            if p.grad is None:
+                continue
+            dev = p.device
+            st = self.state[p]
+            if "exp_avg" not in st:
+                st["exp_avg"] = torch.zeros_like(p)
+                st["exp_avg_sq"] = torch.zeros_like(p)
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            rows.append((p, g, st))
+        return rows, dev
+
+    @staticmethod
+    def _table_ptrs(rows):
+        return [x for p, g, st in rows for x in (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())]
+
+    @torch.no_grad()
+    def stage_for_capture(self, grad_scale: float = 1.0):
+        """While a CUDA graph is being captured: put the uploads ``step`` needs -- the pointer table and the hyper-parameter block
+        the graph re-reads from pinned memory on every replay -- on a forked stream at the START of the step.  Two memcpy nodes
+        in front of the Adam launch cost ~20 us of the step's critical path; here they run under the render.  ``step`` joins the
+        fork.  Gradients must already exist at their final addresses (they do after a warm-up step of the fused route)."""
+        if not torch.cuda.is_current_stream_capturing():
+            return
+        cur = torch.cuda.current_stream()
+        fork = self.__dict__.get("_b200_stage_stream")
+        if fork is None or fork.device != cur.device:
+            fork = self.__dict__["_b200_stage_stream"] = torch.cuda.Stream(device=cur.device)
+        fork.wait_stream(cur)
+        staged = {}
+        with torch.cuda.stream(fork):
+            for gi, group in enumerate(self.param_groups):
+                rows, dev = self._rows(group)
+                if not rows:
+                    continue
+                buf = self._group_buffers(gi, group, dev)
+                ptrs = self._table_ptrs(rows)
+                host = buf["graph_table_host"][: len(rows)]
+                host.view(-1).numpy()[:] = ptrs
+                table = buf["graph_table"][: len(rows)]
+                table.copy_(host, non_blocking=True)
+                b1, b2 = group["betas"]
+                buf["hyper_host"].numpy()[:] = [float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(grad_scale)]
+                buf["hyper"].copy_(buf["hyper_host"], non_blocking=True)   # a memcpy node that re-reads the host values on every replay
+                staged[gi] = ptrs
+        self.__dict__["_b200_staged"] = (fork, staged)
+
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         L = _lib.lib()
         capturing = torch.cuda.is_current_stream_capturing()
+        fork, staged = self.__dict__.pop("_b200_staged", (None, {})) if capturing else (None, {})
+        if fork is not None:
+            torch.cuda.current_stream().wait_stream(fork)
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group["betas"]
-            rows, dev = [], None
-            for p in group["params"]:
-                if p.grad is None:
-                    continue
-                dev = p.device
-                st = self.state[p]
-                if "exp_avg" not in st:
-                    st["exp_avg"] = torch.zeros_like(p)
-                    st["exp_avg_sq"] = torch.zeros_like(p)
-                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                rows.append((p, g, st))
+            rows, dev = self._rows(group)
             if not rows:
                 continue
             buf = self._group_buffers(gi, group, dev)
@@ -353,12 +395,20 @@ class Adam(torch.optim.Optimizer):
                         buf["step"].fill_(int(prev))
                     st["step"] = buf["step"]
             with torch.cuda.device(dev):
-                ptrs = [x for p, g, st in rows for x in (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel())]
-                if capturing:
+                ptrs = self._table_ptrs(rows)
+                vals = [float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(grad_scale)]
+                if capturing and staged.get(gi) == ptrs:
+                    # uploads already captured by stage_for_capture; the host block is plain memory: keep it current
+                    table = buf["graph_table"][: len(rows)]
+                    buf["hyper_host"].numpy()[:] = vals
+                elif capturing:
                     host = buf["graph_table_host"][: len(rows)]
                     host.view(-1).numpy()[:] = ptrs
                     table = buf["graph_table"][: len(rows)]
                     table.copy_(host, non_blocking=True)
+                    hh = buf["hyper_host"]
+                    hh.numpy()[:] = vals
+                    buf["hyper"].copy_(hh, non_blocking=True)   # a memcpy node that re-reads the host values on every replay
                 else:
                     if ptrs != buf["ptrs"]:
                         # gradients are new tensors after an eager backward: refresh the pointer table (a fresh pinned buffer
@@ -368,12 +418,6 @@ class Adam(torch.optim.Optimizer):
                         buf["table"] = host.to(dev, non_blocking=True)
                         buf["keep"] = [g for _, g, _ in rows]
                     table = buf["table"]
-                vals = [float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(grad_scale)]
-                if capturing:
-                    hh = buf["hyper_host"]
-                    hh.numpy()[:] = vals
-                    buf["hyper"].copy_(hh, non_blocking=True)   # a memcpy node that re-reads the host values on every replay
-                else:
                     slot = buf["hyper_ring"][buf["hyper_slot"]]
                     buf["hyper_slot"] = (buf["hyper_slot"] + 1) % len(buf["hyper_ring"])
                     if slot[1] is not None:
@@ -471,6 +515,9 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            if self.capture_step:
+                world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+                self.opt.stage_for_capture(grad_scale=1.0 / world)   # Adam's uploads, forked to the start of the step
             loss, dn_loss, psnr, _ = self.trainer.render_and_backward(self.opt, self.kw, (self.rays[0], self.rays[1]), 100, self.target)
             if self.capture_step:
                 self.trainer.reduce_and_step(self.opt)
