@@ -192,12 +192,13 @@ static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
     P.M = q.M; P.N = q.N; P.nseg = q.nseg; P.ldc = q.ldc; P.beta = q.beta; P.act = q.act; P.ld_dact = q.ld_dact; P.slope = q.slope;
     P.tiles_x = (q.N + tg::BN - 1) / tg::BN;
     P.tiles_y = (q.M + tg::BM - 1) / tg::BM;
-    // long reductions into a small output (weight gradients): split K until the launch fills the GPU about twice
     int splits = 1;
     const int K0 = q.seg[0].K;
     if (q.nseg == 1 && !q.act && !q.dact && K0 >= 512) {
-      // ~8 chunks per CTA, like the CTAs of the other problems in the group: a CTA that walks the whole reduction would be
-      // the launch's tail (ncu: SMs idle 55 % of a backward group when the weight-gradient CTAs had 64 chunks each)
+      // a long reduction into a small output: ~8 chunks per CTA like the CTAs of the other problems of the group -- a CTA that walks
+      // the whole reduction would be the launch's tail.  (Measured for the split backward's group of 16 weight gradients, 136 tiles
+      // of 128 chunks: ONE wave of unsplit CTAs with plain stores is no faster than 2,176 CTAs of 8 chunks with atomics, 1.651 vs
+      // 1.644 ms per 4096-ray step -- the launch is bound by the strided operand reads, not by the per-CTA fixed cost.)
       splits = K0 / 256;
       const int own_tiles = P.tiles_x * P.tiles_y;
       while (splits > 1 && own_tiles * splits > 4 * g_sm_count) splits >>= 1;
@@ -474,30 +475,53 @@ constexpr int CH_STAGES = 4;
 constexpr int CH_ROWS = 32;                        // rows of W_i per ring stage
 constexpr int CH_STAGE_BYTES = 49152;              // >= 32 x (256 + 126) x 4
 constexpr int CH_PART_BYTES = 4 * CH_MAXH * CH_CW * 4;   // bwd: partial sums of the four row groups
-constexpr int CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + CH_PART_BYTES + 128;
+// The rows of every layer are split over a cluster of CH_R CTAs (same columns): a CTA streams and multiplies only its CH_RPR rows of
+// U_i and the slices meet in distributed shared memory once per layer -- the kernels were instruction-bound on ONE CTA per
+// column group (136 / 87 us whatever the batch: the head of the forward chain and the tail of the backward of every step).
+constexpr int CH_R = 2;
+constexpr int CH_RPR = CH_MAXH / CH_R;
+constexpr int CH_SLOT_BYTES = 2 * CH_MAXH * CH_CW * 4;          // bwd: the peer's partial sums, double-buffered by layer parity
+constexpr int CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + CH_PART_BYTES + CH_SLOT_BYTES + 128;
+static_assert(CH_R == 2, "the kernels exchange with ONE peer");
+static_assert(CH_SMEM_BYTES + 8448 <= 232448, "dynamic + static shared memory of the chain kernels");
+
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// rows of a layer of width h that rank `rank` owns: [rank * CH_RPR, rank * CH_RPR + own)
+__device__ __forceinline__ int chain_own_rows(int h, int rank) {
+  const int left = h - rank * CH_RPR;
+  return left < 0 ? 0 : (left < CH_RPR ? left : CH_RPR);
+}
 
 // the producer side of the ring, run by thread 0: blocks are numbered q = 0, 1, ... over the layers in visiting order
 struct ChainFeed {
   int layer, block, issued;
 };
 template <bool FWD>
-__device__ __forceinline__ void chain_feed(const ChainBranch& B, int L, ChainFeed& f, uint8_t* ring, uint64_t* full, uint64_t* empty) {
+__device__ __forceinline__ void chain_feed(const ChainBranch& B, int L, int rank, ChainFeed& f, uint8_t* ring, uint64_t* full,
+                                           uint64_t* empty) {
+  // layers in which this rank owns no row (widths <= CH_RPR) contribute no block
+  while ((FWD ? f.layer < L : f.layer >= 1) && chain_own_rows(B.h[f.layer], rank) == 0) f.layer += FWD ? 1 : -1;
   if (FWD ? f.layer >= L : f.layer < 1) return;
-  const int h = B.h[f.layer], ldw = B.h[f.layer - 1] + B.d;
+  const int own = chain_own_rows(B.h[f.layer], rank), ldw = B.h[f.layer - 1] + B.d;
   const int s = f.issued % CH_STAGES, use = f.issued / CH_STAGES;
   if (use > 0) b200::mbar_wait(&empty[s], static_cast<uint32_t>(use - 1) & 1u);   // every warp has read the stage's previous block
   const int r0 = f.block * CH_ROWS;
-  const int rows = h - r0 < CH_ROWS ? h - r0 : CH_ROWS;
+  const int rows = own - r0 < CH_ROWS ? own - r0 : CH_ROWS;
   const uint32_t bytes = static_cast<uint32_t>(rows) * ldw * 4u;
   b200::mbar_arrive_expect_tx(&full[s], bytes);
   // four 8-row copies per block: the latency of one bulk copy (~2 us for 40 KB) bounds the stream unless enough are in flight
   for (int sub = 0; sub < rows; sub += CH_ROWS / 4) {
     const int nr = rows - sub < CH_ROWS / 4 ? rows - sub : CH_ROWS / 4;
     b200::tma_load_1d(ring + static_cast<size_t>(s) * CH_STAGE_BYTES + static_cast<size_t>(sub) * ldw * 4,
-                      B.W[f.layer] + static_cast<size_t>(r0 + sub) * ldw, static_cast<uint32_t>(nr) * ldw * 4u, &full[s]);
+                      B.W[f.layer] + static_cast<size_t>(rank * CH_RPR + r0 + sub) * ldw, static_cast<uint32_t>(nr) * ldw * 4u, &full[s]);
   }
   ++f.issued;
-  if (++f.block * CH_ROWS >= h) {
+  if (++f.block * CH_ROWS >= own) {
     f.block = 0;
     f.layer += FWD ? 1 : -1;
   }
@@ -510,8 +534,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(const __grid_c
   __shared__ __align__(16) float buf[2][CH_MAXH][CH_CW];
   __shared__ uint64_t full[CH_STAGES], empty[CH_STAGES];
   uint8_t* ring = ch_smem_ + ((128u - (b200::smem_u32(ch_smem_) & 127u)) & 127u);
+  const int rank = static_cast<int>(b200::cluster_ctarank());
   int local;
-  const ChainBranch& B = chain_branch(p, blockIdx.x, &local);
+  const ChainBranch& B = chain_branch(p, blockIdx.x / CH_R, &local);
   const int d = B.d, c0 = local * CH_CW, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     for (int s = 0; s < CH_STAGES; ++s) {
@@ -520,7 +545,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(const __grid_c
     }
     b200::fence_mbar_init();
   }
-  if (tid < CH_MAXH) {
+  if (tid < CH_MAXH) {   // layer 0 needs no product: every rank fills its own copy, the owner of a row writes it out
     const int m = tid, h = B.h[0], ldw = 2 * d;
     const float* W0 = B.W[0];
 #pragma unroll
@@ -529,19 +554,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(const __grid_c
       float v = 0.f;
       if (m < h && c <= d) v = c < d ? W0[static_cast<size_t>(m) * ldw + c] + W0[static_cast<size_t>(m) * ldw + d + c] : B.b[0][m];
       buf[0][m][j] = v;
-      if (m < h && c <= d) B.Aaug[static_cast<size_t>(m) * CH_LD + c] = v;
+      if (m < h && c <= d && m / CH_RPR == rank) B.Aaug[static_cast<size_t>(m) * CH_LD + c] = v;
     }
   }
   __syncthreads();
+  b200::cluster_sync_all();   // the peer's shared memory exists and is initialised before anyone writes into it
   ChainFeed feed{1, 0, 0};
   if (tid == 0)
-    for (int k = 0; k < CH_STAGES - 1; ++k) chain_feed<true>(B, p.L, feed, ring, full, empty);
+    for (int k = 0; k < CH_STAGES - 1; ++k) chain_feed<true>(B, p.L, rank, feed, ring, full, empty);
   static_assert(CH_CW == 4, "the forward recurrence keeps a 4-column slice of [A | c] in registers");
   const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
   const int my_col = c0 + (b4 ? 2 : 0) + (b3 ? 1 : 0);   // the column whose sum this lane ends up with
+  const uint32_t peer_buf = b200::mapa_u32(b200::smem_u32(&buf[0][0][0]), static_cast<uint32_t>(rank ^ 1));
   int q = 0;
   for (int i = 1; i < p.L; ++i) {
-    const int h = B.h[i], pw = B.h[i - 1], ldw = pw + d;
+    const int h = B.h[i], pw = B.h[i - 1], ldw = pw + d, own = chain_own_rows(h, rank), row_base = rank * CH_RPR;
     float(*dst)[CH_CW] = buf[i & 1];
     const float* bias = B.b[i];
     // this lane's rows k = lane + 32 j of [A_{i-1} | c_{i-1}] stay in registers for the whole layer: every warp multiplies them
@@ -552,14 +579,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(const __grid_c
       const int k = lane + 32 * j;
       a[j] = k < pw ? *reinterpret_cast<const float4*>(buf[(i - 1) & 1][k]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int r0 = 0; r0 < h; r0 += CH_ROWS, ++q) {
-      if (tid == 0) chain_feed<true>(B, p.L, feed, ring, full, empty);
+    for (int r0 = 0; r0 < own; r0 += CH_ROWS, ++q) {
+      if (tid == 0) chain_feed<true>(B, p.L, rank, feed, ring, full, empty);
       const int s = q % CH_STAGES;
       b200::mbar_wait(&full[s], static_cast<uint32_t>(q / CH_STAGES) & 1u);
       const float* Us = reinterpret_cast<const float*>(ring + static_cast<size_t>(s) * CH_STAGE_BYTES) + warp * ldw;
-      const int m = r0 + warp;
+      const int m = row_base + r0 + warp;
+      const bool live = r0 + warp < own;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      if (m < h) {
+      if (live) {
 #pragma unroll
         for (int j = 0; j < CH_MAXH / 32; ++j) {
           const int k = lane + 32 * j;
@@ -579,21 +607,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_fwd_kernel(const __grid_c
       y += __shfl_xor_sync(0xffffffffu, y, 4);
       y += __shfl_xor_sync(0xffffffffu, y, 2);
       y += __shfl_xor_sync(0xffffffffu, y, 1);
-      if ((lane & 7) == 0 && m < h) {
+      if ((lane & 7) == 0 && live) {
         float v = 0.f;
         if (my_col <= d) {
           v = y + (my_col < d ? Us[pw + my_col] : bias[m]);
           B.Aaug[(static_cast<size_t>(i) * CH_MAXH + m) * CH_LD + my_col] = v;
         }
         dst[m][my_col - c0] = v;
+        // the peer multiplies the next layer with the whole slice: its copy of this row
+        st_cluster_f32(peer_buf + static_cast<uint32_t>((((i & 1) * CH_MAXH + m) * CH_CW + (my_col - c0)) * 4), v);
       }
       __syncwarp();
       if (lane == 0) b200::mbar_arrive(&empty[s]);
     }
-    __syncthreads();
+    b200::cluster_sync_all();   // both halves of [A_i | c_i] are in both CTAs (release / acquire at cluster scope)
   }
   const int hl = B.h[p.L - 1];
-  if (d >= c0 && d < c0 + CH_CW && tid < hl) B.c_last[tid] = buf[(p.L - 1) & 1][tid][d - c0];
+  if (rank == 0 && d >= c0 && d < c0 + CH_CW && tid < hl) B.c_last[tid] = buf[(p.L - 1) & 1][tid][d - c0];
 }
 
 // R_{i-1}[k, c] = sum_m U_i[m, k] R_i[m, c]: thread (g, k) sums rows 8 g .. 8 g + 7 of every 32-row block (consecutive threads read
@@ -604,8 +634,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(const __grid_c
   __shared__ uint64_t full[CH_STAGES], empty[CH_STAGES];
   uint8_t* ring = ch_smem_ + ((128u - (b200::smem_u32(ch_smem_) & 127u)) & 127u);
   float(*part)[CH_MAXH][CH_CW] = reinterpret_cast<float(*)[CH_MAXH][CH_CW]>(ring + CH_STAGES * CH_STAGE_BYTES);
+  // slot[parity][k][c]: the PEER's partial sums over its rows of U_i (it writes them here through distributed shared memory)
+  float(*slot)[CH_MAXH][CH_CW] = reinterpret_cast<float(*)[CH_MAXH][CH_CW]>(ring + CH_STAGES * CH_STAGE_BYTES + CH_PART_BYTES);
+  const int rank = static_cast<int>(b200::cluster_ctarank());
   int local;
-  const ChainBranch& B = chain_branch(p, blockIdx.x, &local);
+  const ChainBranch& B = chain_branch(p, blockIdx.x / CH_R, &local);
   const int d = B.d, c0 = local * CH_CW, tid = threadIdx.x, lane = tid & 31, k = tid & (CH_MAXH - 1), g = tid >> 8;
   if (tid == 0) {
     for (int s = 0; s < CH_STAGES; ++s) {
@@ -625,14 +658,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(const __grid_c
     }
   }
   __syncthreads();
+  b200::cluster_sync_all();   // the peer's shared memory exists before anyone writes into it
+  const uint32_t peer_slot = b200::mapa_u32(b200::smem_u32(&slot[0][0][0]), static_cast<uint32_t>(rank ^ 1));
   ChainFeed feed{p.L - 1, 0, 0};
   if (tid == 0)
-    for (int n = 0; n < CH_STAGES - 1; ++n) chain_feed<false>(B, p.L, feed, ring, full, empty);
+    for (int n = 0; n < CH_STAGES - 1; ++n) chain_feed<false>(B, p.L, rank, feed, ring, full, empty);
   int q = 0;
   for (int i = p.L - 1; i >= 0; --i) {
     const int h = B.h[i], pw = i ? B.h[i - 1] : d, ldw = pw + d;
     const float(*src)[CH_CW] = buf[i & 1];
-    if (tid < h) {   // gradients of layer i that are columns of R_i
+    if (tid < h && tid / CH_RPR == rank) {   // gradients of layer i that are columns of R_i: the owner of a row writes it
       float* gw = B.gW[i] + static_cast<size_t>(tid) * ldw;
 #pragma unroll
       for (int j = 0; j < CH_CW; ++j) {
@@ -648,19 +683,20 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(const __grid_c
       }
     }
     if (i == 0) break;
+    const int own = chain_own_rows(h, rank), row_base = rank * CH_RPR;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int r0 = 0; r0 < h; r0 += CH_ROWS, ++q) {
-      if (tid == 0) chain_feed<false>(B, p.L, feed, ring, full, empty);
+    for (int r0 = 0; r0 < own; r0 += CH_ROWS, ++q) {
+      if (tid == 0) chain_feed<false>(B, p.L, rank, feed, ring, full, empty);
       const int s = q % CH_STAGES;
       b200::mbar_wait(&full[s], static_cast<uint32_t>(q / CH_STAGES) & 1u);
       const float* Us = reinterpret_cast<const float*>(ring + static_cast<size_t>(s) * CH_STAGE_BYTES) + k;
       if (k < pw) {
 #pragma unroll
         for (int r = 0; r < CH_ROWS / 4; ++r) {
-          const int rr = g * (CH_ROWS / 4) + r, m = r0 + rr;
-          if (m < h) {
+          const int rr = g * (CH_ROWS / 4) + r;
+          if (r0 + rr < own) {
             const float u = Us[rr * ldw];
-            const float4 a = *reinterpret_cast<const float4*>(src[m]);
+            const float4 a = *reinterpret_cast<const float4*>(src[row_base + r0 + rr]);
             a0 = fmaf(u, a.x, a0);
             a1 = fmaf(u, a.y, a1);
             a2 = fmaf(u, a.z, a2);
@@ -673,9 +709,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1) chain_bwd_kernel(const __grid_c
     }
     *reinterpret_cast<float4*>(part[g][k]) = make_float4(a0, a1, a2, a3);
     __syncthreads();
-    {
-      const int kk = tid >> 2, c = tid & 3;   // one (row, column) element per thread
-      buf[(i - 1) & 1][kk][c] = kk < pw ? (part[0][kk][c] + part[1][kk][c]) + (part[2][kk][c] + part[3][kk][c]) : 0.f;
+    const int par = i & 1;
+    float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < CH_MAXH) {   // this rank's partial sums of row tid of R_{i-1}: kept here, sent to the peer
+      if (tid < pw) {
+        const float4 p0 = *reinterpret_cast<const float4*>(part[0][tid]), p1 = *reinterpret_cast<const float4*>(part[1][tid]);
+        const float4 p2 = *reinterpret_cast<const float4*>(part[2][tid]), p3 = *reinterpret_cast<const float4*>(part[3][tid]);
+        mine = make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z),
+                           (p0.w + p1.w) + (p2.w + p3.w));
+      }
+      st_cluster_v4(peer_slot + static_cast<uint32_t>(((par * CH_MAXH + tid) * CH_CW) * 4), mine);
+    }
+    b200::cluster_sync_all();   // the peer's partial sums have arrived; the parity keeps the next layer's writes apart
+    if (tid < CH_MAXH) {
+      const float4 o = *reinterpret_cast<const float4*>(slot[par][tid]);
+      // a + b == b + a bit for bit: both CTAs continue with the same R_{i-1}
+      *reinterpret_cast<float4*>(buf[(i - 1) & 1][tid]) = make_float4(mine.x + o.x, mine.y + o.y, mine.z + o.z, mine.w + o.w);
     }
     __syncthreads();
   }
@@ -854,6 +903,25 @@ static ChainParams chain_params(const DnArch& ar, const DnWs& w, float* ws, cons
   return cp;
 }
 static int chain_ctas(const ChainParams& cp) { return cp.br[2].cta_begin + (cp.br[2].d + 1 + CH_CW - 1) / CH_CW; }
+// one cluster of CH_R CTAs per column group
+static int launch_chain(void (*kern)(const ChainParams), const ChainParams& cp, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CH_R;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(CH_R * chain_ctas(cp));
+  cfg.blockDim = dim3(CH_THREADS);
+  cfg.dynamicSmemBytes = CH_SMEM_BYTES;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, cp));
+  LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" size_t b200nerf_depthnet_train_ws_floats(int n_rays, int n_branch, const int* hidden, int n_cat, const int* cat_hidden) {
   DnArch ar;
@@ -882,8 +950,7 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
       // collapsed branches: [A_i | c_i] recurrences over the weights (one launch), then x_last = e A_last^T + c_last per ray
       const ChainParams cp = chain_params(ar, w, ws, params, nullptr);
       if (chain_configure()) return 1;
-      chain_fwd_kernel<<<chain_ctas(cp), CH_THREADS, CH_SMEM_BYTES, st>>>(cp);
-      LAUNCH_CHECK();
+      if (launch_chain(chain_fwd_kernel, cp, st)) return 1;
       GemmProb q[3];
       const int hlast = ar.h[ar.nb - 1];
       for (int b = 0; b < 3; ++b) {
@@ -1005,8 +1072,7 @@ static int chain_backward(const DnArch& ar, const DnWs& w, float* ws, const floa
   const int ed[3] = {63, 63, 126};
   const ChainParams cp = chain_params(ar, w, ws, params, grads);
   if (chain_configure()) return 1;
-  chain_bwd_kernel<<<chain_ctas(cp), CH_THREADS, CH_SMEM_BYTES, st>>>(cp);
-  LAUNCH_CHECK();
+  if (launch_chain(chain_bwd_kernel, cp, st)) return 1;
   if (ar.nb > 1) {
     DuBatch batch;
     memset(&batch, 0, sizeof(batch));

@@ -248,7 +248,8 @@ def test_fused_training_step_equals_autograd_route(lib, oracle_models):
     assert abs(float(out[1]) - float(dn_loss)) <= 1e-6 * max(1.0, float(dn_loss))
     assert abs(float(out[2]) - float(-10.0 * torch.log10(img_loss))) <= 1e-4
     for p, g in zip(params, fused):
-        assert float((p.grad - g).abs().max()) <= 1e-5 * float(g.abs().max()) + 1e-12   # split-K atomics reorder the last bits
+        # two 3xTF32 chains that round differently (the fused route runs the split backward, autograd the one-pass form)
+        assert float((p.grad - g).abs().max()) <= 2e-5 * float(g.abs().max()) + 1e-12
     for p in params:
         p.grad = None
 
