@@ -15,6 +15,7 @@
 #include "mlp_fast.cuh"
 #include "composite_tma.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 using namespace b200;
 
@@ -353,7 +354,7 @@ static int launch_exact(exact::ExactParams& p, const XProgram& pg, const void* w
     const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p, tm);
     if (e != cudaSuccess)
       return fail("mlp_exact_kernel<%s> launch failed: %s (rows %d, grid %d, index list %d)",
-                  INPUT == exact::IN_DEPTHNET ? "DEPTHNET" : (INPUT == exact::IN_NERF ? "NERF" : (INPUT == exact::IN_NERF_MASK ? "NERF+masks" : "NERF tangent")),
+                  INPUT == exact::IN_DEPTHNET ? "DEPTHNET" : (INPUT == exact::IN_NERF ? "NERF" : (INPUT == exact::IN_NERF_MASK ? "NERF+masks" : (INPUT == exact::IN_NERF_TAN ? "NERF tangent" : (INPUT == exact::IN_ACT ? "cat chain" : "cat chain Jacobian")))),
                   cudaGetErrorString(e), p.n_rows, grid, p.row_index != nullptr);
   }
   LAUNCH_CHECK();
@@ -1053,6 +1054,125 @@ extern "C" int b200nerf_nerf_point_jvp_packed(const void* wpack, const float* au
   if (launch_exact<exact::IN_NERF_MASK>(xp, pg, wpack, st)) return 1;
   xp.out = out_draw_dz;
   return launch_exact<exact::IN_NERF_TAN>(xp, pg, wpack, st);
+}
+
+// ------------------------------------------------------------------------------------------- cat-layer chain of the training step
+// (declarations and the reference lines in host_common.h / mlp_exact.cuh: IN_ACT, IN_JAC)
+static XProgram catchain_xprogram(int n_layers, bool forward) {
+  XProgram pg;
+  const XSeg none = {0, 0, nullptr, 0, 0, 0};
+  for (int i = 0; i < n_layers; ++i) {
+    XLayer l;
+    const bool last = i == n_layers - 1;
+    l.st = xstep(8, 0, 0, 0, 8, 8, 2, (forward && last) ? exact::EPI_DEPTH_OUT : exact::EPI_STORE, exact::ACT_LEAKY, 256u * i);
+    if (i == 0) {
+      l.st.wait_p = 1;   // input columns 0..127
+      l.st.wait_v = 2;   // input columns 128..255
+    }
+    if (last) {
+      l.st.sig_p = 1;
+      l.st.sig_v = 2;
+    }
+    l.n_out = 256;
+    l.segs[0] = XSeg{0, 16, nullptr, 256, 0, 256};
+    l.segs[1] = none;
+    l.n_segs = 1;
+    pg.layers.push_back(l);
+  }
+  return pg;
+}
+size_t b200_catchain_img_bytes(int n_layers) { return catchain_xprogram(n_layers, true).pack_bytes(); }
+size_t b200_catchain_aux_floats() { return exact::AUX_FLOATS; }
+size_t b200_catchain_mask_words(int n_layers, int n_rows) { return static_cast<size_t>(n_layers + 1) * static_cast<size_t>(n_rows) * 4; }
+
+struct ChainPackArgs {
+  const float* W[B200_CATCHAIN_MAX_LAYERS];    // forward image: layer l streams W[l]; transposed image: W[n_layers - 1 - l]^T
+  const float* b[B200_CATCHAIN_MAX_LAYERS];
+  const float* head_w;
+  const float* head_b;
+  int n_layers;
+};
+// The layout of pack_xprogram for 256 x 256 layers (per rank: layer -> [half 0: K blocks 0..7][half 1: 0..7][half 0: 8..15][half 1:
+// 8..15]; a block = hi piece | lo piece of this rank's 64 rows x 16 k), one element per thread.  blockIdx.y: 0 = W, 1 = W^T, 2 = aux.
+__global__ void __launch_bounds__(256) catchain_pack_kernel(const __grid_constant__ ChainPackArgs a, uint8_t* __restrict__ img_fwd,
+                                                            uint8_t* __restrict__ img_jac, float* __restrict__ aux) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.y == 2) {
+    if (t < exact::AUX_FLOATS) {
+      float v = 0.f;
+      const int l = t >> 8, c = t & 255;
+      if (l < a.n_layers) v = a.b[l][c];
+      else if (l == a.n_layers) v = a.head_w[c];
+      else if (l == a.n_layers + 1 && c == 0) v = a.head_b[0];
+      aux[t] = v;
+    }
+    return;
+  }
+  const int per_layer = 32 * 1024, per_rank = a.n_layers * per_layer;   // elements (one hi + one lo bf16 each)
+  if (t >= 2 * per_rank) return;
+  const int r = t / per_rank, rem0 = t % per_rank;
+  const int l = rem0 / per_layer, rem1 = rem0 % per_layer;
+  const int bi = rem1 >> 10, idx = rem1 & 1023;
+  const int range = bi >> 4, half = (bi >> 3) & 1, kb = range * 8 + (bi & 7);
+  const int kc = idx >> 9, rem = idx & 511;
+  const int n = (rem >> 6) * 8 + ((rem >> 3) & 7), e = rem & 7;
+  const int k = kb * 16 + kc * 8 + e, row = half * 128 + r * 64 + n;
+  const float w = blockIdx.y == 0 ? a.W[l][row * 256 + k] : a.W[a.n_layers - 1 - l][k * 256 + row];
+  const __nv_bfloat16 h = __float2bfloat16_rn(w);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(h));
+  uint8_t* img = blockIdx.y == 0 ? img_fwd : img_jac;
+  uint8_t* blk = img + (static_cast<size_t>(r) * per_rank + static_cast<size_t>(l) * per_layer + static_cast<size_t>(bi) * 1024) * 4;
+  reinterpret_cast<__nv_bfloat16*>(blk)[idx] = h;
+  reinterpret_cast<__nv_bfloat16*>(blk + 2048)[idx] = lo;
+}
+int b200_catchain_pack(const float* const* W, const float* const* b, const float* head_w, const float* head_b, int n_layers,
+                       void* img_fwd, void* img_jac, float* aux, cudaStream_t st) {
+  if (n_layers < 1 || n_layers > B200_CATCHAIN_MAX_LAYERS || n_layers > exact::MAX_STEPS) return fail("catchain pack: %d layers", n_layers);
+  ChainPackArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < n_layers; ++i) {
+    a.W[i] = W[i];
+    a.b[i] = b[i];
+  }
+  a.head_w = head_w;
+  a.head_b = head_b;
+  a.n_layers = n_layers;
+  const int elems = 2 * n_layers * 32 * 1024;
+  catchain_pack_kernel<<<dim3((elems + 255) / 256, 3), 256, 0, st>>>(a, static_cast<uint8_t*>(img_fwd), static_cast<uint8_t*>(img_jac), aux);
+  LAUNCH_CHECK();
+  return 0;
+}
+static void catchain_params(exact::ExactParams& xp, const float* aux, int n_layers, int n_rows, float near_, float far_) {
+  memset(&xp, 0, sizeof(xp));
+  xp.aux = aux;
+  xp.n_rows = n_rows;
+  xp.S = 1;
+  xp.head_w_off = 256 * n_layers;
+  xp.head_b_off = 256 * (n_layers + 1);
+  xp.near = near_;
+  xp.far = far_;
+  xp.mask_slope = 0.01f;
+}
+int b200_catchain_fwd(const void* img_fwd, const float* aux, int n_layers, const float* in_act, int n_rows, float near_, float far_,
+                      float* const* save, unsigned long long* mask, float* out_z, float* out_s, cudaStream_t st) {
+  exact::ExactParams xp;
+  catchain_params(xp, aux, n_layers, n_rows, near_, far_);
+  xp.in_act = in_act;
+  xp.mask = mask;
+  xp.out = out_z;
+  xp.out2 = out_s;
+  for (int i = 0; i < n_layers; ++i) xp.save[i] = save[i];
+  return launch_exact<exact::IN_ACT>(xp, catchain_xprogram(n_layers, true), img_fwd, st);
+}
+int b200_catchain_jac(const void* img_jac, const float* aux, int n_layers, const float* s, int n_rows, float near_, float far_,
+                      float* j_last, float* const* save, const unsigned long long* mask, cudaStream_t st) {
+  exact::ExactParams xp;
+  catchain_params(xp, aux, n_layers, n_rows, near_, far_);
+  xp.sgm = s;
+  xp.mask = const_cast<unsigned long long*>(mask);
+  xp.out2 = j_last;
+  for (int i = 0; i < n_layers; ++i) xp.save[i] = save[i];
+  return launch_exact<exact::IN_JAC>(xp, catchain_xprogram(n_layers, false), img_jac, st);
 }
 
 extern "C" int b200nerf_nerf_mlp_fwd(const void* wpack, const float* aux, int prec, const float* rays_o, const float* rays_d,

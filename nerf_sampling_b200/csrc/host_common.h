@@ -39,3 +39,20 @@ static inline bool b200_sync_check() {
     CUDA_TRY(cudaGetLastError());                             \
     if (b200_sync_check()) CUDA_TRY(cudaDeviceSynchronize()); \
   } while (0)
+
+// ---- DepthNet's activated cat layers of the training step on the fused split-precision MLP kernel (b200nerf.cu; called by train.cu) ----
+// n_layers LeakyReLU layers of 256 x 256 behind cat_layers.0 (+ the depth head for the forward).  The weights change every step, so
+// the bf16 hi / lo images the kernel streams (forward: W_j, backward: W_j^T) and the fp32 bias / head block are rebuilt on the device.
+constexpr int B200_CATCHAIN_MAX_LAYERS = 11;
+size_t b200_catchain_img_bytes(int n_layers);      // one image (forward or transposed)
+size_t b200_catchain_aux_floats();
+size_t b200_catchain_mask_words(int n_layers, int n_rows);   // 64-bit words
+// W[j], b[j]: device pointers of the n_layers weight [256,256] / bias [256] tensors; head_w [256], head_b [1]
+int b200_catchain_pack(const float* const* W, const float* const* b, const float* head_w, const float* head_b, int n_layers,
+                       void* img_fwd, void* img_jac, float* aux, cudaStream_t st);
+// in_act [n,256] -> save[j] = activations of layer j [n,256] (j < n_layers), out_z / out_s [n], masks
+int b200_catchain_fwd(const void* img_fwd, const float* aux, int n_layers, const float* in_act, int n_rows, float near_, float far_,
+                      float* const* save, unsigned long long* mask, float* out_z, float* out_s, cudaStream_t st);
+// J_last [n,256] = d z / d(pre-activation of the last layer); save[t] = J of layer n_layers - 1 - t's input side, t = 0 .. n_layers - 1
+int b200_catchain_jac(const void* img_jac, const float* aux, int n_layers, const float* s, int n_rows, float near_, float far_,
+                      float* j_last, float* const* save, const unsigned long long* mask, cudaStream_t st);

@@ -45,7 +45,13 @@ constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, PRO_WARP0 = 12, PRO_WARPS = 4;
 // under Trainer.core_optimization_loop) as two passes over the SAME packed weights.  The primal pass is IN_NERF plus one 64-bit
 // word per (layer, row, 64 columns) of ReLU masks; the tangent pass feeds d gamma(o + d z) / dz through the layers without biases,
 // t_k = mask_k * (W_k t_{k-1}), and writes the heads applied to the tangents.
-enum : int { IN_NERF = 0, IN_DEPTHNET = 1, IN_NERF_MASK = 2, IN_NERF_TAN = 3 };
+//
+// IN_ACT / IN_JAC: DepthNet's activated cat layers in the TRAINING step (depth_nets/depth_net.py:158-169 under
+// Trainer.core_optimization_loop), weights re-packed on the device every step.  IN_ACT: rows of fp32 activations in (the output of
+// cat_layers.0), the remaining LeakyReLU layers + head, every layer's activations saved in fp32 for the backward, one mask word
+// per (layer, row, 64 columns).  IN_JAC: the backward's input-gradient chain with a unit upstream gradient over the TRANSPOSED
+// weights, J_{j-1} = (J_j W_j) * LeakyReLU'(a_{j-1}), every J_j saved.  One launch each instead of ten grouped products.
+enum : int { IN_NERF = 0, IN_DEPTHNET = 1, IN_NERF_MASK = 2, IN_NERF_TAN = 3, IN_ACT = 4, IN_JAC = 5 };
 enum : uint8_t { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_MASK = 3 };
 enum : uint8_t {
   EPI_STORE = 0,        // bias + activation -> next layer's operand (hi/lo planes)
@@ -88,6 +94,12 @@ struct ExactParams {
   const int* n_rows_dev;  // optional: actual row count on the device
   uint8_t* scratch;       // DepthNet: per-CTA staging image of the next tile's encoded input (2 planes x 64 KB)
   unsigned long long* mask;   // IN_NERF_MASK writes / IN_NERF_TAN reads: [step][row][4] words, bit c = output column 64 g + c is > 0
+                              // IN_ACT writes [layer 0 .. n_steps][row][4] (layer 0 = the input rows), IN_JAC reads them
+  float* save[MAX_STEPS];     // IN_ACT / IN_JAC: fp32 copy of step s's output rows [rows, 256] (null: not saved)
+  const float* in_act;        // IN_ACT: input rows [rows, 256] fp32
+  const float* sgm;           // IN_JAC: s = sigmoid(head) per row (the head's derivative)
+  float* out2;                // IN_ACT: s per row;  IN_JAC: the loader's own rows, J of the last layer's pre-activation [rows, 256]
+  float mask_slope;           // ACT_MASK: factor of the columns whose bit is clear (0: ReLU, 0.01: LeakyReLU)
   uint32_t head_w_off, head_b_off;   // sigma head (NeRF) / depth head (DepthNet): 256 weights + bias
   uint32_t rgb_w_off, rgb_b_off;     // rgb head [3,128] + bias
   float radius, near, far;
@@ -224,10 +236,11 @@ __device__ __forceinline__ float act_apply(float x) {
 
 // 64 accumulator columns of one row: + bias, activation, optional heads, optional hi/lo operand store
 // WM: collect the ReLU mask of the 64 columns into `mask`; ACT_MASK: no bias, column c passes iff bit c of `mask` is set
-template <int EPI, int ACT, bool WM = false>
+// SAVE: fp32 copy of the 64 outputs to gsave
+template <int EPI, int ACT, bool WM = false, bool SAVE = false>
 __device__ __forceinline__ void epi_cols64(const uint32_t (&va)[32], const uint32_t (&vb)[32], const float* bias, const float* hw,
                                            const float* wr, uint8_t* dst, float& hsum, float& rs, float& gs, float& bs,
-                                           unsigned long long& mask) {
+                                           unsigned long long& mask, float mslope = 0.f, float* gsave = nullptr) {
   constexpr bool STORE = EPI == EPI_STORE || EPI == EPI_STORE_ALPHA;
   constexpr bool HEAD1 = EPI == EPI_STORE_ALPHA || EPI == EPI_DEPTH_OUT;
 #pragma unroll
@@ -240,7 +253,10 @@ __device__ __forceinline__ void epi_cols64(const uint32_t (&va)[32], const uint3
       if (ACT == ACT_MASK) {
         const uint32_t m8 = static_cast<uint32_t>(mask >> c) & 0xffu;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = (m8 >> i) & 1u ? __uint_as_float(cc == 0 ? va[j + i] : vb[j + i]) : 0.f;
+        for (int i = 0; i < 8; ++i) {
+          const float a = __uint_as_float(cc == 0 ? va[j + i] : vb[j + i]);
+          x[i] = (m8 >> i) & 1u ? a : a * mslope;
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = act_apply<ACT>(__uint_as_float(cc == 0 ? va[j + i] : vb[j + i]) + x[i]);
@@ -250,6 +266,10 @@ __device__ __forceinline__ void epi_cols64(const uint32_t (&va)[32], const uint3
 #pragma unroll
         for (int i = 0; i < 8; ++i) m8 |= (x[i] > 0.f ? 1u : 0u) << i;
         mask |= static_cast<unsigned long long>(m8) << c;
+      }
+      if (SAVE) {
+        *reinterpret_cast<float4*>(gsave + c) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(gsave + c + 4) = make_float4(x[4], x[5], x[6], x[7]);
       }
       if (HEAD1) {
         const float4 w0 = *reinterpret_cast<const float4*>(hw + c), w1 = *reinterpret_cast<const float4*>(hw + c + 4);
@@ -308,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
     mbar_init(&tail->tmem_free_b, EPI_WARPS * NCTA);
     mbar_init(&tail->ready_p, (INPUT == IN_DEPTHNET ? 1 : PRO_WARPS) * NCTA);
     mbar_init(&tail->ready_v, (INPUT == IN_DEPTHNET ? 1 : PRO_WARPS) * NCTA);
-    static_assert(INPUT == IN_NERF || INPUT == IN_DEPTHNET || INPUT == IN_NERF_MASK || INPUT == IN_NERF_TAN, "input mode");
+    static_assert(INPUT >= IN_NERF && INPUT <= IN_JAC, "input mode");
     mbar_init(&tail->in_full[0], 1);
     mbar_init(&tail->in_full[1], 1);
     mbar_init(&tail->free_p, 1);
@@ -463,7 +483,57 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
       const int tile = (cluster_id + u * n_clusters) * NCTA + static_cast<int>(rank);
       const int lrow = tile * TILE_M + row;
       const bool valid = lrow < n_rows;
-      if (INPUT != IN_DEPTHNET) {
+      if (INPUT == IN_ACT || INPUT == IN_JAC) {
+        // one thread per row: 256 fp32 values -> hi / lo operand planes, columns 0..127 then 128..255 (each half as soon as the
+        // previous tile has released it).  IN_ACT reads the rows; IN_JAC builds them: J = dt w_head LeakyReLU'(a_last), dt = (far - near) s (1 - s).
+        float dt = 0.f;
+        if (INPUT == IN_JAC && valid) {
+          const float sg = __ldg(p.sgm + lrow);
+          dt = (p.far - p.near) * sg * (1.0f - sg);
+        }
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+          if (u > 0) {
+            mbar_wait_lean(part == 0 ? free_p_addr : free_v_addr, (u - 1) & 1u);
+            tc_fence_after();
+          }
+#pragma unroll 1
+          for (int g = 0; g < 2; ++g) {
+            const int col0 = part * 128 + g * 64;
+            unsigned long long mbits = 0ull;
+            const size_t mi = ((static_cast<size_t>(INPUT == IN_JAC ? p.n_steps : 0) * p.n_rows + static_cast<size_t>(lrow)) << 2) + (col0 >> 6);
+            if (INPUT == IN_JAC && valid) mbits = __ldg(p.mask + mi);
+#pragma unroll 2
+            for (int ch = 0; ch < 8; ++ch) {
+              const int c = col0 + ch * 8;
+              float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (valid) {
+                if (INPUT == IN_ACT) {
+                  const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.in_act + static_cast<size_t>(lrow) * 256 + c));
+                  const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.in_act + static_cast<size_t>(lrow) * 256 + c + 4));
+                  v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+                  uint32_t m8 = 0;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) m8 |= (v[i] > 0.f ? 1u : 0u) << i;
+                  mbits |= static_cast<unsigned long long>(m8) << (ch * 8);
+                } else {
+                  const uint32_t m8 = static_cast<uint32_t>(mbits >> (ch * 8)) & 0xffu;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = dt * saux[p.head_w_off + c + i] * ((m8 >> i) & 1u ? 1.0f : p.mask_slope);
+                  float* o = p.out2 + static_cast<size_t>(lrow) * 256 + c;
+                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+              }
+              store_split8(act + (c >> 3) * KC_STRIDE + row_off, v);
+            }
+            if (INPUT == IN_ACT && valid) p.mask[mi] = mbits;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(part == 0 ? rp_bar : rv_bar);
+        }
+      } else if (INPUT != IN_DEPTHNET) {
         const int grow = valid ? (p.row_index != nullptr ? __ldg(p.row_index + lrow) : lrow) : 0;
         const int ray = grow / p.S;
         float x[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
@@ -591,8 +661,14 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
           const int col0 = half * 128 + sub * 64;           // first accumulator / layer-output column of this thread
           const float* bias = saux + st.bias_off + col0;
           unsigned long long mbits = 0ull;
-          const size_t midx = ((static_cast<size_t>(s) * p.n_rows + static_cast<size_t>(lrow)) << 2) + (col0 >> 6);
-          if (TAN && valid) mbits = __ldg(p.mask + midx);
+          // mask layer of this step's output: the step itself (NeRF), s + 1 (IN_ACT: layer 0 is the input), n_steps - 1 - s (IN_JAC:
+          // step s produces the gradient of layer n_steps - 1 - s's pre-activation)
+          const int mlayer = INPUT == IN_ACT ? s + 1 : (INPUT == IN_JAC ? p.n_steps - 1 - s : s);
+          const size_t midx = ((static_cast<size_t>(mlayer) * p.n_rows + static_cast<size_t>(lrow)) << 2) + (col0 >> 6);
+          if ((TAN || INPUT == IN_JAC) && valid) mbits = __ldg(p.mask + midx);
+          // out-of-range rows of the last tile save into a row that exists (their values are zeros or garbage nobody reads): row 0
+          float* gsave = (INPUT == IN_ACT || INPUT == IN_JAC) && p.save[s] != nullptr
+                             ? p.save[s] + static_cast<size_t>(valid ? lrow : 0) * 256 + col0 : nullptr;
           uint32_t va[32], vb[32];
           tmem_ld_32x32b_x32(t_lane + col0, va);
           tmem_ld_32x32b_x32(t_lane + col0 + 32, vb);
@@ -609,7 +685,21 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
           const float* wr = saux + p.rgb_w_off + col0;
           uint8_t* dst = act + (col0 >> 3) * KC_STRIDE + row_off;
           float hsum = 0.f, rs = 0.f, gs = 0.f, bs = 0.f;
-          if (TAN) {
+          if (INPUT == IN_ACT) {
+            if (!valid) gsave = nullptr;
+            if (st.epi == EPI_STORE) {
+              if (gsave) epi_cols64<EPI_STORE, ACT_LEAKY, true, true>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits, 0.f, gsave);
+              else epi_cols64<EPI_STORE, ACT_LEAKY, true, false>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
+            } else {
+              if (gsave) epi_cols64<EPI_DEPTH_OUT, ACT_LEAKY, true, true>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits, 0.f, gsave);
+              else epi_cols64<EPI_DEPTH_OUT, ACT_LEAKY, true, false>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
+            }
+            if (valid) p.mask[midx] = mbits;
+          } else if (INPUT == IN_JAC) {
+            if (!valid) gsave = nullptr;
+            if (gsave) epi_cols64<EPI_STORE, ACT_MASK, false, true>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits, p.mask_slope, gsave);
+            else epi_cols64<EPI_STORE, ACT_MASK, false, false>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits, p.mask_slope);
+          } else if (TAN) {
             if (st.epi == EPI_STORE) epi_cols64<EPI_STORE, ACT_MASK>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
             else if (st.epi == EPI_STORE_ALPHA) epi_cols64<EPI_STORE_ALPHA, ACT_MASK>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
             else epi_cols64<EPI_NERF_OUT, ACT_MASK>(va, vb, bias, hw, wr, dst, hsum, rs, gs, bs, mbits);
@@ -671,6 +761,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
               const float sg = 1.0f / (1.0f + expf(-t));
               // near*(1-s) + far*s with every product / sum rounded separately (depth_net.py:168)
               p.out[grow] = __fadd_rn(__fmul_rn(p.near, __fadd_rn(1.0f, -sg)), __fmul_rn(p.far, sg));
+              if (INPUT == IN_ACT) p.out2[grow] = sg;
             }
             named_bar_sync(1, EPI_WARPS * 32);   // head_part may be rewritten by the next tile
           }

@@ -809,6 +809,7 @@ struct DnWs {             // float offsets into the workspace
   size_t g0, g1, g2;           // gradient scratch, [n, maxw] each
   size_t gx[6];                // per-branch ping/pong scratch of the grouped backward
   std::vector<size_t> jac;     // J_j = d z / d(pre-activation of cat layer j) per ray (the split backward)
+  size_t img_fwd, img_jac, aux, mask;   // fused cat chain: bf16 hi / lo weight images (W_j, W_j^T), fp32 bias / head block, sign masks
   size_t Aaug[3], Raug[3], G[3], gv[3], c_last[3];   // collapsed-branch chain matrices (weights only, no ray dimension)
 };
 static DnWs dn_layout(const DnArch& ar, size_t n) {
@@ -829,6 +830,13 @@ static DnWs dn_layout(const DnArch& ar, size_t n) {
   w.g2 = take(n * maxw);
   for (int i = 0; i < 6; ++i) w.gx[i] = take(n * maxw);
   for (int j = 0; j < ar.nc; ++j) w.jac.push_back(take(n * ar.c[j]));
+  {
+    const int nl = ar.nc > 1 ? ar.nc - 1 : 1;
+    w.img_fwd = take(b200_catchain_img_bytes(nl) / 4);
+    w.img_jac = take(b200_catchain_img_bytes(nl) / 4);
+    w.aux = take(b200_catchain_aux_floats());
+    w.mask = take(2 * b200_catchain_mask_words(nl, static_cast<int>(n)));
+  }
   for (int b = 0; b < 3; ++b) {
     w.Aaug[b] = take(static_cast<size_t>(ar.nb) * CH_MAXH * CH_LD);
     w.Raug[b] = take(static_cast<size_t>(ar.nb) * CH_MAXH * CH_LD);
@@ -861,6 +869,18 @@ static bool can_collapse(const DnArch& ar, int n, const float* const* params) {
   for (int b = 0; b < 3; ++b)
     for (int i = 0; i < ar.nb; ++i)
       if (reinterpret_cast<uintptr_t>(params[pidx_branch(ar, b, i)]) & 15) return false;
+  return true;
+}
+// The activated cat layers behind cat_layers.0 as ONE launch of the fused split-precision MLP kernel (forward: with saved activations;
+// split backward: the Jacobian chain over the transposed weights) instead of one grouped product per layer.  Needs 256-wide layers;
+// B200NERF_TRAIN_CHAIN=gemm keeps the per-layer 3xTF32 products (A/B measurements, and the reference point of the tests).
+static bool fused_chain_ok(const DnArch& ar, int n, const float* const* params) {
+  const char* e = getenv("B200NERF_TRAIN_CHAIN");   // read per call: the tests run both routes in one process
+  if ((e && strcmp(e, "gemm") == 0) || !can_collapse(ar, n, params) || ar.nc < 2 || ar.nc - 1 > B200_CATCHAIN_MAX_LAYERS) return false;
+  for (int c : ar.c)
+    if (c != 256) return false;
+  for (int j = 0; j < ar.nc; ++j)
+    if (reinterpret_cast<uintptr_t>(params[pidx_cat(ar, j)]) & 15) return false;
   return true;
 }
 static int chain_configure() {
@@ -984,6 +1004,22 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
       for (int b = 0; b < 3; ++b) seg_fwd(q, ws + w.xb[b][ar.nb - 1], hl, W, ldw, b * hl, hl);
       seg_fwd(q, E, 252, W, ldw, 3 * hl, 252);
       if (tgemm_group(st, &q, 1)) return 1;
+    }
+    if (fused_chain_ok(ar, n, params)) {
+      // cat_layers.1 .. nc-1 + head in one launch: this step's weights -> bf16 hi / lo images (W_j for this pass, W_j^T for the
+      // Jacobian pass), then the chain with every layer's activations saved for the backward
+      const int nl = ar.nc - 1;
+      const float* Wl[B200_CATCHAIN_MAX_LAYERS];
+      const float* bl[B200_CATCHAIN_MAX_LAYERS];
+      float* save[B200_CATCHAIN_MAX_LAYERS];
+      for (int j = 1; j < ar.nc; ++j) {
+        Wl[j - 1] = params[pidx_cat(ar, j)];
+        bl[j - 1] = params[pidx_cat(ar, j) + 1];
+        save[j - 1] = ws + w.a[j];
+      }
+      if (b200_catchain_pack(Wl, bl, params[pidx_head(ar)], params[pidx_head(ar) + 1], nl, ws + w.img_fwd, ws + w.img_jac, ws + w.aux, st)) return 1;
+      return b200_catchain_fwd(ws + w.img_fwd, ws + w.aux, nl, ws + w.a[0], n, near_, far_, save,
+                               reinterpret_cast<unsigned long long*>(ws + w.mask), out_z, ws + w.s, st);
     }
     for (int j = 1; j < ar.nc; ++j) {
       GemmProb q = prob_fwd(n, ar.c[j], ws + w.a[j], ar.c[j], params[pidx_cat(ar, j) + 1], 1, 0.01f);
@@ -1265,14 +1301,24 @@ extern "C" int b200nerf_depthnet_train_jac(const float* const* params, int n_bra
   const int ph = pidx_head(ar);
   if (zero_grads(ar, grads, st)) return 1;
   CUDA_TRY(cudaMemsetAsync(ws + w.G[0], 0, (w.gv[2] + CH_MAXH - w.G[0]) * sizeof(float), st));
-  depth_head_bwd_fused_kernel<<<(n + HEAD_ROWS - 1) / HEAD_ROWS, 256, 0, st>>>(nullptr, ws + w.s, ws + w.a[ar.nc - 1], params[ph], n, cl, near_,
-                                                                            far_, 0.01f, ws + w.jac[ar.nc - 1], nullptr, nullptr);
-  LAUNCH_CHECK();
-  for (int j = ar.nc - 1; j >= 1; --j) {
-    const int pc = pidx_cat(ar, j);
-    GemmProb q = prob_dgrad(n, ar.c[j], ar.c[j - 1], ws + w.jac[j], ar.c[j], params[pc], ar.c[j - 1], 0, ws + w.jac[j - 1], ar.c[j - 1],
-                            ws + w.a[j - 1], ar.c[j - 1], 0.01f);
-    if (tgemm_group(st, &q, 1)) return 1;
+  if (fused_chain_ok(ar, n, params)) {
+    // the whole chain in one launch over the transposed images the forward pass packed; step t turns J_{nc-1-t} into J_{nc-2-t}
+    const int nl = ar.nc - 1;
+    float* save[B200_CATCHAIN_MAX_LAYERS];
+    for (int t = 0; t < nl; ++t) save[t] = ws + w.jac[ar.nc - 2 - t];
+    if (b200_catchain_jac(ws + w.img_jac, ws + w.aux, nl, ws + w.s, n, near_, far_, ws + w.jac[ar.nc - 1], save,
+                          reinterpret_cast<const unsigned long long*>(ws + w.mask), st))
+      return 1;
+  } else {
+    depth_head_bwd_fused_kernel<<<(n + HEAD_ROWS - 1) / HEAD_ROWS, 256, 0, st>>>(nullptr, ws + w.s, ws + w.a[ar.nc - 1], params[ph], n, cl, near_,
+                                                                              far_, 0.01f, ws + w.jac[ar.nc - 1], nullptr, nullptr);
+    LAUNCH_CHECK();
+    for (int j = ar.nc - 1; j >= 1; --j) {
+      const int pc = pidx_cat(ar, j);
+      GemmProb q = prob_dgrad(n, ar.c[j], ar.c[j - 1], ws + w.jac[j], ar.c[j], params[pc], ar.c[j - 1], 0, ws + w.jac[j - 1], ar.c[j - 1],
+                              ws + w.a[j - 1], ar.c[j - 1], 0.01f);
+      if (tgemm_group(st, &q, 1)) return 1;
+    }
   }
   const int pc0 = pidx_cat(ar, 0), ldw0 = 3 * hl + 252;
   GemmProb q[3];

@@ -483,15 +483,26 @@ def test_training_step_gradients_match_golden(lib, b200_models):
         p.grad = None
 
 
-def test_depthnet_literal_forward_and_backward_vs_torch(lib, oracle_models):
-    """The fp32 training form of DepthNet against the oracle's literal forward differentiated by torch autograd."""
+@pytest.mark.parametrize("chain,H,W", [("gemm", 9, 13), ("fused", 9, 13), ("fused", 40, 50)])
+def test_depthnet_literal_forward_and_backward_vs_torch(lib, oracle_models, chain, H, W, monkeypatch):
+    """The training form of DepthNet against the oracle's literal forward differentiated by torch autograd.  "gemm": every layer a
+    3xTF32 product (2^-20 per link); "fused": the activated cat layers as ONE launch of the split-precision MLP kernel (bf16 hi + lo
+    operands, 2^-17 per link; its saved activations agree with the 3xTF32 ones to 5e-6, tools/chain_diag.py).
+
+    The derivative of a LeakyReLU network jumps where a pre-activation changes sign.  A hidden value within rounding distance of
+    zero may take the other slope than torch's; that changes ONE ray's contribution to one row of a weight gradient by ~100 %, i.e.
+    the row by ~1 / n_rays.  With 2^-17 links this happens for about 3 of 1000 rays x 2560 hidden values (0 or 1 of the 117 rays of
+    the small case: observed 1e-2 of the tensor's largest entry when it does), so the fused route is held to the 2e-3 bound on 2000
+    rays and to 2 / n_rays on 117; at the 4096 rays of BASELINE config #5 a flip moves a gradient by 2.4e-4
+    (test_training_step_4096_rays_all_gradients_vs_autograd: worst tensor 4.4e-4 with either route)."""
     from nerf_sampling_b200.depth_nets import DepthNet
 
+    monkeypatch.setenv("B200NERF_TRAIN_CHAIN", chain)
     _, _, dn = oracle_models
     m = DepthNet(hidden_sizes=[256] * 10, cat_hidden_sizes=[256] * 10, sphere_radius=2.0)
     m.load_state_dict(dn)
     m.to(DEV)
-    _, packed = scene_rays(9, 13)
+    _, packed = scene_rays(H, W)
     ro, rd = packed[:, 0:3].contiguous().to(DEV), packed[:, 3:6].contiguous().to(DEV)
     z = m(ro, rd)
     w = torch.linspace(0.5, 1.5, z.numel(), device=DEV).reshape(z.shape)  # one sign: no cancellation in the bias sums
@@ -500,9 +511,13 @@ def test_depthnet_literal_forward_and_backward_vs_torch(lib, oracle_models):
     zr = O.depthnet_forward(ref, ro, rd)
     (zr * w).sum().backward()
     assert float((z - zr).abs().max()) <= 1e-5
+    tol = 2e-3 if (chain == "gemm" or H * W >= 2000) else 2.0 / (H * W)
+    worst = ("", 0.0)
     for k, p in m.named_parameters():
         want = ref[k].grad
-        assert float((p.grad - want).abs().max()) <= 2e-3 * float(want.abs().max()) + 1e-7, k  # sums with cancellation
+        worst = max(worst, (k, float((p.grad - want).abs().max()) / (float(want.abs().max()) + 1e-12)), key=lambda t: t[1])
+        assert float((p.grad - want).abs().max()) <= tol * float(want.abs().max()) + 1e-7, k  # sums with cancellation
+    print(f"DepthNet training form, chain={chain}, {H * W} rays: worst tensor {worst[0]} {worst[1]:.2e} of its largest entry")
 
 
 @pytest.mark.parametrize("route,side", [("fp32", 8), ("split", 8), ("split", 37)])

@@ -248,8 +248,8 @@ def test_fused_training_step_equals_autograd_route(lib, oracle_models):
     assert abs(float(out[1]) - float(dn_loss)) <= 1e-6 * max(1.0, float(dn_loss))
     assert abs(float(out[2]) - float(-10.0 * torch.log10(img_loss))) <= 1e-4
     for p, g in zip(params, fused):
-        # two 3xTF32 chains that round differently (the fused route runs the split backward, autograd the one-pass form)
-        assert float((p.grad - g).abs().max()) <= 2e-5 * float(g.abs().max()) + 1e-12
+        # the fused route runs the split backward (Jacobian chain on the split-precision MLP kernel), autograd the one-pass 3xTF32 form
+        assert float((p.grad - g).abs().max()) <= 1e-4 * float(g.abs().max()) + 1e-12
     for p in params:
         p.grad = None
 
@@ -293,7 +293,9 @@ def test_split_backward_equals_one_pass_backward(lib, oracle_models, n):
         assert bool(torch.isfinite(b).all())
         worst = max(worst, float((a - b).abs().max()) / (float(a.abs().max()) + 1e-20))
     print(f"split backward vs one-pass backward, {n} rays: worst tensor rel max-abs difference {worst:.2e}")
-    assert worst <= 2e-5      # both are 3xTF32 chains (2^-20 per link); they round differently, not less accurately
+    # the one-pass backward walks the input-gradient chain as 3xTF32 products, the split one as ONE launch of the split-precision
+    # MLP kernel (bf16 hi + lo operands, ~2^-17 per link): observed 2e-5 .. 3e-5 of a tensor's largest entry
+    assert worst <= 1e-4
 
 
 # ------------------------------------------------------------------------------------------- render.py flags and the -e sweep
