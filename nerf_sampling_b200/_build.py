@@ -10,7 +10,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("B200NERF_LIB") or os.path.join(PKG_DIR, "libb200nerf.so")
 SOURCES = ["b200nerf.cu", "sampling.cu", "train.cu"]
-HEADERS = ["ptx.cuh", "umma_selftest.cuh", "mlp_fast.cuh", "mlp_exact.cuh", "composite_tma.cuh", "tgemm.cuh", "host_common.h", os.path.join("..", "..", "include", "b200nerf.h")]
+HEADERS = ["ptx.cuh", "umma_selftest.cuh", "mlp_fast.cuh", "mlp_exact.cuh", "composite_tma.cuh", "tgemm.cuh", "tgemm_reg.cuh", "host_common.h", os.path.join("..", "..", "include", "b200nerf.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

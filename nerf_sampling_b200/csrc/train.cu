@@ -18,6 +18,7 @@
 #include "../../include/b200nerf.h"
 #include "host_common.h"
 #include "tgemm.cuh"
+#include "tgemm_reg.cuh"
 
 // ------------------------------------------------------------------------------------------- strided SGEMM
 // C[M,N] (row-major, ldc) = (beta ? C : 0) + sum_k A(m,k) * B(k,n) [+ bias[n]] [then LeakyReLU(slope) if act]
@@ -163,6 +164,7 @@ static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
   if (dev < 0) return b200_fail("tgemm_group: no usable CUDA device");
   if (sm_counts[dev] == 0) {
     CUDA_TRY(cudaFuncSetAttribute(tg::tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(b200::tgr::tgemm_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b200::tgr::SMEM_BYTES));
     CUDA_TRY(cudaDeviceGetAttribute(&sm_counts[dev], cudaDevAttrMultiProcessorCount, dev));
   }
   const int g_sm_count = sm_counts[dev];
@@ -226,13 +228,22 @@ static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    // single-wave launches: the staged kernel (one CTA per SM, operands three chunks ahead); launches of many waves: the register
+    // form, two CTAs per SM (tgemm_reg.cuh).  B200NERF_TGEMM=staged / reg forces one of them (A/B measurements).
+    static int form = -1;
+    if (form < 0) {
+      const char* e = getenv("B200NERF_TGEMM");
+      form = (e && strcmp(e, "staged") == 0) ? 1 : ((e && strcmp(e, "reg") == 0) ? 2 : 0);
+    }
+    const bool reg_form = form == 2 || (form == 0 && cta > 2 * g_sm_count);
     cfg.gridDim = dim3(cta);
     cfg.blockDim = dim3(tg::CTA_THREADS);
-    cfg.dynamicSmemBytes = tg::SMEM_BYTES;
+    cfg.dynamicSmemBytes = reg_form ? b200::tgr::SMEM_BYTES : tg::SMEM_BYTES;
     cfg.stream = st;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, tg::tgemm_kernel, g));
+    if (reg_form) CUDA_TRY(cudaLaunchKernelEx(&cfg, b200::tgr::tgemm_reg_kernel, g));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, tg::tgemm_kernel, g));
   }
   LAUNCH_CHECK();
   return 0;

@@ -164,7 +164,7 @@ def nerf_params(module) -> List[torch.nn.Parameter]:
 
 # Persistent-grid cap (in SMs) of the frozen target render while the DepthNet / JVP chain of the same step runs on a side stream;
 # 0 runs the step on one stream.  B200NERF_TARGET_SMS overrides (measurement).
-TARGET_SM_LIMIT = int(__import__("os").environ.get("B200NERF_TARGET_SMS", "128"))
+TARGET_SM_LIMIT = int(__import__("os").environ.get("B200NERF_TARGET_SMS", "148"))
 # The backward split at the losses (b200nerf_depthnet_train_jac / _bwd_jac): the sequential input-gradient chain runs with a unit
 # upstream gradient in front of the losses -- on a third stream beside d raw / d z (THIRD_STREAM) -- and the weight-only branch
 # chain beside the weight gradients after them (FORK_BRANCH_CHAIN).  Measured per graphed step, one-pass -> split:
