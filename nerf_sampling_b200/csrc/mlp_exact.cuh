@@ -227,6 +227,14 @@ __device__ __forceinline__ void encode_store_img(const float (&x)[3], uint8_t* d
   }
 }
 
+// eight consecutive floats as ONE 256-bit store (STG.E.256: a full 32-byte sector per lane and instruction; the rows of a tile are
+// 1 KB apart, so the lanes of a warp can never share a sector)
+__device__ __forceinline__ void st_global_v8(float* p, const float (&x)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]), "f"(x[4]),
+               "f"(x[5]), "f"(x[6]), "f"(x[7])
+               : "memory");
+}
+
 template <int ACT>
 __device__ __forceinline__ float act_apply(float x) {
   if (ACT == ACT_RELU) return fmaxf(x, 0.f);
@@ -267,10 +275,7 @@ __device__ __forceinline__ void epi_cols64(const uint32_t (&va)[32], const uint3
         for (int i = 0; i < 8; ++i) m8 |= (x[i] > 0.f ? 1u : 0u) << i;
         mask |= static_cast<unsigned long long>(m8) << c;
       }
-      if (SAVE) {
-        *reinterpret_cast<float4*>(gsave + c) = make_float4(x[0], x[1], x[2], x[3]);
-        *reinterpret_cast<float4*>(gsave + c + 4) = make_float4(x[4], x[5], x[6], x[7]);
-      }
+      if (SAVE) st_global_v8(gsave + c, x);
       if (HEAD1) {
         const float4 w0 = *reinterpret_cast<const float4*>(hw + c), w1 = *reinterpret_cast<const float4*>(hw + c + 4);
         const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -520,9 +525,7 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
                   const uint32_t m8 = static_cast<uint32_t>(mbits >> (ch * 8)) & 0xffu;
 #pragma unroll
                   for (int i = 0; i < 8; ++i) v[i] = dt * saux[p.head_w_off + c + i] * ((m8 >> i) & 1u ? 1.0f : p.mask_slope);
-                  float* o = p.out2 + static_cast<size_t>(lrow) * 256 + c;
-                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                  *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                  st_global_v8(p.out2 + static_cast<size_t>(lrow) * 256 + c, v);
                 }
               }
               store_split8(act + (c >> 3) * KC_STRIDE + row_off, v);

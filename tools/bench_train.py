@@ -31,7 +31,7 @@ tr.H, tr.W, tr.K, tr.chunk = bench.H, bench.W, bench.intrinsics(), 32768
 kw = dict(network_fn=coarse, network_fine=fine, depth_network=dn, network_query_fn=None, N_samples=64, N_importance=128,
           trainer=tr, white_bkgd=True, raw_noise_std=0.0, perturb=0.0, lindisp=True, ndc=False, near=2.0, far=6.0,
           use_viewdirs=True, model_mode="train")
-n_total = 4096
+n_total = int(sys.argv[sys.argv.index("--rays") + 1]) if "--rays" in sys.argv else 4096
 per = n_total // world
 ro, rd, _ = ops.get_rays(bench.H, bench.W, bench.intrinsics(), bench.pose_for_step(0), dev)
 sel = torch.randperm(ro.shape[0], generator=torch.Generator().manual_seed(0))[:n_total][rank * per:(rank + 1) * per].to(dev)
@@ -60,6 +60,7 @@ if world > 1:
 if rank == 0:
     print(json.dumps({"metric": "train_steps_per_sec", "value": 1e3 / float(ms), "ms_per_step": float(ms), "rays_per_step": n_total,
                       "rays_per_sec": n_total * 1e3 / float(ms), "n_gpus": world, "cuda_graph": use_graph, "loss": float(out[0]), "depth_net_loss": float(out[1]),
-                      "config": "DepthNet training step, 4096 rays/batch, 64+128 hierarchical target, data parallel (BASELINE config #5)"}))
+                      "config": "DepthNet training step, %d rays/batch, 64+128 hierarchical target, data parallel (BASELINE config #5)" % n_total,
+                      "switches": {k: v for k, v in os.environ.items() if k.startswith("B200NERF_")}}))
 if world > 1:
     dist.destroy_process_group()

@@ -1,6 +1,5 @@
-"""Two eager training steps (config #5 shapes) for ncu: `ncu --set full -k regex:"tgemm|chain_" --launch-skip 36 -c 36 python tools/profile_train.py`
-captures the 33 grouped-GEMM and 3 chain launches of the second step (launch order: chain_fwd, branch product, cat_layers.0, 9 cat layers, the
-11 NeRF point JVP groups, 9 cat backward groups, cat_layers.0 backward, the G reduction, chain_bwd, chain_du)."""
+"""Two eager training steps (config #5 shapes) for ncu: `ncu --set full -k regex:"tgemm|chain|mlp_exact" --launch-skip 16 -c 16 python
+tools/profile_train.py` captures the 16 matching launches of the second step (see tools/gpu_profile.sh for the order)."""
 import os
 import sys
 
