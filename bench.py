@@ -389,9 +389,10 @@ def bench_config5(models, dev, world, rank, steps=20):
             for p, s0 in zip(models[2].parameters(), saved):
                 p.copy_(s0)
     out.update({"n_gpus": world, "rays_per_step": n_total, "steps": steps,
-                "workload": "core_optimization_loop: 64 + 192 hierarchical target on the frozen NeRFs, DepthNet fwd/bwd (3xTF32 on "
-                            "tcgen05), colour gradient through the frozen fine NeRF, flat NCCL all-reduce, fused Adam; 'graph' = the "
-                            "whole step (collective and Adam included) replayed as one CUDA graph"})
+                "workload": "core_optimization_loop: 64 + 192 hierarchical target on the frozen NeRFs, DepthNet fwd/bwd (cat layers and their "
+                            "Jacobian chain as single launches of the split-precision tensor-core MLP kernel, the other products 3xTF32 on "
+                            "tcgen05), colour gradient through the frozen fine NeRF (two launches of the same kernel), flat NCCL "
+                            "all-reduce, fused Adam; 'graph' = the whole step (collective and Adam included) replayed as one CUDA graph"})
     return out
 
 

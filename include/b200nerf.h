@@ -217,7 +217,10 @@ int b200nerf_argmax_gather(const float* weights, const float* z, const float* ra
 
 /* ---- training (config #5: Trainer.core_optimization_loop, trainers/Trainer.py:506-544) --------------------------- */
 
-/* DepthNet in its literal per-layer form with saved activations (depth_nets/depth_net.py:117-169), fp32.
+/* DepthNet's training forward with saved activations (depth_nets/depth_net.py:117-169): the activation-free branches collapsed to
+ * weight-only recurrences (fp32), the branch product and cat_layers.0 as error-compensated 3xTF32 products, the 256-wide activated
+ * cat layers behind it + the head as ONE launch of the split-precision tensor-core MLP kernel (bf16 hi + lo operands, fp32
+ * accumulate; B200NERF_TRAIN_CHAIN=gemm: per-layer 3xTF32 products; B200NERF_TRAIN_GEMM=fp32: CUDA-core fp32 everywhere).
  * `params` = device pointers of the state_dict tensors in order: origin_layers.{i}.{weight,bias} (n_branch layers of
  * widths hidden[]), direction_layers..., intersection_layers..., cat_layers.{2j}.{weight,bias} (n_cat layers of widths
  * cat_hidden[]), to_depth.0.{weight,bias}: b200nerf_depthnet_n_params() pointers.  `ws` holds

@@ -1090,6 +1090,7 @@ struct ChainPackArgs {
   const float* b[B200_CATCHAIN_MAX_LAYERS];
   const float* head_w;
   const float* head_b;
+  const float* in_bias;
   int n_layers;
 };
 // The layout of pack_xprogram for 256 x 256 layers (per rank: layer -> [half 0: K blocks 0..7][half 1: 0..7][half 0: 8..15][half 1:
@@ -1104,6 +1105,7 @@ __global__ void __launch_bounds__(256) catchain_pack_kernel(const __grid_constan
       if (l < a.n_layers) v = a.b[l][c];
       else if (l == a.n_layers) v = a.head_w[c];
       else if (l == a.n_layers + 1 && c == 0) v = a.head_b[0];
+      else if (l == a.n_layers + 2 && a.in_bias != nullptr) v = a.in_bias[c];
       aux[t] = v;
     }
     return;
@@ -1125,9 +1127,10 @@ __global__ void __launch_bounds__(256) catchain_pack_kernel(const __grid_constan
   reinterpret_cast<__nv_bfloat16*>(blk)[idx] = h;
   reinterpret_cast<__nv_bfloat16*>(blk + 2048)[idx] = lo;
 }
-int b200_catchain_pack(const float* const* W, const float* const* b, const float* head_w, const float* head_b, int n_layers,
-                       void* img_fwd, void* img_jac, float* aux, cudaStream_t st) {
+int b200_catchain_pack(const float* const* W, const float* const* b, const float* head_w, const float* head_b, const float* in_bias,
+                       int n_layers, void* img_fwd, void* img_jac, float* aux, cudaStream_t st) {
   if (n_layers < 1 || n_layers > B200_CATCHAIN_MAX_LAYERS || n_layers > exact::MAX_STEPS) return fail("catchain pack: %d layers", n_layers);
+  if (in_bias != nullptr && 256 * (n_layers + 3) > exact::AUX_FLOATS) return fail("catchain pack: no room for the input bias with %d layers", n_layers);
   ChainPackArgs a;
   memset(&a, 0, sizeof(a));
   for (int i = 0; i < n_layers; ++i) {
@@ -1136,6 +1139,7 @@ int b200_catchain_pack(const float* const* W, const float* const* b, const float
   }
   a.head_w = head_w;
   a.head_b = head_b;
+  a.in_bias = in_bias;
   a.n_layers = n_layers;
   const int elems = 2 * n_layers * 32 * 1024;
   catchain_pack_kernel<<<dim3((elems + 255) / 256, 3), 256, 0, st>>>(a, static_cast<uint8_t*>(img_fwd), static_cast<uint8_t*>(img_jac), aux);
@@ -1153,11 +1157,12 @@ static void catchain_params(exact::ExactParams& xp, const float* aux, int n_laye
   xp.far = far_;
   xp.mask_slope = 0.01f;
 }
-int b200_catchain_fwd(const void* img_fwd, const float* aux, int n_layers, const float* in_act, int n_rows, float near_, float far_,
-                      float* const* save, unsigned long long* mask, float* out_z, float* out_s, cudaStream_t st) {
+int b200_catchain_fwd(const void* img_fwd, const float* aux, int n_layers, float* in_act, bool in_is_preact, int n_rows, float near_,
+                      float far_, float* const* save, unsigned long long* mask, float* out_z, float* out_s, cudaStream_t st) {
   exact::ExactParams xp;
   catchain_params(xp, aux, n_layers, n_rows, near_, far_);
   xp.in_act = in_act;
+  xp.in_bias_off = in_is_preact ? 256 * (n_layers + 2) : -1;
   xp.mask = mask;
   xp.out = out_z;
   xp.out2 = out_s;
@@ -1169,6 +1174,7 @@ int b200_catchain_jac(const void* img_jac, const float* aux, int n_layers, const
   exact::ExactParams xp;
   catchain_params(xp, aux, n_layers, n_rows, near_, far_);
   xp.sgm = s;
+  xp.in_bias_off = -1;
   xp.mask = const_cast<unsigned long long*>(mask);
   xp.out2 = j_last;
   for (int i = 0; i < n_layers; ++i) xp.save[i] = save[i];

@@ -47,12 +47,14 @@ constexpr int B200_CATCHAIN_MAX_LAYERS = 11;
 size_t b200_catchain_img_bytes(int n_layers);      // one image (forward or transposed)
 size_t b200_catchain_aux_floats();
 size_t b200_catchain_mask_words(int n_layers, int n_rows);   // 64-bit words
-// W[j], b[j]: device pointers of the n_layers weight [256,256] / bias [256] tensors; head_w [256], head_b [1]
-int b200_catchain_pack(const float* const* W, const float* const* b, const float* head_w, const float* head_b, int n_layers,
-                       void* img_fwd, void* img_jac, float* aux, cudaStream_t st);
-// in_act [n,256] -> save[j] = activations of layer j [n,256] (j < n_layers), out_z / out_s [n], masks
-int b200_catchain_fwd(const void* img_fwd, const float* aux, int n_layers, const float* in_act, int n_rows, float near_, float far_,
-                      float* const* save, unsigned long long* mask, float* out_z, float* out_s, cudaStream_t st);
+// W[j], b[j]: device pointers of the n_layers weight [256,256] / bias [256] tensors; head_w [256], head_b [1]; in_bias [256] or null:
+// the bias of the layer in FRONT of the chain, for b200_catchain_fwd(in_is_preact = true)
+int b200_catchain_pack(const float* const* W, const float* const* b, const float* head_w, const float* head_b, const float* in_bias,
+                       int n_layers, void* img_fwd, void* img_jac, float* aux, cudaStream_t st);
+// in_act [n,256] -> save[j] = activations of layer j [n,256] (j < n_layers), out_z / out_s [n], masks.  in_is_preact: in_act holds the
+// pre-activation sums of the layer in front (no bias yet); the kernel's loader adds the bias, applies LeakyReLU and writes the rows back
+int b200_catchain_fwd(const void* img_fwd, const float* aux, int n_layers, float* in_act, bool in_is_preact, int n_rows, float near_,
+                      float far_, float* const* save, unsigned long long* mask, float* out_z, float* out_s, cudaStream_t st);
 // J_last [n,256] = d z / d(pre-activation of the last layer); save[t] = J of layer n_layers - 1 - t's input side, t = 0 .. n_layers - 1
 int b200_catchain_jac(const void* img_jac, const float* aux, int n_layers, const float* s, int n_rows, float near_, float far_,
                       float* j_last, float* const* save, const unsigned long long* mask, cudaStream_t st);

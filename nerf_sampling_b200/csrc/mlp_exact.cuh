@@ -96,7 +96,9 @@ struct ExactParams {
   unsigned long long* mask;   // IN_NERF_MASK writes / IN_NERF_TAN reads: [step][row][4] words, bit c = output column 64 g + c is > 0
                               // IN_ACT writes [layer 0 .. n_steps][row][4] (layer 0 = the input rows), IN_JAC reads them
   float* save[MAX_STEPS];     // IN_ACT / IN_JAC: fp32 copy of step s's output rows [rows, 256] (null: not saved)
-  const float* in_act;        // IN_ACT: input rows [rows, 256] fp32
+  float* in_act;              // IN_ACT: input rows [rows, 256] fp32
+  int in_bias_off;            // IN_ACT, >= 0: the rows are PRE-activations (split-K sums of the layer in front): the loader adds
+                              // aux[in_bias_off + c], applies LeakyReLU and writes the activated rows back for the backward
   const float* sgm;           // IN_JAC: s = sigmoid(head) per row (the head's derivative)
   float* out2;                // IN_ACT: s per row;  IN_JAC: the loader's own rows, J of the last layer's pre-activation [rows, 256]
   float mask_slope;           // ACT_MASK: factor of the columns whose bit is clear (0: ReLU, 0.01: LeakyReLU)
@@ -514,9 +516,14 @@ __global__ void __launch_bounds__(THREADS, 1) mlp_exact_kernel(const __grid_cons
               float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
               if (valid) {
                 if (INPUT == IN_ACT) {
-                  const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.in_act + static_cast<size_t>(lrow) * 256 + c));
-                  const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.in_act + static_cast<size_t>(lrow) * 256 + c + 4));
+                  float* src = p.in_act + static_cast<size_t>(lrow) * 256 + c;
+                  const float4 q0 = *reinterpret_cast<const float4*>(src), q1 = *reinterpret_cast<const float4*>(src + 4);
                   v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+                  if (p.in_bias_off >= 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = act_apply<ACT_LEAKY>(v[i] + saux[p.in_bias_off + c + i]);
+                    st_global_v8(src, v);
+                  }
                   uint32_t m8 = 0;
 #pragma unroll
                   for (int i = 0; i < 8; ++i) m8 |= (v[i] > 0.f ? 1u : 0u) << i;

@@ -126,6 +126,7 @@ struct GemmProb {
   int ld_dact = 0;
   const float* kscale = nullptr; // A(m,k) *= kscale[k]: the per-ray factor dz_r of a weight gradient built from a unit-upstream Jacobian
   bool c_zeroed = false;         // C is known to be zero: a split-K launch needs no memset
+  int force_splits = 0;          // > 0: this many K slices, partial sums added atomically (no bias / activation then)
   void add(const float* A, long sAm, long sAk, const float* B, long sBk, long sBn, int K) {
     seg[nseg++] = GemmSeg{A, sAm, sAk, B, sBk, sBn, K};
   }
@@ -196,7 +197,10 @@ static int tgemm_group(cudaStream_t st, const GemmProb* probs, int nprob) {
     P.tiles_y = (q.M + tg::BM - 1) / tg::BM;
     int splits = 1;
     const int K0 = q.seg[0].K;
-    if (q.nseg == 1 && !q.act && !q.dact && K0 >= 512) {
+    if (q.force_splits > 0) {
+      if (q.nseg != 1 || q.act || q.dact || q.bias) return b200_fail("tgemm_group: force_splits needs one K segment and a plain epilogue");
+      splits = q.force_splits;
+    } else if (q.nseg == 1 && !q.act && !q.dact && K0 >= 512) {
       // a long reduction into a small output: ~8 chunks per CTA like the CTAs of the other problems of the group -- a CTA that walks
       // the whole reduction would be the launch's tail.  (Measured for the split backward's group of 16 weight gradients, 136 tiles
       // of 128 chunks: ONE wave of unsplit CTAs with plain stores is no faster than 2,176 CTAs of 8 chunks with atomics, 1.651 vs
@@ -1008,15 +1012,35 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
       if (tgemm_group(st, q, 3)) return 1;
     }
     const int hl = ar.h[ar.nb - 1];
+    const bool fused = fused_chain_ok(ar, n, params);
     {
       const float* W = params[pidx_cat(ar, 0)];
       const int ldw = 3 * hl + 252;
-      GemmProb q = prob_fwd(n, ar.c[0], ws + w.a[0], ar.c[0], params[pidx_cat(ar, 0) + 1], 1, 0.01f);
-      for (int b = 0; b < 3; ++b) seg_fwd(q, ws + w.xb[b][ar.nb - 1], hl, W, ldw, b * hl, hl);
-      seg_fwd(q, E, 252, W, ldw, 3 * hl, 252);
-      if (tgemm_group(st, &q, 1)) return 1;
+      if (fused) {
+        // cat_layers.0 as FOUR split-K problems (one per K segment, two K slices each) that add into the zeroed output: K = 1020 in
+        // one CTA is 32 chunks and, at 512 rays, the longest launch in front of the fused chain (58 us); the bias and the LeakyReLU
+        // move into the chain kernel's loader, which reads these rows anyway and writes the activated rows back for the backward
+        CUDA_TRY(cudaMemsetAsync(ws + w.a[0], 0, static_cast<size_t>(n) * ar.c[0] * sizeof(float), st));
+        GemmProb q[4];
+        for (int b = 0; b < 3; ++b) {
+          q[b] = prob_fwd(n, ar.c[0], ws + w.a[0], ar.c[0], nullptr, 0, 0.f);
+          seg_fwd(q[b], ws + w.xb[b][ar.nb - 1], hl, W, ldw, b * hl, hl);
+        }
+        q[3] = prob_fwd(n, ar.c[0], ws + w.a[0], ar.c[0], nullptr, 0, 0.f);
+        seg_fwd(q[3], E, 252, W, ldw, 3 * hl, 252);
+        for (int i = 0; i < 4; ++i) {
+          q[i].force_splits = 2;
+          q[i].c_zeroed = true;
+        }
+        if (tgemm_group(st, q, 4)) return 1;
+      } else {
+        GemmProb q = prob_fwd(n, ar.c[0], ws + w.a[0], ar.c[0], params[pidx_cat(ar, 0) + 1], 1, 0.01f);
+        for (int b = 0; b < 3; ++b) seg_fwd(q, ws + w.xb[b][ar.nb - 1], hl, W, ldw, b * hl, hl);
+        seg_fwd(q, E, 252, W, ldw, 3 * hl, 252);
+        if (tgemm_group(st, &q, 1)) return 1;
+      }
     }
-    if (fused_chain_ok(ar, n, params)) {
+    if (fused) {
       // cat_layers.1 .. nc-1 + head in one launch: this step's weights -> bf16 hi / lo images (W_j for this pass, W_j^T for the
       // Jacobian pass), then the chain with every layer's activations saved for the backward
       const int nl = ar.nc - 1;
@@ -1028,8 +1052,10 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
         bl[j - 1] = params[pidx_cat(ar, j) + 1];
         save[j - 1] = ws + w.a[j];
       }
-      if (b200_catchain_pack(Wl, bl, params[pidx_head(ar)], params[pidx_head(ar) + 1], nl, ws + w.img_fwd, ws + w.img_jac, ws + w.aux, st)) return 1;
-      return b200_catchain_fwd(ws + w.img_fwd, ws + w.aux, nl, ws + w.a[0], n, near_, far_, save,
+      if (b200_catchain_pack(Wl, bl, params[pidx_head(ar)], params[pidx_head(ar) + 1], params[pidx_cat(ar, 0) + 1], nl, ws + w.img_fwd,
+                             ws + w.img_jac, ws + w.aux, st))
+        return 1;
+      return b200_catchain_fwd(ws + w.img_fwd, ws + w.aux, nl, ws + w.a[0], true, n, near_, far_, save,
                                reinterpret_cast<unsigned long long*>(ws + w.mask), out_z, ws + w.s, st);
     }
     for (int j = 1; j < ar.nc; ++j) {
