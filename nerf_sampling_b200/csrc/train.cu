@@ -892,6 +892,7 @@ static bool can_collapse(const DnArch& ar, int n, const float* const* params) {
 static bool fused_chain_ok(const DnArch& ar, int n, const float* const* params) {
   const char* e = getenv("B200NERF_TRAIN_CHAIN");   // read per call: the tests run both routes in one process
   if ((e && strcmp(e, "gemm") == 0) || !can_collapse(ar, n, params) || ar.nc < 2 || ar.nc - 1 > B200_CATCHAIN_MAX_LAYERS) return false;
+  if (256 * static_cast<size_t>(ar.nc - 1 + 3) > b200_catchain_aux_floats()) return false;   // biases + head + cat_layers.0's bias in the kernel's aux block
   for (int c : ar.c)
     if (c != 256) return false;
   for (int j = 0; j < ar.nc; ++j)

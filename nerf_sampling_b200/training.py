@@ -184,11 +184,13 @@ def _side_stream(dev, which=0):
 
 
 def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, target_s):
-    """The DepthNet training render and both backward passes of ``Trainer.core_optimization_loop`` (Trainer.py:515-538) as six
-    C calls and no autograd graph: hierarchical arg-max target on the frozen NeRFs (tensor-core kernels), DepthNet forward with
-    saved activations, frozen fine NeRF at one sample per ray with its forward-mode d raw / d z, both losses and the gradient
-    they send into z in one kernel (``b200nerf_train_loss``), DepthNet backward into ONE flat gradient buffer whose address
-    never changes (so the optimizer's pointer table and ``parallel.allreduce_gradients`` see the same tensors every step).
+    """The DepthNet training render and both backward passes of ``Trainer.core_optimization_loop`` (Trainer.py:515-538) as a
+    handful of C calls on three streams and no autograd graph: hierarchical arg-max target on the frozen NeRFs (tensor-core
+    kernels; main stream), DepthNet forward with saved activations and the frozen fine NeRF at one sample per ray with its
+    forward-mode d raw / d z (side stream), the backward's input-gradient chain with a unit upstream gradient (third stream:
+    it needs neither the losses nor the colour path), then -- after the join -- both losses and the gradient they send into z in
+    one kernel (``b200nerf_train_loss``) and DepthNet's weight gradients into ONE flat gradient buffer whose address never
+    changes (so the optimizer's pointer table and ``parallel.allreduce_gradients`` see the same tensors every step).
 
     Returns ``(loss, depth_net_loss, psnr)`` as 0-dim tensors, or ``None`` when the configuration is not the standard one
     (foreign DepthNet / NeRF modules, optimizer over other parameters): the caller then takes the autograd route, which
