@@ -1014,10 +1014,13 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
     }
     const int hl = ar.h[ar.nb - 1];
     const bool fused = fused_chain_ok(ar, n, params);
+    // the split form of cat_layers.0 pays where the step is a latency chain (512 rays: 58 -> 26 us, step 0.60 -> 0.56 ms); at 4096
+    // rays its extra CTAs, atomics and memset cost SM time beside the target render (1.365 -> 1.41 ms)
+    const bool split0 = fused && n <= 2048;
     {
       const float* W = params[pidx_cat(ar, 0)];
       const int ldw = 3 * hl + 252;
-      if (fused) {
+      if (split0) {
         // cat_layers.0 as FOUR split-K problems (one per K segment, two K slices each) that add into the zeroed output: K = 1020 in
         // one CTA is 32 chunks and, at 512 rays, the longest launch in front of the fused chain (58 us); the bias and the LeakyReLU
         // move into the chain kernel's loader, which reads these rows anyway and writes the activated rows back for the backward
@@ -1053,10 +1056,10 @@ extern "C" int b200nerf_depthnet_train_fwd(const float* const* params, int n_bra
         bl[j - 1] = params[pidx_cat(ar, j) + 1];
         save[j - 1] = ws + w.a[j];
       }
-      if (b200_catchain_pack(Wl, bl, params[pidx_head(ar)], params[pidx_head(ar) + 1], params[pidx_cat(ar, 0) + 1], nl, ws + w.img_fwd,
-                             ws + w.img_jac, ws + w.aux, st))
+      if (b200_catchain_pack(Wl, bl, params[pidx_head(ar)], params[pidx_head(ar) + 1], split0 ? params[pidx_cat(ar, 0) + 1] : nullptr, nl,
+                             ws + w.img_fwd, ws + w.img_jac, ws + w.aux, st))
         return 1;
-      return b200_catchain_fwd(ws + w.img_fwd, ws + w.aux, nl, ws + w.a[0], true, n, near_, far_, save,
+      return b200_catchain_fwd(ws + w.img_fwd, ws + w.aux, nl, ws + w.a[0], split0, n, near_, far_, save,
                                reinterpret_cast<unsigned long long*>(ws + w.mask), out_z, ws + w.s, st);
     }
     for (int j = 1; j < ar.nc; ++j) {
