@@ -1725,19 +1725,39 @@ extern "C" int b200nerf_adam_step_multi(const void* d_table, int n_tensors, floa
 // CUDA-graph friendly variant: the step counter lives on the device and the hyper-parameters are read from device memory
 // (d_hyper = {lr, beta1, beta2, eps, grad_scale}), so a captured launch stays valid while lr / step change.
 __global__ void adam_tick_kernel(int* step) { *step += 1; }
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float lr_bc1, float b1, float b2, float eps,
+                                            float bc2_sqrt, float gscale) {
+  const float gi = g * gscale;
+  const float mi = b1 * m + (1.f - b1) * gi;
+  const float vi = b2 * v + (1.f - b2) * gi * gi;
+  m = mi;
+  v = vi;
+  p -= lr_bc1 * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+}
+// 16-byte accesses where the four arrays of a tensor allow it (they do for every DepthNet tensor: 13.4 MB of parameters, 94 MB of
+// traffic per step), scalar tail / scalar path otherwise
 __global__ void adam_multi_dev_kernel(const AdamEntry* __restrict__ table, const float* __restrict__ hyper, const int* __restrict__ step) {
   const AdamEntry e = table[blockIdx.y];
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], gscale = hyper[4];
   const float t = static_cast<float>(*step);
   const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < e.n; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float gi = e.g[i] * gscale;
-    const float mi = b1 * e.m[i] + (1.f - b1) * gi;
-    const float vi = b2 * e.v[i] + (1.f - b2) * gi * gi;
-    e.m[i] = mi;
-    e.v[i] = vi;
-    e.p[i] -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  const float lr_bc1 = lr / bc1;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x, nthr = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(e.p) | reinterpret_cast<uintptr_t>(e.g) | reinterpret_cast<uintptr_t>(e.m) |
+                     reinterpret_cast<uintptr_t>(e.v)) & 15) == 0;
+  const size_t n4 = vec ? e.n / 4 : 0;
+  for (size_t i = tid; i < n4; i += nthr) {
+    float4 p4 = reinterpret_cast<float4*>(e.p)[i], m4 = reinterpret_cast<float4*>(e.m)[i], v4 = reinterpret_cast<float4*>(e.v)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(e.g)[i];
+    adam_update(p4.x, g4.x, m4.x, v4.x, lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
+    adam_update(p4.y, g4.y, m4.y, v4.y, lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
+    adam_update(p4.z, g4.z, m4.z, v4.z, lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
+    adam_update(p4.w, g4.w, m4.w, v4.w, lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
+    reinterpret_cast<float4*>(e.p)[i] = p4;
+    reinterpret_cast<float4*>(e.m)[i] = m4;
+    reinterpret_cast<float4*>(e.v)[i] = v4;
   }
+  for (size_t i = n4 * 4 + tid; i < e.n; i += nthr) adam_update(e.p[i], e.g[i], e.m[i], e.v[i], lr_bc1, b1, b2, eps, bc2_sqrt, gscale);
 }
 extern "C" int b200nerf_adam_step_multi_dev(const void* d_table, int n_tensors, const float* d_hyper, int* d_step, void* stream) {
   if (n_tensors <= 0) return 0;
