@@ -242,6 +242,7 @@ int b200nerf_depthnet_train_bwd(const float* const* params, int n_branch, const 
  * b200nerf_depthnet_train_bwd_jac then forms every gradient from dz and the J_j as independent products (one grouped launch) plus
  * the weight-only branch chain.  Same results as b200nerf_depthnet_train_bwd up to rounding; where the split does not apply
  * (CUDA-core GEMM path, literal branches, fewer than 32 rays) _jac does nothing and _bwd_jac IS b200nerf_depthnet_train_bwd.
+ * One _bwd_jac per _jac: the gradients and the branches' ray reduction are accumulated into what _jac zeroed.
  * stream_aux (optional, another stream of the same device): the weight-only branch chain runs there beside the cat layers' weight
  * gradients; `stream` waits for it before the call's work is complete (event fork / join, capturable in a CUDA graph). */
 int b200nerf_depthnet_train_jac(const float* const* params, int n_branch, const int* hidden, int n_cat, const int* cat_hidden,

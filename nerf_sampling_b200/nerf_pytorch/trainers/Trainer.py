@@ -200,7 +200,7 @@ class Trainer:
         from ... import training
 
         fused = training.fused_render_and_backward(self, sampling_optimizer, render_kwargs_train, batch_rays, target_s)
-        if fused is not None:   # the standard configuration: six C calls, no autograd graph
+        if fused is not None:   # the standard configuration: a handful of C calls on three streams, no autograd graph
             return fused[0], fused[1], fused[2], None
         depth_net_rgb, depth_net_disp, extras = nerf_utils.render(self.H, self.W, self.K, chunk=self.chunk, rays=batch_rays,
                                                                   verbose=i < 10, retraw=True, **render_kwargs_train)

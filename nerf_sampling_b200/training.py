@@ -163,7 +163,8 @@ def nerf_params(module) -> List[torch.nn.Parameter]:
 
 
 # Persistent-grid cap (in SMs) of the frozen target render while the DepthNet / JVP chain of the same step runs on a side stream;
-# 0 runs the step on one stream.  B200NERF_TARGET_SMS overrides (measurement).
+# 0 runs the step on one stream; 148 = every SM of a B200, i.e. no cap but still two streams (the best setting since the side chain
+# is four fused-kernel launches; it was 128 while the chain was ~25 grouped GEMMs).  B200NERF_TARGET_SMS overrides (measurement).
 TARGET_SM_LIMIT = int(__import__("os").environ.get("B200NERF_TARGET_SMS", "148"))
 # The backward split at the losses (b200nerf_depthnet_train_jac / _bwd_jac): the sequential input-gradient chain runs with a unit
 # upstream gradient in front of the losses -- on a third stream beside d raw / d z (THIRD_STREAM) -- and the weight-only branch
@@ -233,8 +234,8 @@ def fused_render_and_backward(trainer, optimizer, render_kwargs, batch_rays, tar
         nf = (float(dn.near), float(dn.far))
         main = torch.cuda.current_stream()
         # Two independent halves until the losses: the frozen hierarchical target (throughput-bound persistent kernels) and the
-        # DepthNet forward + NeRF point JVP (a ~25-launch latency-bound chain).  The chain runs on a side stream beside the target,
-        # whose persistent grids are capped so that it finds free SMs (TARGET_SM_LIMIT; 0 = one stream, no cap).
+        # DepthNet forward + NeRF point JVP (a latency-bound chain of ~10 launches).  The chain runs on a side stream beside the
+        # target, whose persistent grids can be capped so that it finds free SMs (TARGET_SM_LIMIT; 0 = one stream).
         side = _side_stream(dev) if TARGET_SM_LIMIT > 0 else None
         # every buffer is allocated on the main stream (the side stream only runs kernels between the two wait_stream calls), so the
         # caching allocator never sees a cross-stream hand-off

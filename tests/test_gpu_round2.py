@@ -218,7 +218,7 @@ def test_training_step_4096_rays_all_gradients_vs_autograd(lib, oracle_models):
 
 
 def test_fused_training_step_equals_autograd_route(lib, oracle_models):
-    """training.fused_render_and_backward (six C calls, no autograd graph) against the autograd route through
+    """training.fused_render_and_backward (C calls on three streams, split backward, no autograd graph) against the autograd route through
     DepthNetTrainFn / NerfPointFn / CompositeSingleFn on the same batch: same losses, same 82 gradients."""
     from nerf_sampling_b200 import training
     from nerf_sampling_b200.nerf_pytorch import nerf_utils
