@@ -307,6 +307,14 @@ int b200nerf_debug_sgemm(int M, int N, int K, const float* A, long sAm, long sAk
  * [0] entry, [1] barriers + TMEM ready, [2] last MMA retired, [3] epilogue stored, [4+c] chunk c handed to the MMA warp. */
 void b200nerf_debug_set_tgemm_timeline(long long* dev_buf);
 
+/* Diagnostics: the per-step device-side re-pack of DepthNet's 256 x 256 cat layers for the fused training chain (bf16 hi / lo
+ * images of W_j for the forward launch and of W_{n-1-j}^T for the Jacobian launch, fp32 bias / head block), exposed so that a
+ * test can compare it byte for byte with the host packer of the inference path.  d_W / d_b: host arrays of n_layers DEVICE
+ * pointers ([256,256] / [256]); images: b200nerf_debug_catchain_img_bytes() bytes each; d_aux: b200nerf_nerf_aux_floats() floats. */
+size_t b200nerf_debug_catchain_img_bytes(int n_layers);
+int b200nerf_debug_catchain_pack(const float* const* d_W, const float* const* d_b, const float* d_head_w, const float* d_head_b,
+                                 int n_layers, void* d_img_fwd, void* d_img_jac, float* d_aux, void* stream);
+
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 unsigned long long b200nerf_launch_count(void);
 

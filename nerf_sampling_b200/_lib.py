@@ -66,6 +66,8 @@ SIGNATURES = {
     "b200nerf_nerf_point_jvp": (I, [P, P, P, P, P, I, P, P, P, P]),
     "b200nerf_nerf_point_jvp_packed_ws_bytes": (SZ, [I]),
     "b200nerf_nerf_point_jvp_packed": (I, [P, P, P, P, P, P, I, P, P, P, P]),
+    "b200nerf_debug_catchain_img_bytes": (SZ, [I]),
+    "b200nerf_debug_catchain_pack": (I, [P, P, P, P, I, P, P, P, P]),
     "b200nerf_train_loss": (I, [P, P, P, P, P, I, P, P, P, P]),
     "b200nerf_adam_step": (I, [P, P, P, P, SZ, F, F, F, F, I, F, P]),
     "b200nerf_adam_step_multi": (I, [P, I, F, F, F, F, I, F, P]),

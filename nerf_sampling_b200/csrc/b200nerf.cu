@@ -1146,6 +1146,15 @@ int b200_catchain_pack(const float* const* W, const float* const* b, const float
   LAUNCH_CHECK();
   return 0;
 }
+/* diagnostics: the device-side re-pack alone, so that a test can compare it byte for byte with the host packer of the inference
+   path (b200nerf_depthnet_pack over the same matrices produces the same program: n_layers steps of 256 x 256) */
+extern "C" int b200nerf_debug_catchain_pack(const float* const* d_W, const float* const* d_b, const float* d_head_w, const float* d_head_b,
+                                            int n_layers, void* d_img_fwd, void* d_img_jac, float* d_aux, void* stream) {
+  if (!d_W || !d_b || !d_head_w || !d_head_b || !d_img_fwd || !d_img_jac || !d_aux) return fail("b200nerf_debug_catchain_pack: null argument");
+  return b200_catchain_pack(d_W, d_b, d_head_w, d_head_b, nullptr, n_layers, d_img_fwd, d_img_jac, d_aux, static_cast<cudaStream_t>(stream));
+}
+extern "C" size_t b200nerf_debug_catchain_img_bytes(int n_layers) { return b200_catchain_img_bytes(n_layers); }
+
 static void catchain_params(exact::ExactParams& xp, const float* aux, int n_layers, int n_rows, float near_, float far_) {
   memset(&xp, 0, sizeof(xp));
   xp.aux = aux;

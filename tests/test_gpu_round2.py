@@ -298,6 +298,53 @@ def test_split_backward_equals_one_pass_backward(lib, oracle_models, n):
     assert worst <= 1e-4
 
 
+def test_device_repack_equals_host_packer(lib):
+    """The per-step device-side re-pack of the fused training chain (catchain_pack_kernel: bf16 hi / lo weight images in the stream
+    order of mlp_exact_kernel, fp32 bias / head block) against the host packer of the inference path on the same matrices: byte
+    for byte, for the forward image (W_j) and for the Jacobian image (W_{n-1-j}^T)."""
+    import ctypes as C
+
+    from nerf_sampling_b200 import _lib
+    from nerf_sampling_b200.packing import PREC_SPLIT
+
+    L = _lib.lib()
+    nl = 9
+    g = torch.Generator().manual_seed(11)
+    W = [(torch.randn(256, 256, generator=g) * (0.05 + 0.01 * j)).contiguous() for j in range(nl)]
+    b = [torch.randn(256, generator=g).contiguous() for _ in range(nl)]
+    hw, hb = torch.randn(256, generator=g).contiguous(), torch.randn(1, generator=g).contiguous()
+    W[3][5, 7] = 0.0
+    W[3][6, 7] = 1e-30          # a value whose lo part underflows
+    nbytes = L.b200nerf_depthnet_wpack_bytes(nl - 1, PREC_SPLIT)
+    assert nbytes == L.b200nerf_debug_catchain_img_bytes(nl)
+
+    def host_pack(mats):
+        wp = torch.empty(nbytes, dtype=torch.uint8)
+        aux = torch.empty(L.b200nerf_depthnet_aux_floats(nl - 1), dtype=torch.float32)
+        hid = [t for j in range(1, nl) for t in (mats[j], b[j])]
+        arr = (C.c_void_p * len(hid))(*[t.data_ptr() for t in hid])
+        _lib.check(L.b200nerf_depthnet_pack(mats[0].data_ptr(), b[0].data_ptr(), C.cast(arr, C.c_void_p), nl - 1, hw.data_ptr(), hb.data_ptr(),
+                                            PREC_SPLIT, wp.data_ptr(), aux.data_ptr()))
+        return wp, aux
+
+    want_fwd, want_aux = host_pack(W)
+    want_jac, _ = host_pack([W[nl - 1 - j].t().contiguous() for j in range(nl)])
+    dW, db = [w.to(DEV) for w in W], [x.to(DEV) for x in b]
+    dhw, dhb = hw.to(DEV), hb.to(DEV)
+    img_f = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+    img_j = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+    aux = torch.full((L.b200nerf_nerf_aux_floats(),), float("nan"), device=DEV)
+    pw = (C.c_void_p * nl)(*[t.data_ptr() for t in dW])
+    pb = (C.c_void_p * nl)(*[t.data_ptr() for t in db])
+    _lib.check(L.b200nerf_debug_catchain_pack(pw, pb, dhw.data_ptr(), dhb.data_ptr(), nl, img_f.data_ptr(), img_j.data_ptr(), aux.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(img_f.cpu(), want_fwd)
+    assert torch.equal(img_j.cpu(), want_jac)
+    k = 256 * (nl + 1) + 1      # biases, head weights, head bias
+    assert torch.equal(aux[:k].cpu(), want_aux[:k]) and bool((aux[k:] == 0).all())
+
+
 # ------------------------------------------------------------------------------------------- render.py flags and the -e sweep
 @pytest.mark.parametrize("mode,S,dist", [("uniform", 2, 0.3), ("uniform", 128, 1.0), ("gaussian", 32, 0.3), ("gaussian", 64, 0.5),
                                          ("gaussian", 2, 1.0), ("uniform", 32, 0.5), ("gaussian", 128, 0.1)])
